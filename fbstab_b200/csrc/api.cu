@@ -1,0 +1,946 @@
+// api.cu -- C-ABI of the batched engine (include/fbstab_b200.h): handles,
+// host<->device staging, kernel selection and launches.
+//
+// Kernels here are persistent: a fixed grid of CTAs pulls instance indices
+// from a global atomic counter, so instances that converge early simply free
+// their CTA for the next instance -- no host round trips, no per-iteration
+// launches, natural load balance over the 9..28-iteration spread.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dense_problem.cuh"
+#include "dense_small.cuh"
+#include "engine.cuh"
+#include "fbstab_b200.h"
+#include "mpc_problem.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int Fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e_ = (expr);                                                  \
+    if (e_ != cudaSuccess)                                                    \
+      return Fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver \
+                      ? FBSTAB_ERR_NOGPU                                      \
+                      : FBSTAB_ERR_CUDA,                                      \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+int EnvInt(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+bool IsDevicePtr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Lazily grown device staging buffer for one host-side argument.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int Ensure(size_t bytes) {
+    if (bytes <= cap) return FBSTAB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return Fail(FBSTAB_ERR_ALLOC, "cudaMalloc of a staging buffer failed");
+    }
+    cap = bytes;
+    return FBSTAB_OK;
+  }
+  void Free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PendingCopy {
+  void* host;
+  const void* dev;
+  size_t bytes;
+};
+
+// Resolves user pointers to device pointers, staging host memory.
+struct Stager {
+  cudaStream_t stream;
+  bool any_host = false;
+  std::vector<PendingCopy> d2h;
+  int In(DevBuf* buf, const void* user, size_t bytes, const void** out) {
+    if (bytes == 0) {
+      *out = nullptr;
+      return FBSTAB_OK;
+    }
+    if (!user) return Fail(FBSTAB_ERR_INVALID, "null input pointer");
+    if (IsDevicePtr(user)) {
+      *out = user;
+      return FBSTAB_OK;
+    }
+    any_host = true;
+    int rc = buf->Ensure(bytes);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(buf->p, user, bytes, cudaMemcpyHostToDevice, stream));
+    *out = buf->p;
+    return FBSTAB_OK;
+  }
+  // in/out or out-only buffer; copy_in = stage the current host contents
+  int InOut(DevBuf* buf, void* user, size_t bytes, bool copy_in, void** out) {
+    if (bytes == 0) {
+      *out = nullptr;
+      return FBSTAB_OK;
+    }
+    if (!user) return Fail(FBSTAB_ERR_INVALID, "null output pointer");
+    if (IsDevicePtr(user)) {
+      *out = user;
+      return FBSTAB_OK;
+    }
+    any_host = true;
+    int rc = buf->Ensure(bytes);
+    if (rc) return rc;
+    if (copy_in)
+      CUDA_TRY(cudaMemcpyAsync(buf->p, user, bytes, cudaMemcpyHostToDevice, stream));
+    d2h.push_back({user, buf->p, bytes});
+    *out = buf->p;
+    return FBSTAB_OK;
+  }
+  int Finish() {
+    for (auto& c : d2h)
+      CUDA_TRY(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, stream));
+    if (any_host) CUDA_TRY(cudaStreamSynchronize(stream));
+    return FBSTAB_OK;
+  }
+};
+
+// ---- options (fbstab_algorithm-impl.h:7-74) --------------------------------
+bool Sat(double* x, double a, double b) {
+  if (a > b) return false;
+  *x = std::max(std::min(*x, b), a);
+  return true;
+}
+
+// ---- kernel argument blocks ------------------------------------------------
+struct CommonArgs {
+  int batch;
+  double *z, *l, *v, *y;
+  fbstab_out* out;
+  double* ws;        // per-CTA workspace base
+  size_t ws_stride;  // doubles per CTA
+  int* counter;
+  int vec_in_smem;
+  fbstab_options opts;
+  // component mode
+  int comp;
+  fbstab_component_io io;
+};
+
+struct DenseArgs {
+  int nz, nl, nv;
+  const double *H, *f, *G, *h, *A, *b;
+  CommonArgs c;
+};
+
+struct MpcArgs {
+  int N, nx, nu, nc;
+  const double *Q, *R, *S, *q, *r, *A, *B, *cc, *E, *L, *d, *x0;
+  CommonArgs c;
+};
+
+__host__ __device__ inline size_t VecDoubles(int nz, int nl, int nv) {
+  return 4 * (size_t)(nz + nl + 2 * nv) + (size_t)(nz + nl + nv);
+}
+
+__device__ inline double* Carve(double*& p, size_t n) {
+  double* r = p;
+  p += n;
+  return r;
+}
+
+__device__ inline void CarveBuffers(double*& p, int nz, int nl, int nv,
+                                    fbs::Buffers* w) {
+  fbs::Vars* vs[4] = {&w->xk, &w->xi, &w->xp, &w->dx};
+  for (int k = 0; k < 4; k++) {
+    vs[k]->z = Carve(p, nz);
+    vs[k]->l = Carve(p, nl);
+    vs[k]->v = Carve(p, nv);
+    vs[k]->y = Carve(p, nv);
+  }
+  w->ri.z = Carve(p, nz);
+  w->ri.l = Carve(p, nl);
+  w->ri.v = Carve(p, nv);
+}
+
+__device__ inline void SetupDense(const DenseArgs& a, int inst, double*& ws,
+                                  fbs::DenseProblem* p) {
+  p->nz = a.nz;
+  p->nl = a.nl;
+  p->nv = a.nv;
+  p->n = a.nz + a.nl;
+  p->H = a.H + (size_t)inst * a.nz * a.nz;
+  p->f = a.f + (size_t)inst * a.nz;
+  p->G = a.G + (size_t)inst * a.nl * a.nz;
+  p->h = a.h + (size_t)inst * a.nl;
+  p->A = a.A + (size_t)inst * a.nv * a.nz;
+  p->bvec = a.b + (size_t)inst * a.nv;
+  p->K = Carve(ws, (size_t)p->n * p->n);
+  p->r1 = Carve(ws, p->n);
+  p->r2 = Carve(ws, a.nv);
+  p->gamma = Carve(ws, a.nv);
+  p->mus = Carve(ws, a.nv);
+  p->tmp = Carve(ws, p->n);
+  p->tz = Carve(ws, a.nz);
+}
+size_t DenseWsDoubles(int nz, int nl, int nv) {
+  const size_t n = nz + nl;
+  return n * n + 2 * n + 3 * (size_t)nv + nz;
+}
+
+__device__ inline void SetupMpc(const MpcArgs& a, int inst, double*& ws,
+                                fbs::MpcProblem* p) {
+  const int N = a.N, nx = a.nx, nu = a.nu, nc = a.nc;
+  const size_t K = N + 1;
+  p->N = N;
+  p->nx = nx;
+  p->nu = nu;
+  p->nc = nc;
+  p->nz = (int)(K * (nx + nu));
+  p->nl = (int)(K * nx);
+  p->nv = (int)(K * nc);
+  p->Q = a.Q + inst * K * nx * nx;
+  p->R = a.R + inst * K * nu * nu;
+  p->S = a.S + inst * K * nu * nx;
+  p->q = a.q + inst * K * nx;
+  p->r = a.r + inst * K * nu;
+  p->A = a.A + (size_t)inst * N * nx * nx;
+  p->B = a.B + (size_t)inst * N * nx * nu;
+  p->c = a.cc + (size_t)inst * N * nx;
+  p->E = a.E + inst * K * nc * nx;
+  p->L = a.L + inst * K * nc * nu;
+  p->d = a.d + inst * K * nc;
+  p->x0 = a.x0 + (size_t)inst * nx;
+  p->gamma = Carve(ws, p->nv);
+  p->mus = Carve(ws, p->nv);
+  p->Gam = Carve(ws, p->nv);
+  p->tv = Carve(ws, p->nv);
+  p->Ls = Carve(ws, K * nx * nx);
+  p->Ms = Carve(ws, K * nx * nx);
+  p->AMs = Carve(ws, K * nx * nx);
+  p->SMs = Carve(ws, K * nu * nx);
+  p->SGs = Carve(ws, K * nu * nu);
+  p->Ps = Carve(ws, K * nu * nx);
+  p->Qt = Carve(ws, nx * nx);
+  p->Rt = Carve(ws, nu * nu);
+  p->St = Carve(ws, nu * nx);
+  p->Linv = Carve(ws, nx * nx);
+  p->r1 = Carve(ws, p->nz);
+  p->r2 = Carve(ws, p->nl);
+  p->hs = Carve(ws, p->nl);
+  p->ths = Carve(ws, p->nl);
+  p->txs = Carve(ws, p->nl);
+  p->tus = Carve(ws, K * nu);
+  const int m = nx > nu ? nx : nu;
+  p->sa = Carve(ws, m);
+  p->sb = Carve(ws, m);
+  p->sc = Carve(ws, m);
+  p->tzs = Carve(ws, p->nz);
+}
+size_t MpcWsDoubles(int N, int nx, int nu, int nc) {
+  const size_t K = N + 1;
+  const size_t nz = K * (nx + nu), nl = K * nx, nv = K * nc;
+  const size_t m = nx > nu ? nx : nu;
+  return 4 * nv + 3 * K * nx * nx + 2 * K * nu * nx + K * nu * nu +
+         2 * (size_t)nx * nx + (size_t)nu * nu + (size_t)nu * nx + 2 * nz +
+         4 * nl + K * nu + 3 * m;
+}
+
+// One component stage on caller-supplied iterates (per-kernel parity tests).
+template <class P>
+__device__ void RunComponent(const fbs::Team& t, P& p, const CommonArgs& c,
+                             int inst, fbs::Buffers& w) {
+  const fbstab_component_io& io = c.io;
+  const size_t oz = (size_t)inst * p.nz, ol = (size_t)inst * p.nl,
+               ov = (size_t)inst * p.nv;
+  const double alpha = c.opts.alpha;
+  if (c.comp == FBSTAB_COMP_MARGIN) {
+    p.margin(t, io.z + oz, io.dy + ov);
+    return;
+  }
+  // load x (and xbar) into the work buffers
+  for (int i = t.rank(); i < p.nz; i += t.size()) {
+    w.xi.z[i] = io.z[oz + i];
+    w.xk.z[i] = io.zbar ? io.zbar[oz + i] : io.z[oz + i];
+  }
+  for (int i = t.rank(); i < p.nl; i += t.size()) {
+    w.xi.l[i] = io.l[ol + i];
+    w.xk.l[i] = io.lbar ? io.lbar[ol + i] : io.l[ol + i];
+  }
+  for (int i = t.rank(); i < p.nv; i += t.size()) {
+    w.xi.v[i] = io.v[ov + i];
+    w.xk.v[i] = io.vbar ? io.vbar[ov + i] : io.v[ov + i];
+    w.xi.y[i] = io.y ? io.y[ov + i] : 0.0;
+  }
+  t.sync();
+  if (c.comp == FBSTAB_COMP_RESIDUAL) {
+    fbs::EvalOut e = fbs::evaluate(t, p, w.xi, w.xk, io.sigma, alpha, w.ri);
+    (void)e;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    // recompute component norms for reporting (evaluate() returns the totals)
+    for (int i = t.rank(); i < p.nz; i += t.size()) {
+      const double r = w.ri.z[i];
+      io.rz[oz + i] = r;
+      s[0] += r * r;
+      const double n = r - io.sigma * (w.xi.z[i] - w.xk.z[i]);
+      s[3] += n * n;
+    }
+    for (int i = t.rank(); i < p.nl; i += t.size()) {
+      const double r = w.ri.l[i];
+      io.rl[ol + i] = r;
+      s[1] += r * r;
+      const double n = r - io.sigma * (w.xi.l[i] - w.xk.l[i]);
+      s[4] += n * n;
+    }
+    for (int i = t.rank(); i < p.nv; i += t.size()) {
+      const double r = w.ri.v[i];
+      io.rv[ov + i] = r;
+      s[2] += r * r;
+      const double n = fbs::pnr(w.xi.y[i], w.xi.v[i], alpha);
+      s[5] += n * n;
+    }
+    fbs::team_sum(t, s);
+    if (t.rank() == 0 && io.norms) {
+      for (int k = 0; k < 6; k++) io.norms[(size_t)inst * 8 + k] = sqrt(s[k]);
+      io.norms[(size_t)inst * 8 + 6] = e.Ei;
+      io.norms[(size_t)inst * 8 + 7] = e.Eo;
+    }
+  } else if (c.comp == FBSTAB_COMP_NEWTON) {
+    const bool ok = p.factor(t, w.xi, w.xk, io.sigma, alpha);
+    // engine convention: solve() receives the residual and solves for -r; the
+    // component API takes the right-hand side r itself, so negate on load.
+    for (int i = t.rank(); i < p.nz; i += t.size()) w.ri.z[i] = -io.rz[oz + i];
+    for (int i = t.rank(); i < p.nl; i += t.size()) w.ri.l[i] = -io.rl[ol + i];
+    for (int i = t.rank(); i < p.nv; i += t.size()) w.ri.v[i] = -io.rv[ov + i];
+    t.sync();
+    p.solve(t, w.ri.z, w.ri.l, w.ri.v, w.dx);
+    for (int i = t.rank(); i < p.nz; i += t.size()) io.dz[oz + i] = w.dx.z[i];
+    for (int i = t.rank(); i < p.nl; i += t.size()) io.dl[ol + i] = w.dx.l[i];
+    for (int i = t.rank(); i < p.nv; i += t.size()) {
+      io.dv[ov + i] = w.dx.v[i];
+      io.dy[ov + i] = w.dx.y[i];
+      if (io.gamma) io.gamma[ov + i] = p.gamma[i];
+      if (io.mus) io.mus[ov + i] = p.mus[i];
+    }
+    if (t.rank() == 0 && io.status)
+      io.status[inst] = ok ? FBSTAB_STATUS_OK : FBSTAB_STATUS_FACTOR_FAILED;
+  } else if (c.comp == FBSTAB_COMP_FEAS) {
+    const int feas = p.feasibility(t, w.xi, io.tol);
+    if (t.rank() == 0 && io.status) io.status[inst] = feas;
+  }
+  t.sync();
+}
+
+template <class Args, class P, void (*Setup)(const Args&, int, double*&, P*)>
+__device__ void PersistentLoop(const Args& a, int nz, int nl, int nv) {
+  extern __shared__ double dyn_smem[];
+  __shared__ double red[fbs::kMaxWarps * fbs::kRedSlots];
+  __shared__ int s_inst;
+  fbs::Team t{red};
+  const CommonArgs& c = a.c;
+  double* ws0 = c.ws + (size_t)blockIdx.x * c.ws_stride;
+  for (;;) {
+    if (threadIdx.x == 0) s_inst = atomicAdd(c.counter, 1);
+    __syncthreads();
+    const int inst = s_inst;
+    __syncthreads();
+    if (inst >= c.batch) break;
+    double* ws = ws0;
+    double* vec = c.vec_in_smem ? dyn_smem : ws;
+    fbs::Buffers w;
+    CarveBuffers(vec, nz, nl, nv, &w);
+    if (!c.vec_in_smem) ws = vec;
+    P p;
+    Setup(a, inst, ws, &p);
+    if (c.comp < 0) {
+      fbs::solve_instance(t, p, c.opts, w, c.z + (size_t)inst * nz,
+                          c.l + (size_t)inst * nl, c.v + (size_t)inst * nv,
+                          c.y + (size_t)inst * nv, c.out + inst);
+    } else {
+      RunComponent(t, p, c, inst, w);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+dense_generic_kernel(const __grid_constant__ DenseArgs a) {
+  PersistentLoop<DenseArgs, fbs::DenseProblem, SetupDense>(a, a.nz, a.nl, a.nv);
+}
+
+__global__ void __launch_bounds__(64, 12)
+mpc_generic_kernel(const __grid_constant__ MpcArgs a) {
+  const int K = a.N + 1;
+  PersistentLoop<MpcArgs, fbs::MpcProblem, SetupMpc>(a, K * (a.nx + a.nu),
+                                                     K * a.nx, K * a.nc);
+}
+
+// ---- handles ----------------------------------------------------------------
+struct HandleBase {
+  int device = 0;
+  int max_batch = 0;
+  int nz = 0, nl = 0, nv = 0;
+  fbstab_options opts;
+  int sm_count = 0;
+  int block = 32;
+  int grid_max = 0;
+  size_t dyn_smem = 0;
+  int vec_in_smem = 0;
+  size_t ws_stride = 0;  // doubles
+  double* ws = nullptr;
+  int* counter = nullptr;
+  DevBuf out_buf;
+  DevBuf in[12];
+  DevBuf io[4];
+  DevBuf comp[18];
+  int last_launches = 0;
+  const char* path = "generic";
+
+  void FreeAll() {
+    cudaSetDevice(device);
+    if (ws) cudaFree(ws);
+    if (counter) cudaFree(counter);
+    out_buf.Free();
+    for (auto& b : in) b.Free();
+    for (auto& b : io) b.Free();
+    for (auto& b : comp) b.Free();
+  }
+};
+
+int InitCommon(HandleBase* h, int device, int max_batch, const void* kernel,
+               size_t ws_doubles_no_vec, int block) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return Fail(FBSTAB_ERR_NOGPU,
+                "no CUDA device available: the engine has no CPU path");
+  }
+  if (device < 0 || device >= ndev)
+    return Fail(FBSTAB_ERR_INVALID, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  h->device = device;
+  h->max_batch = max_batch;
+  fbstab_default_options(&h->opts);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  h->block = EnvInt("FBSTAB_BLOCK", block);
+  const size_t vec_bytes = VecDoubles(h->nz, h->nl, h->nv) * sizeof(double);
+  const size_t smem_max = (size_t)EnvInt("FBSTAB_VEC_SMEM_MAX", 12 * 1024);
+  h->vec_in_smem = vec_bytes <= smem_max ? 1 : 0;
+  h->dyn_smem = h->vec_in_smem ? vec_bytes : 0;
+  if (h->dyn_smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)h->dyn_smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, h->block,
+                                                         h->dyn_smem));
+  if (occ < 1) return Fail(FBSTAB_ERR_CUDA, "kernel does not fit on an SM");
+  h->ws_stride = ws_doubles_no_vec + (h->vec_in_smem ? 0 : vec_bytes / sizeof(double));
+  // bound the workspace for large problems: at most ~2 GiB
+  size_t grid = (size_t)h->sm_count * occ;
+  const size_t per_cta = std::max<size_t>(h->ws_stride * sizeof(double), 1);
+  const size_t cap = ((size_t)2 << 30) / per_cta;
+  grid = std::min(grid, std::max<size_t>(cap, (size_t)h->sm_count));
+  grid = std::min<size_t>(grid, (size_t)std::max(max_batch, 1));
+  h->grid_max = (int)grid;
+  if (cudaMalloc(&h->ws, std::max<size_t>(h->ws_stride * grid, 1) * sizeof(double)) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return Fail(FBSTAB_ERR_ALLOC, "cudaMalloc of the solver workspace failed");
+  }
+  CUDA_TRY(cudaMalloc(&h->counter, sizeof(int)));
+  return FBSTAB_OK;
+}
+
+int SetOptions(HandleBase* h, const fbstab_options* o) {
+  if (!h || !o) return Fail(FBSTAB_ERR_INVALID, "null argument");
+  fbstab_options c = *o;  // UpdateParameters copies field by field, impl:308-332
+  int rc = fbstab_validate_options(&c);
+  if (rc) return rc;
+  h->opts = c;
+  return FBSTAB_OK;
+}
+
+}  // namespace
+
+struct fbstab_dense_batch : HandleBase {
+  fbs::DenseSmallPlan small;
+};
+struct fbstab_mpc_batch : HandleBase {
+  int N = 0, nx = 0, nu = 0, nc = 0;
+};
+
+namespace {
+
+int StageComponentIo(HandleBase* h, Stager* st, int batch,
+                     const fbstab_component_io* io, fbstab_component_io* dio) {
+  const size_t bz = (size_t)batch * h->nz * sizeof(double),
+               bl = (size_t)batch * h->nl * sizeof(double),
+               bv = (size_t)batch * h->nv * sizeof(double);
+  *dio = *io;
+  int rc;
+  auto in = [&](int slot, const double* user, size_t bytes, const double** out) {
+    if (!user) {
+      *out = nullptr;
+      return FBSTAB_OK;
+    }
+    const void* p;
+    int r = st->In(&h->comp[slot], user, bytes, &p);
+    *out = (const double*)p;
+    return r;
+  };
+  auto out = [&](int slot, void* user, size_t bytes, bool copy_in, void** o) {
+    if (!user) {
+      *o = nullptr;
+      return FBSTAB_OK;
+    }
+    return st->InOut(&h->comp[slot], user, bytes, copy_in, o);
+  };
+  if ((rc = in(0, io->z, bz, &dio->z))) return rc;
+  if ((rc = in(1, io->l, bl, &dio->l))) return rc;
+  if ((rc = in(2, io->v, bv, &dio->v))) return rc;
+  if ((rc = in(3, io->y, bv, &dio->y))) return rc;
+  if ((rc = in(4, io->zbar, bz, &dio->zbar))) return rc;
+  if ((rc = in(5, io->lbar, bl, &dio->lbar))) return rc;
+  if ((rc = in(6, io->vbar, bv, &dio->vbar))) return rc;
+  if ((rc = out(7, io->rz, bz, true, (void**)&dio->rz))) return rc;
+  if ((rc = out(8, io->rl, bl, true, (void**)&dio->rl))) return rc;
+  if ((rc = out(9, io->rv, bv, true, (void**)&dio->rv))) return rc;
+  if ((rc = out(10, io->dz, bz, false, (void**)&dio->dz))) return rc;
+  if ((rc = out(11, io->dl, bl, false, (void**)&dio->dl))) return rc;
+  if ((rc = out(12, io->dv, bv, false, (void**)&dio->dv))) return rc;
+  if ((rc = out(13, io->dy, bv, false, (void**)&dio->dy))) return rc;
+  if ((rc = out(14, io->gamma, bv, false, (void**)&dio->gamma))) return rc;
+  if ((rc = out(15, io->mus, bv, false, (void**)&dio->mus))) return rc;
+  if ((rc = out(16, io->norms, (size_t)batch * 8 * sizeof(double), false,
+                (void**)&dio->norms)))
+    return rc;
+  if ((rc = out(17, io->status, (size_t)batch * sizeof(int32_t), false,
+                (void**)&dio->status)))
+    return rc;
+  return FBSTAB_OK;
+}
+
+void FillCommon(HandleBase* h, CommonArgs* c, int batch) {
+  c->batch = batch;
+  c->ws = h->ws;
+  c->ws_stride = h->ws_stride;
+  c->counter = h->counter;
+  c->vec_in_smem = h->vec_in_smem;
+  c->opts = h->opts;
+  c->comp = -1;
+  memset(&c->io, 0, sizeof(c->io));
+}
+
+void StampSolveTime(fbstab_out* out, int batch, double seconds) {
+  for (int i = 0; i < batch; i++) out[i].solve_time = seconds;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fbstab_last_error(void) { return g_last_error.c_str(); }
+
+int fbstab_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void fbstab_default_options(fbstab_options* o) {
+  o->sigma0 = 1e-8;
+  o->sigma_max = 1e-6;
+  o->sigma_min = 1e-12;
+  o->alpha = 0.95;
+  o->beta = 0.75;
+  o->eta = 1e-8;
+  o->delta = 0.2;
+  o->gamma = 0.1;
+  o->abs_tol = 1e-6;
+  o->rel_tol = 1e-12;
+  o->stall_tol = 1e-10;
+  o->infeas_tol = 1e-8;
+  o->inner_tol_max = 1e-2;
+  o->inner_tol_min = 1e-12;
+  o->max_newton_iters = 200;
+  o->max_prox_iters = 30;
+  o->max_inner_iters = 50;
+  o->max_linesearch_iters = 20;
+  o->check_feasibility = 1;
+  o->nonmonotone_linesearch = 1;
+  o->display_level = 1;  // Display::FINAL
+}
+
+void fbstab_reliable_options(fbstab_options* o) {
+  fbstab_default_options(o);
+  o->sigma0 = 1e-4;
+  o->sigma_max = 1e-2;
+  o->sigma_min = 1e-10;
+  o->beta = 0.9;
+  o->abs_tol = 1e-4;
+  o->rel_tol = 1e-6;
+  o->max_linesearch_iters = 40;
+  o->max_newton_iters = 500;
+  o->max_prox_iters = 100;
+  o->nonmonotone_linesearch = 0;
+}
+
+int fbstab_validate_options(fbstab_options* o) {
+  if (!o) return Fail(FBSTAB_ERR_INVALID, "null options");
+  bool ok = true;
+  o->sigma0 = std::max(o->sigma0, 1e-10);
+  ok = ok && Sat(&o->sigma_max, 1e-6, 1e2);
+  ok = ok && Sat(&o->sigma_min, 1e-13, 1e-8);
+  ok = ok && Sat(&o->sigma0, o->sigma_min, o->sigma_max);
+  ok = ok && Sat(&o->alpha, 0.001, 0.999);
+  ok = ok && Sat(&o->beta, 0.1, 0.99);
+  ok = ok && Sat(&o->eta, 1e-12, 0.499);
+  ok = ok && Sat(&o->delta, 0.0001, 0.99);
+  ok = ok && Sat(&o->gamma, 0.001, 0.9);
+  o->abs_tol = std::max(o->abs_tol, 1e-14);
+  o->rel_tol = std::max(o->rel_tol, 0.0);
+  o->stall_tol = std::max(o->stall_tol, 1e-14);
+  o->infeas_tol = std::max(o->infeas_tol, 1e-14);
+  ok = ok && Sat(&o->inner_tol_max, 1e-8, 1e2);
+  ok = ok && Sat(&o->inner_tol_min, 1e-14, 1e-2);
+  o->max_newton_iters = std::max(o->max_newton_iters, 1);
+  o->max_prox_iters = std::max(o->max_prox_iters, 1);
+  o->max_inner_iters = std::max(o->max_inner_iters, 1);
+  o->max_linesearch_iters = std::max(o->max_linesearch_iters, 1);
+  if (!ok) return Fail(FBSTAB_ERR_INVALID, "saturate(): lower bound above upper bound");
+  return FBSTAB_OK;
+}
+
+// ---- dense -------------------------------------------------------------------
+int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
+                              fbstab_dense_batch** handle) {
+  if (!handle) return Fail(FBSTAB_ERR_INVALID, "null handle pointer");
+  *handle = nullptr;
+  // fbstab_dense.cc:19-23
+  if (nz <= 0 || nv <= 0 || nl < 0)
+    return Fail(FBSTAB_ERR_INVALID,
+                "nz and nv must be positive, nl nonnegative");
+  if (max_batch < 1) return Fail(FBSTAB_ERR_INVALID, "max_batch must be >= 1");
+  auto* h = new fbstab_dense_batch;
+  h->nz = nz;
+  h->nl = nl;
+  h->nv = nv;
+  const int n = nz + nl;
+  const int block = n <= 8 ? 32 : n <= 48 ? 64 : n <= 128 ? 128 : 256;
+  int rc = InitCommon(h, device, max_batch, (const void*)dense_generic_kernel,
+                      DenseWsDoubles(nz, nl, nv), block);
+  if (rc == FBSTAB_OK && !EnvInt("FBSTAB_FORCE_GENERIC", 0))
+    rc = fbs::DenseSmallInit(&h->small, nz, nl, nv, h->sm_count, h->counter);
+  if (rc) {
+    std::string keep = g_last_error;
+    h->FreeAll();
+    delete h;
+    g_last_error = keep;
+    return rc;
+  }
+  if (h->small.enabled) h->path = h->small.name;
+  *handle = h;
+  return FBSTAB_OK;
+}
+
+int fbstab_dense_batch_destroy(fbstab_dense_batch* h) {
+  if (!h) return FBSTAB_OK;
+  h->FreeAll();
+  delete h;
+  return FBSTAB_OK;
+}
+
+int fbstab_dense_batch_set_options(fbstab_dense_batch* h, const fbstab_options* o) {
+  return SetOptions(h, o);
+}
+int fbstab_dense_batch_get_options(const fbstab_dense_batch* h, fbstab_options* o) {
+  if (!h || !o) return Fail(FBSTAB_ERR_INVALID, "null argument");
+  *o = h->opts;
+  return FBSTAB_OK;
+}
+int fbstab_dense_batch_last_launches(const fbstab_dense_batch* h) {
+  return h ? h->last_launches : 0;
+}
+const char* fbstab_dense_batch_path(const fbstab_dense_batch* h) {
+  return h ? h->path : "";
+}
+
+static int DenseStageData(fbstab_dense_batch* h, Stager* st, int batch,
+                          const double* H, const double* f, const double* G,
+                          const double* hh, const double* A, const double* b,
+                          DenseArgs* a) {
+  const size_t nz = h->nz, nl = h->nl, nv = h->nv, B = batch, D = sizeof(double);
+  a->nz = h->nz;
+  a->nl = h->nl;
+  a->nv = h->nv;
+  int rc;
+  if ((rc = st->In(&h->in[0], H, B * nz * nz * D, (const void**)&a->H))) return rc;
+  if ((rc = st->In(&h->in[1], f, B * nz * D, (const void**)&a->f))) return rc;
+  if ((rc = st->In(&h->in[2], G, B * nl * nz * D, (const void**)&a->G))) return rc;
+  if ((rc = st->In(&h->in[3], hh, B * nl * D, (const void**)&a->h))) return rc;
+  if ((rc = st->In(&h->in[4], A, B * nv * nz * D, (const void**)&a->A))) return rc;
+  if ((rc = st->In(&h->in[5], b, B * nv * D, (const void**)&a->b))) return rc;
+  return FBSTAB_OK;
+}
+
+int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
+                             const double* f, const double* G, const double* hh,
+                             const double* A, const double* b, double* z,
+                             double* l, double* v, double* y, fbstab_out* out,
+                             void* stream) {
+  if (!h) return Fail(FBSTAB_ERR_INVALID, "null handle");
+  if (batch < 0 || batch > h->max_batch)
+    return Fail(FBSTAB_ERR_INVALID, "batch exceeds the handle's max_batch");
+  if (!out) return Fail(FBSTAB_ERR_INVALID, "null out pointer");
+  h->last_launches = 0;
+  if (batch == 0) return FBSTAB_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const auto t0 = std::chrono::steady_clock::now();
+  Stager st;
+  st.stream = (cudaStream_t)stream;
+  DenseArgs a;
+  int rc = DenseStageData(h, &st, batch, H, f, G, hh, A, b, &a);
+  if (rc) return rc;
+  const size_t nz = h->nz, nl = h->nl, nv = h->nv, B = batch, D = sizeof(double);
+  FillCommon(h, &a.c, batch);
+  if ((rc = st.InOut(&h->io[0], z, B * nz * D, true, (void**)&a.c.z))) return rc;
+  if ((rc = st.InOut(&h->io[1], l, B * nl * D, true, (void**)&a.c.l))) return rc;
+  if ((rc = st.InOut(&h->io[2], v, B * nv * D, true, (void**)&a.c.v))) return rc;
+  if ((rc = st.InOut(&h->io[3], y, B * nv * D, false, (void**)&a.c.y))) return rc;
+  if ((rc = st.InOut(&h->out_buf, out, B * sizeof(fbstab_out), false,
+                     (void**)&a.c.out)))
+    return rc;
+  CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
+  if (h->small.enabled) {
+    rc = fbs::DenseSmallLaunch(h->small, batch, a.H, a.f, a.G, a.h, a.A, a.b,
+                               a.c.z, a.c.l, a.c.v, a.c.y, a.c.out, h->opts,
+                               st.stream);
+    if (rc) return Fail(FBSTAB_ERR_CUDA, "dense small-path launch failed");
+  } else {
+    const int grid = std::min(batch, h->grid_max);
+    dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->last_launches = 1;
+  if ((rc = st.Finish())) return rc;
+  if (st.any_host && !IsDevicePtr(out)) {
+    const double sec =
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    StampSolveTime(out, batch, sec);
+  }
+  return FBSTAB_OK;
+}
+
+int fbstab_dense_batch_component(fbstab_dense_batch* h, int comp, int batch,
+                                 const double* H, const double* f,
+                                 const double* G, const double* hh,
+                                 const double* A, const double* b,
+                                 const fbstab_component_io* io, void* stream) {
+  if (!h || !io) return Fail(FBSTAB_ERR_INVALID, "null argument");
+  if (batch < 0 || batch > h->max_batch)
+    return Fail(FBSTAB_ERR_INVALID, "batch exceeds the handle's max_batch");
+  if (comp < FBSTAB_COMP_MARGIN || comp > FBSTAB_COMP_FEAS)
+    return Fail(FBSTAB_ERR_INVALID, "unknown component");
+  if (batch == 0) return FBSTAB_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  Stager st;
+  st.stream = (cudaStream_t)stream;
+  DenseArgs a;
+  int rc = DenseStageData(h, &st, batch, H, f, G, hh, A, b, &a);
+  if (rc) return rc;
+  FillCommon(h, &a.c, batch);
+  a.c.comp = comp;
+  if ((rc = StageComponentIo(h, &st, batch, io, &a.c.io))) return rc;
+  CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
+  const int grid = std::min(batch, h->grid_max);
+  dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->last_launches = 1;
+  return st.Finish();
+}
+
+// ---- mpc ---------------------------------------------------------------------
+int fbstab_mpc_batch_create(int N, int nx, int nu, int nc, int max_batch,
+                            int device, fbstab_mpc_batch** handle) {
+  if (!handle) return Fail(FBSTAB_ERR_INVALID, "null handle pointer");
+  *handle = nullptr;
+  // fbstab_mpc.cc:62-65
+  if (N < 1 || nx < 1 || nu < 1 || nc < 1)
+    return Fail(FBSTAB_ERR_INVALID, "problem sizes must be positive");
+  if (max_batch < 1) return Fail(FBSTAB_ERR_INVALID, "max_batch must be >= 1");
+  auto* h = new fbstab_mpc_batch;
+  h->N = N;
+  h->nx = nx;
+  h->nu = nu;
+  h->nc = nc;
+  h->nz = (N + 1) * (nx + nu);
+  h->nl = (N + 1) * nx;
+  h->nv = (N + 1) * nc;
+  const int block = (nx + nu) <= 12 ? 32 : 64;
+  int rc = InitCommon(h, device, max_batch, (const void*)mpc_generic_kernel,
+                      MpcWsDoubles(N, nx, nu, nc), block);
+  if (rc) {
+    std::string keep = g_last_error;
+    h->FreeAll();
+    delete h;
+    g_last_error = keep;
+    return rc;
+  }
+  h->path = "mpc-riccati-team";
+  *handle = h;
+  return FBSTAB_OK;
+}
+
+int fbstab_mpc_batch_destroy(fbstab_mpc_batch* h) {
+  if (!h) return FBSTAB_OK;
+  h->FreeAll();
+  delete h;
+  return FBSTAB_OK;
+}
+int fbstab_mpc_batch_set_options(fbstab_mpc_batch* h, const fbstab_options* o) {
+  return SetOptions(h, o);
+}
+int fbstab_mpc_batch_get_options(const fbstab_mpc_batch* h, fbstab_options* o) {
+  if (!h || !o) return Fail(FBSTAB_ERR_INVALID, "null argument");
+  *o = h->opts;
+  return FBSTAB_OK;
+}
+int fbstab_mpc_batch_last_launches(const fbstab_mpc_batch* h) {
+  return h ? h->last_launches : 0;
+}
+const char* fbstab_mpc_batch_path(const fbstab_mpc_batch* h) {
+  return h ? h->path : "";
+}
+
+static int MpcStageData(fbstab_mpc_batch* h, Stager* st, int batch,
+                        const double* const* user, MpcArgs* a) {
+  const size_t N = h->N, nx = h->nx, nu = h->nu, nc = h->nc, K = N + 1,
+               B = batch, D = sizeof(double);
+  const size_t sizes[12] = {K * nx * nx, K * nu * nu, K * nu * nx, K * nx,
+                            K * nu,      N * nx * nx, N * nx * nu, N * nx,
+                            K * nc * nx, K * nc * nu, K * nc,      nx};
+  const double** dst[12] = {&a->Q, &a->R, &a->S, &a->q, &a->r, &a->A,
+                            &a->B, &a->cc, &a->E, &a->L, &a->d, &a->x0};
+  a->N = h->N;
+  a->nx = h->nx;
+  a->nu = h->nu;
+  a->nc = h->nc;
+  for (int k = 0; k < 12; k++) {
+    int rc = st->In(&h->in[k], user[k], B * sizes[k] * D, (const void**)dst[k]);
+    if (rc) return rc;
+  }
+  return FBSTAB_OK;
+}
+
+int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
+                           const double* R, const double* S, const double* q,
+                           const double* r, const double* A, const double* B,
+                           const double* c, const double* E, const double* L,
+                           const double* d, const double* x0, double* z,
+                           double* l, double* v, double* y, fbstab_out* out,
+                           void* stream) {
+  if (!h) return Fail(FBSTAB_ERR_INVALID, "null handle");
+  if (batch < 0 || batch > h->max_batch)
+    return Fail(FBSTAB_ERR_INVALID, "batch exceeds the handle's max_batch");
+  if (!out) return Fail(FBSTAB_ERR_INVALID, "null out pointer");
+  h->last_launches = 0;
+  if (batch == 0) return FBSTAB_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const auto t0 = std::chrono::steady_clock::now();
+  Stager st;
+  st.stream = (cudaStream_t)stream;
+  MpcArgs a;
+  const double* user[12] = {Q, R, S, q, r, A, B, c, E, L, d, x0};
+  int rc = MpcStageData(h, &st, batch, user, &a);
+  if (rc) return rc;
+  const size_t nz = h->nz, nl = h->nl, nv = h->nv, Bn = batch, D = sizeof(double);
+  FillCommon(h, &a.c, batch);
+  if ((rc = st.InOut(&h->io[0], z, Bn * nz * D, true, (void**)&a.c.z))) return rc;
+  if ((rc = st.InOut(&h->io[1], l, Bn * nl * D, true, (void**)&a.c.l))) return rc;
+  if ((rc = st.InOut(&h->io[2], v, Bn * nv * D, true, (void**)&a.c.v))) return rc;
+  if ((rc = st.InOut(&h->io[3], y, Bn * nv * D, false, (void**)&a.c.y))) return rc;
+  if ((rc = st.InOut(&h->out_buf, out, Bn * sizeof(fbstab_out), false,
+                     (void**)&a.c.out)))
+    return rc;
+  CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
+  const int grid = std::min(batch, h->grid_max);
+  mpc_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->last_launches = 1;
+  if ((rc = st.Finish())) return rc;
+  if (st.any_host && !IsDevicePtr(out)) {
+    const double sec =
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    StampSolveTime(out, batch, sec);
+  }
+  return FBSTAB_OK;
+}
+
+int fbstab_mpc_batch_component(fbstab_mpc_batch* h, int comp, int batch,
+                               const double* Q, const double* R,
+                               const double* S, const double* q,
+                               const double* r, const double* A,
+                               const double* B, const double* c,
+                               const double* E, const double* L,
+                               const double* d, const double* x0,
+                               const fbstab_component_io* io, void* stream) {
+  if (!h || !io) return Fail(FBSTAB_ERR_INVALID, "null argument");
+  if (batch < 0 || batch > h->max_batch)
+    return Fail(FBSTAB_ERR_INVALID, "batch exceeds the handle's max_batch");
+  if (comp < FBSTAB_COMP_MARGIN || comp > FBSTAB_COMP_FEAS)
+    return Fail(FBSTAB_ERR_INVALID, "unknown component");
+  if (batch == 0) return FBSTAB_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  Stager st;
+  st.stream = (cudaStream_t)stream;
+  MpcArgs a;
+  const double* user[12] = {Q, R, S, q, r, A, B, c, E, L, d, x0};
+  int rc = MpcStageData(h, &st, batch, user, &a);
+  if (rc) return rc;
+  FillCommon(h, &a.c, batch);
+  a.c.comp = comp;
+  if ((rc = StageComponentIo(h, &st, batch, io, &a.c.io))) return rc;
+  CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
+  const int grid = std::min(batch, h->grid_max);
+  mpc_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->last_launches = 1;
+  return st.Finish();
+}
+
+}  // extern "C"

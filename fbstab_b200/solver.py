@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's solver interface over the C-ABI.
+
+`FBstabDense` / `FBstabMpc` keep the reference's names, argument meaning and
+error behaviour (reference fbstab/fbstab_dense.h:50-194, fbstab_mpc.h:56-243):
+construct with the problem sizes, `update_options`, `default_options`,
+`reliable_options`, `solve` for one instance, plus the batched `solve_batch`.
+Size errors raise RuntimeError like the reference's std::runtime_error.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import OUT_DTYPE, ComponentIO, Options
+
+
+def _is_host(a):
+    return isinstance(a, np.ndarray)
+
+
+def _flat(a, n, name):
+    if a is None:
+        if n == 0:
+            return None
+        raise RuntimeError(f"{name} is required")
+    size = a.size if isinstance(a, np.ndarray) else a.numel()
+    if size != n:
+        raise RuntimeError(
+            f"size mismatch for {name}: expected {n} elements, got {size}")
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+            raise RuntimeError(f"{name} must be contiguous float64")
+    return a
+
+
+class _Base:
+    _prefix = None
+    _fields = ()
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        self.opts = capi.default_options()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            getattr(capi.lib(), f"fbstab_{self._prefix}_batch_destroy")(h)
+            self._h = None
+
+    # -- options: UpdateOptions / DefaultOptions / ReliableOptions ----------
+    def update_options(self, opts):
+        capi.check(getattr(capi.lib(), f"fbstab_{self._prefix}_batch_set_options")(
+            self._h, C.byref(opts)))
+        got = Options()
+        capi.check(getattr(capi.lib(), f"fbstab_{self._prefix}_batch_get_options")(
+            self._h, C.byref(got)))
+        self.opts = got
+
+    @staticmethod
+    def default_options(**kw):
+        return capi.default_options(**kw)
+
+    @staticmethod
+    def reliable_options(**kw):
+        return capi.reliable_options(**kw)
+
+    @property
+    def path(self):
+        return getattr(capi.lib(), f"fbstab_{self._prefix}_batch_path")(self._h).decode()
+
+    @property
+    def last_launches(self):
+        return getattr(capi.lib(), f"fbstab_{self._prefix}_batch_last_launches")(self._h)
+
+    def _data_ptrs(self, data, batch):
+        sizes = self.field_sizes
+        return [capi.ptr(_flat(data[k], batch * sizes[k], k)) for k in self._fields]
+
+    def solve_batch(self, data, z, l, v, y=None, out=None, stream=None):
+        """Solve `batch` instances.  `data` maps field name -> flat array
+        (numpy host array or torch tensor, host or CUDA).  z,l,v are the warm
+        start and are overwritten; returns (out, y)."""
+        batch = (z.size if _is_host(z) else z.numel()) // self.nz
+        if batch > self.max_batch:
+            raise RuntimeError("batch exceeds max_batch")
+        _flat(z, batch * self.nz, "z")
+        _flat(l, batch * self.nl, "l")
+        _flat(v, batch * self.nv, "v")
+        if y is None:
+            y = np.zeros(batch * self.nv) if _is_host(z) else z.new_zeros(batch * self.nv)
+        if out is None:
+            if _is_host(z):
+                out = np.zeros(batch, dtype=OUT_DTYPE)
+            else:
+                import torch
+                out = torch.zeros(batch * OUT_DTYPE.itemsize, dtype=torch.uint8,
+                                  device=z.device)
+        fn = getattr(capi.lib(), f"fbstab_{self._prefix}_batch_solve")
+        capi.check(fn(self._h, batch, *self._data_ptrs(data, batch), capi.ptr(z),
+                      capi.ptr(l), capi.ptr(v), capi.ptr(y), capi.ptr(out),
+                      stream))
+        return out, y
+
+    def component(self, comp, data, batch, stream=None, **io):
+        """Run one engine stage (see FBSTAB_COMP_* in the header)."""
+        cio = ComponentIO()
+        keep = []
+        for name, _ in ComponentIO._fields_:
+            if name in ("sigma", "tol"):
+                setattr(cio, name, float(io.get(name, 0.0)))
+            else:
+                a = io.get(name)
+                keep.append(a)
+                setattr(cio, name, capi.ptr(a))
+        fn = getattr(capi.lib(), f"fbstab_{self._prefix}_batch_component")
+        capi.check(fn(self._h, comp, batch, *self._data_ptrs(data, batch),
+                      C.byref(cio), stream))
+
+
+class FBstabDense(_Base):
+    """min 1/2 z'Hz + f'z  s.t. Gz = h, Az <= b   (fbstab_dense.h:17-49)."""
+    _prefix = "dense"
+    _fields = ("H", "f", "G", "h", "A", "b")
+
+    def __init__(self, nz, nl, nv, max_batch=1, device=0):
+        super().__init__()
+        if nz <= 0 or nv <= 0 or nl < 0:  # fbstab_dense.cc:19-23
+            raise RuntimeError("In FBstabDense::FBstabDense: nz and nv must be "
+                               "positive, nl nonnegative")
+        self.nz, self.nl, self.nv, self.max_batch = nz, nl, nv, max_batch
+        self.field_sizes = {"H": nz * nz, "f": nz, "G": nl * nz, "h": nl,
+                            "A": nv * nz, "b": nv}
+        capi.check(capi.lib().fbstab_dense_batch_create(
+            nz, nl, nv, max_batch, device, C.byref(self._h)))
+
+    def solve(self, H, f, G, h, A, b, x0=None):
+        """One instance from 2-D numpy matrices (any memory order).
+        Returns (out record, (z, l, v, y))."""
+        cm = lambda M, r, c: np.ascontiguousarray(  # column-major flatten
+            np.asarray(M, dtype=np.float64).reshape(r, c).T).reshape(-1)
+        vec = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(-1)
+        nz, nl, nv = self.nz, self.nl, self.nv
+        f_, h_, b_ = vec(f), vec(h), vec(b)
+        if f_.size != nz or h_.size != nl or b_.size != nv:
+            raise RuntimeError("In FBstabDense::Solve: mismatch between *this "
+                               "and data dimensions.")
+        data = {"H": cm(H, nz, nz), "f": f_, "G": cm(G, nl, nz) if nl else np.zeros(0),
+                "h": h_, "A": cm(A, nv, nz), "b": b_}
+        if x0 is None:
+            z, l, v = np.zeros(nz), np.zeros(nl), np.zeros(nv)
+        else:
+            z, l, v = [vec(t).copy() for t in x0]
+            if z.size != nz or l.size != nl or v.size != nv:
+                raise RuntimeError("In FBstabDense::Solve: mismatch between "
+                                   "*this and initial guess dimensions.")
+        out, y = self.solve_batch(data, z, l, v)
+        return out[0], (z, l, v, y)
+
+
+class FBstabMpc(_Base):
+    """Linear-quadratic OCP in the reference's stage form (fbstab_mpc.h:17-55)."""
+    _prefix = "mpc"
+    _fields = ("Q", "R", "S", "q", "r", "A", "B", "c", "E", "L", "d", "x0")
+
+    def __init__(self, N, nx, nu, nc, max_batch=1, device=0):
+        super().__init__()
+        if N < 1 or nx < 1 or nu < 1 or nc < 1:  # fbstab_mpc.cc:62-65
+            raise RuntimeError(
+                "In FBstabMpc::FBstabMpc: problem sizes must be positive.")
+        self.N, self.nx, self.nu, self.nc = N, nx, nu, nc
+        self.max_batch = max_batch
+        K = N + 1
+        self.nz, self.nl, self.nv = K * (nx + nu), K * nx, K * nc
+        self.field_sizes = {"Q": K * nx * nx, "R": K * nu * nu, "S": K * nu * nx,
+                            "q": K * nx, "r": K * nu, "A": N * nx * nx,
+                            "B": N * nx * nu, "c": N * nx, "E": K * nc * nx,
+                            "L": K * nc * nu, "d": K * nc, "x0": nx}
+        capi.check(capi.lib().fbstab_mpc_batch_create(
+            N, nx, nu, nc, max_batch, device, C.byref(self._h)))
+
+    def solve(self, data, x0=None):
+        """One instance; `data` as produced by problems.ocp_batch(count=1)."""
+        if x0 is None:
+            z, l, v = np.zeros(self.nz), np.zeros(self.nl), np.zeros(self.nv)
+        else:
+            z, l, v = [np.ascontiguousarray(t, dtype=np.float64).reshape(-1).copy()
+                       for t in x0]
+        out, y = self.solve_batch(data, z, l, v)
+        return out[0], (z, l, v, y)

@@ -1,0 +1,249 @@
+/*
+ * fbstab_b200.h -- C-ABI of the B200-native batched FBstab engine.
+ *
+ * This is the drop-in boundary: plain C types only (pointers, sizes, PODs), no
+ * torch / Eigen types.  The C++ facade in include/fbstab/ (FBstabDense,
+ * FBstabMpc -- same names and signatures as the reference) is a thin host
+ * layer over these entry points, and INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * What each entry point replaces in the reference (paths relative to the
+ * reference tree):
+ *   fbstab_dense_batch_create   <- FBstabDense::FBstabDense(nz,nl,nv)
+ *                                  fbstab/fbstab_dense.cc:18-42
+ *   fbstab_dense_batch_solve    <- FBstabDense::Solve(qp,&x)
+ *                                  fbstab/fbstab_dense.h:136-149 ->
+ *                                  FBstabAlgorithm::Solve
+ *                                  fbstab/fbstab_algorithm-impl.h:113-224
+ *                                  (one call = `batch` independent Solve calls)
+ *   fbstab_mpc_batch_create     <- FBstabMpc::FBstabMpc(N,nx,nu,nc)
+ *                                  fbstab/fbstab_mpc.cc:61-89
+ *   fbstab_mpc_batch_solve      <- FBstabMpc::Solve(qp,&x)
+ *                                  fbstab/fbstab_mpc.h:181-195
+ *   fbstab_*_batch_set_options  <- UpdateOptions -> UpdateParameters +
+ *                                  ValidateOptions
+ *                                  fbstab/fbstab_algorithm-impl.h:7-31,308-332
+ *   fbstab_default_options      <- AlgorithmParameters::DefaultParameters
+ *                                  fbstab/fbstab_algorithm-impl.h:33-59
+ *   fbstab_reliable_options     <- AlgorithmParameters::ReliableParameters
+ *                                  fbstab/fbstab_algorithm-impl.h:61-74
+ *   fbstab_*_batch_component    <- the component methods the algorithm is
+ *                                  built from (fbstab/components/
+ *                                  abstract_components.h:24-338); exposed so
+ *                                  each kernel stage can be parity-tested
+ *
+ * Data layout (identical to the reference's, so a facade call is a memcpy):
+ *   dense: per instance H (nz x nz), G (nl x nz), A (nv x nz) column-major
+ *          (Eigen default, fbstab/components/dense_data.h:44-52), vectors
+ *          f(nz) h(nl) b(nv); a batch is instance-major and contiguous:
+ *          H[i] starts at H + i*nz*nz, and so on.
+ *   mpc:   per instance the 11 sequences of fbstab/fbstab_mpc.h:67-83, each
+ *          `len x rows x cols` contiguous, column-major per matrix
+ *          (tools/matrix_sequence.h:81-83); Q,R,S,q,r,E,L,d have N+1 entries,
+ *          A,B,c have N; x0(nx).  A batch is instance-major and contiguous.
+ *   iterates: z(nz) l(nl) v(nv) y(nv) per instance, instance-major.
+ *
+ * Every data/iterate pointer may be a HOST pointer or a DEVICE pointer on the
+ * handle's device (checked per pointer).  Host buffers are staged through the
+ * handle's device buffers inside the call; device buffers are used in place.
+ * If every pointer is a device pointer the call only enqueues work on `stream`
+ * (asynchronous); otherwise it returns after the results are in host memory.
+ *
+ * There is NO CPU fallback: with no usable CUDA device every create/solve call
+ * fails with FBSTAB_ERR_NOGPU / FBSTAB_ERR_CUDA.
+ */
+#ifndef FBSTAB_B200_H_
+#define FBSTAB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (return value of every int function) ------------------- */
+#define FBSTAB_OK 0
+#define FBSTAB_ERR_INVALID 1 /* bad size / null pointer / batch > max_batch   */
+#define FBSTAB_ERR_CUDA 2    /* a CUDA runtime call failed                    */
+#define FBSTAB_ERR_NOGPU 3   /* no CUDA device: the engine has no CPU path    */
+#define FBSTAB_ERR_ALLOC 4   /* device or host allocation failed              */
+
+/* ---- ExitFlag, reference fbstab/fbstab_algorithm.h:17-24 ---------------- */
+#define FBSTAB_SUCCESS 0
+#define FBSTAB_DIVERGENCE 1
+#define FBSTAB_MAXITERATIONS 2
+#define FBSTAB_PRIMAL_INFEASIBLE 3
+#define FBSTAB_DUAL_INFEASIBLE 4
+#define FBSTAB_PRIMAL_DUAL_INFEASIBLE 5
+
+/* ---- per-instance status (where the reference throws) ------------------- */
+#define FBSTAB_STATUS_OK 0
+#define FBSTAB_STATUS_FACTOR_FAILED 1 /* LinearSolver::Initialize returned false,
+                                         fbstab_algorithm-impl.h:263-267       */
+#define FBSTAB_STATUS_SATURATE 2      /* tools::saturate lower > upper,
+                                         tools/utilities.h:21-25               */
+
+/* AlgorithmParameters, reference fbstab/fbstab_algorithm.h:48-82. */
+typedef struct fbstab_options {
+  double sigma0, sigma_max, sigma_min;
+  double alpha, beta, eta, delta, gamma;
+  double abs_tol, rel_tol, stall_tol, infeas_tol;
+  double inner_tol_max, inner_tol_min;
+  int32_t max_newton_iters, max_prox_iters, max_inner_iters,
+      max_linesearch_iters;
+  int32_t check_feasibility, nonmonotone_linesearch, display_level;
+} fbstab_options;
+
+/* SolverOut, reference fbstab/fbstab_algorithm.h:30-37, plus the trajectory
+ * counters the work model needs.  48 bytes. */
+typedef struct fbstab_out {
+  int32_t eflag;
+  int32_t newton_iters;
+  int32_t prox_iters;
+  int32_t status;
+  double residual;
+  double initial_residual;
+  double solve_time; /* seconds for the whole batch; negative = not timed */
+  int32_t ls_backtracks;
+  int32_t residual_evals; /* residual evaluations the engine actually ran */
+} fbstab_out;
+
+void fbstab_default_options(fbstab_options* o);
+void fbstab_reliable_options(fbstab_options* o);
+/* Clamps exactly like ValidateOptions; returns FBSTAB_ERR_INVALID where the
+ * reference's saturate() would throw. */
+int fbstab_validate_options(fbstab_options* o);
+
+/* Thread-local description of the last error on this thread. */
+const char* fbstab_last_error(void);
+/* Number of CUDA devices visible (0 if none / driver missing). */
+int fbstab_device_count(void);
+
+/* ---- dense QPs ----------------------------------------------------------- */
+typedef struct fbstab_dense_batch fbstab_dense_batch;
+
+int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
+                              fbstab_dense_batch** handle);
+int fbstab_dense_batch_destroy(fbstab_dense_batch* handle);
+int fbstab_dense_batch_set_options(fbstab_dense_batch* handle,
+                                   const fbstab_options* o);
+int fbstab_dense_batch_get_options(const fbstab_dense_batch* handle,
+                                   fbstab_options* o);
+/* z,l,v: warm start in, solution out (or the infeasibility certificate, as in
+ * fbstab_algorithm-impl.h:209).  y: out only (input ignored, impl:342).
+ * stream: a cudaStream_t (NULL = default stream). */
+int fbstab_dense_batch_solve(fbstab_dense_batch* handle, int batch,
+                             const double* H, const double* f, const double* G,
+                             const double* h, const double* A, const double* b,
+                             double* z, double* l, double* v, double* y,
+                             fbstab_out* out, void* stream);
+/* Number of kernels the last solve launched on this handle. */
+int fbstab_dense_batch_last_launches(const fbstab_dense_batch* handle);
+/* Engine path the handle selected: a short static string for logs. */
+const char* fbstab_dense_batch_path(const fbstab_dense_batch* handle);
+
+/* ---- MPC-structured QPs -------------------------------------------------- */
+typedef struct fbstab_mpc_batch fbstab_mpc_batch;
+
+int fbstab_mpc_batch_create(int N, int nx, int nu, int nc, int max_batch,
+                            int device, fbstab_mpc_batch** handle);
+int fbstab_mpc_batch_destroy(fbstab_mpc_batch* handle);
+int fbstab_mpc_batch_set_options(fbstab_mpc_batch* handle,
+                                 const fbstab_options* o);
+int fbstab_mpc_batch_get_options(const fbstab_mpc_batch* handle,
+                                 fbstab_options* o);
+int fbstab_mpc_batch_solve(fbstab_mpc_batch* handle, int batch, const double* Q,
+                           const double* R, const double* S, const double* q,
+                           const double* r, const double* A, const double* B,
+                           const double* c, const double* E, const double* L,
+                           const double* d, const double* x0, double* z,
+                           double* l, double* v, double* y, fbstab_out* out,
+                           void* stream);
+int fbstab_mpc_batch_last_launches(const fbstab_mpc_batch* handle);
+const char* fbstab_mpc_batch_path(const fbstab_mpc_batch* handle);
+
+/* ---- component stages (for per-kernel parity tests) ----------------------
+ * One CTA per instance runs ONE stage of the engine on caller-supplied
+ * iterates.  All pointers host or device as above; unused ones may be NULL.
+ *
+ *  FBSTAB_COMP_MARGIN     y = b - A z
+ *                         (FullVariable::InitializeConstraintMargin,
+ *                          fbstab/components/full_variable.cc:47-53)
+ *  FBSTAB_COMP_RESIDUAL   inner residual R(x,xbar,sigma) -> (rz,rl,rv) and
+ *                         norms[0..2]; penalised natural residual norms ->
+ *                         norms[3..5] (FullResidual::InnerResidual /
+ *                         PenalizedNaturalResidual, full_residual.cc:49-109).
+ *                         y of x is an INPUT here.
+ *  FBSTAB_COMP_NEWTON     LinearSolver::Initialize(x,xbar,sigma) then
+ *                         ::Solve(r,&dx) with r = (rz,rl,rv) -> (dz,dl,dv,dy),
+ *                         gamma, mus; status[i] = factor status
+ *                         (dense_cholesky_solver.cc:32-127 /
+ *                          riccati_linear_solver.cc:77-344)
+ *  FBSTAB_COMP_FEAS       FullFeasibility::CheckFeasibility on (dz,dl,dv)
+ *                         passed in (z,l,v); status[i] = 0 feasible,
+ *                         1 primal infeasible, 2 dual infeasible, 3 both
+ *                         (full_feasibility.cc:25-88)
+ */
+#define FBSTAB_COMP_MARGIN 0
+#define FBSTAB_COMP_RESIDUAL 1
+#define FBSTAB_COMP_NEWTON 2
+#define FBSTAB_COMP_FEAS 3
+
+typedef struct fbstab_component_io {
+  /* iterate x and proximal centre xbar */
+  const double *z, *l, *v, *y;
+  const double *zbar, *lbar, *vbar;
+  /* residual in (NEWTON) / out (RESIDUAL) */
+  double *rz, *rl, *rv;
+  /* step out (NEWTON), margin out (MARGIN uses dy) */
+  double *dz, *dl, *dv, *dy;
+  double *gamma, *mus; /* nv each, out (NEWTON) */
+  double* norms;       /* 8 per instance, out (RESIDUAL): inner |rz|,|rl|,|rv|,
+                          natural |rz|,|rl|,|rv|, then Ei and Eo */
+  int32_t* status;     /* 1 per instance, out */
+  double sigma;
+  double tol; /* FEAS */
+} fbstab_component_io;
+
+int fbstab_dense_batch_component(fbstab_dense_batch* handle, int comp,
+                                 int batch, const double* H, const double* f,
+                                 const double* G, const double* h,
+                                 const double* A, const double* b,
+                                 const fbstab_component_io* io, void* stream);
+int fbstab_mpc_batch_component(fbstab_mpc_batch* handle, int comp, int batch,
+                               const double* Q, const double* R,
+                               const double* S, const double* q,
+                               const double* r, const double* A,
+                               const double* B, const double* c,
+                               const double* E, const double* L,
+                               const double* d, const double* x0,
+                               const fbstab_component_io* io, void* stream);
+
+/* ---- synthetic problems (host code; mirrors fbstab/test/ocp_generator.h) - */
+#define FBSTAB_OCP_DOUBLE_INTEGRATOR 0 /* ocp_generator.cc:319-363 nx2 nu1 nc6  */
+#define FBSTAB_OCP_SERVO_MOTOR 1       /* ocp_generator.cc:245-315 nx4 nu1 nc4  */
+#define FBSTAB_OCP_SPACECRAFT 2        /* ocp_generator.cc:171-244 nx6 nu3 nc12 */
+#define FBSTAB_OCP_COPOLYMERIZATION 3  /* ocp_generator.cc:73-169 nx18 nu5 nc10 */
+
+int fbstab_ocp_dims(int kind, int* nx, int* nu, int* nc);
+/* One instance in the wire format (time-varying, E(0)=0; ocp_generator.cc:365-421). */
+int fbstab_ocp_generate(int kind, int N, double* Q, double* R, double* S,
+                        double* q, double* r, double* A, double* B, double* c,
+                        double* E, double* L, double* d, double* x0);
+/* `count` instances first..first+count-1 of benchmark config `config`:
+ * identical stage data, x0 = nominal + rho*U(-1,1)^nx (instance 0 unperturbed). */
+int fbstab_ocp_generate_batch(int kind, int N, int config, long first, int count,
+                              double rho, double* Q, double* R, double* S,
+                              double* q, double* r, double* A, double* B,
+                              double* c, double* E, double* L, double* d,
+                              double* x0);
+/* Seeded random strictly convex, strictly feasible dense QPs (kind 0), or with
+ * a planted infeasibility (kind 1) / unbounded ray (kind 2). */
+int fbstab_random_dense_qp(int config, long first, int count, int nz, int nl,
+                           int nv, int kind, double* H, double* f, double* G,
+                           double* h, double* A, double* b, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBSTAB_B200_H_ */

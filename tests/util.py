@@ -1,0 +1,67 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+# Reference test problems, fbstab/test/fbstab_dense_unit_tests.cc
+DENSE_CASES = {
+    # name: (H, f, G, h, A, b, expected flag)
+    "FeasibleQP": ([[3, 1], [1, 1]], [10, 5], np.zeros((0, 2)), [],
+                   [[-1, 0], [0, 1]], [0, 0], "SUCCESS"),            # :28-61
+    "FeasibleQPwithEQ": ([[4, 1], [1, 2]], [1, 1], [[1, 1]], [1],
+                         [[-1, 0], [0, -1]], [0, 0], "SUCCESS"),     # :75-104
+    "DegenerateQP": ([[1, 0], [0, 0]], [1, 0], np.zeros((0, 2)), [],
+                     [[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1]],
+                     [0, 3, 3, -1, -1], "SUCCESS"),                  # :121-177
+    "InfeasibleQP": ([[1, 0], [0, 0]], [1, -1], np.zeros((0, 2)), [],
+                     [[1, 1], [1, 0], [0, 1], [-1, 0], [0, -1]],
+                     [0, 3, 3, -1, -1], "PRIMAL_INFEASIBLE"),        # :195-217
+    "UnboundedQP": ([[1, 0], [0, 0]], [1, -1], np.zeros((0, 2)), [],
+                    [[0, 0], [1, 0], [-1, 0], [0, -1]], [0, 3, -1, -1],
+                    "DUAL_INFEASIBLE"),                              # :233-256
+}
+
+
+def dense_case(name):
+    H, f, G, h, A, b, flag = DENSE_CASES[name]
+    H = np.array(H, dtype=float)
+    A = np.array(A, dtype=float)
+    f = np.array(f, dtype=float)
+    h = np.array(h, dtype=float)
+    b = np.array(b, dtype=float)
+    G = np.array(G, dtype=float).reshape(h.size, f.size)
+    return H, f, G, h, A, b, flag
+
+
+def colmajor(M):
+    return np.ascontiguousarray(np.asarray(M, dtype=np.float64).T).reshape(-1)
+
+
+def rel_err(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max())) if a.size else 0.0
+
+
+# DoubleIntegrator N=2 golden solution "computed using MATLAB's quadprog",
+# reference fbstab/test/fbstab_mpc_unit_tests.cc:38-47
+DI2_Z = np.array([-5.31028204670497e-14, 5.02854354118183e-13, 0.311688311338095,
+                  5.35637944798588e-13, 0.311688311339015, -0.0779220779990502,
+                  0.311688311339667, 0.233766233340057, -0.103896103779874])
+DI2_L = np.array([-5.24675324688535, -4.49350649223710, -3.55844155822323,
+                  -0.935064934014372, -1.48051948022526, 0.233766233996585])
+DI2_V = np.array([1.06213597221667e-13, -1.41190425869539e-21, 0, 0, 0, 0,
+                  -1.50393600622818e-21, -8.75144622575045e-10, 0, 0, 0, 0,
+                  -8.75144611157041e-10, -6.56358459377444e-10, 0, 0, 0, 0])
+
+# The reference's live MPC tests: (kind, N), fbstab_mpc_unit_tests.cc:15-148
+MPC_CASES = [("double_integrator", 2), ("double_integrator", 20),
+             ("servo_motor", 25), ("spacecraft", 40), ("copolymerization", 80)]
+
+
+def component_ocp(fb):
+    """The OCP of the reference's MPC component tests
+    (mpc_component_unit_tests.h:37-94): double integrator N=2 with E applied at
+    stage 0 as well (the solver-level fixture zeroes E(0))."""
+    dims, d = fb.problems.ocp_batch("double_integrator", 2)
+    N, nx, nu, nc = dims
+    d["E"][:nc * nx] = d["E"][nc * nx:2 * nc * nx]
+    return dims, d
