@@ -32,7 +32,7 @@ SYMBOLS = [
     "fbstab_mpc_batch_solve", "fbstab_mpc_batch_last_launches",
     "fbstab_mpc_batch_path", "fbstab_mpc_batch_component",
     "fbstab_ocp_dims", "fbstab_ocp_generate", "fbstab_ocp_generate_batch",
-    "fbstab_random_dense_qp",
+    "fbstab_random_dense_qp", "fbstab_fp64_peak",
 ]
 
 
@@ -112,6 +112,8 @@ def lib():
         L.fbstab_random_dense_qp.argtypes = (
             [C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] +
             [C.c_void_p] * 6 + [C.c_int])
+        L.fbstab_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -158,3 +160,10 @@ def validate_options(o):
 
 def device_count():
     return lib().fbstab_device_count()
+
+
+def fp64_peak(device=0):
+    """(DFMA, DMMA) measured FP64 peaks in TFLOP/s."""
+    a, b = C.c_double(), C.c_double()
+    check(lib().fbstab_fp64_peak(device, C.byref(a), C.byref(b)))
+    return a.value, b.value

@@ -119,6 +119,11 @@ const char* fbstab_last_error(void);
 /* Number of CUDA devices visible (0 if none / driver missing). */
 int fbstab_device_count(void);
 
+/* Measured FP64 peaks of `device` in TFLOP/s: a register-resident DFMA loop
+ * and an FP64 mma.sync (DMMA) loop over all SMs (roofline denominators; the
+ * driver's MEASURED_PEAKS.json has no FP64 figure). */
+int fbstab_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
+
 /* ---- dense QPs ----------------------------------------------------------- */
 typedef struct fbstab_dense_batch fbstab_dense_batch;
 

@@ -1,0 +1,447 @@
+"""GPU parity tests: the CUDA engine, called through the C-ABI, against the CPU
+oracle on identical inputs.
+
+Parity definition (BASELINE.json north_star): same exit flags, same iterate
+trajectory (newton / prox / line-search counts), solutions within 1e-8
+relative in FP64.  The FP64 arithmetic of the two sides differs only in
+summation order and FMA contraction, which leaves the trajectory unchanged on
+well-conditioned instances; where sigma = 1e-8 makes the Newton system so
+ill-conditioned that rounding alone moves an instance across a convergence
+threshold (documented in DESIGN.md: two builds of the *oracle itself*, with and
+without FMA, differ by +-1 iteration on ~4% of servo-motor instances), the
+tests bound the fraction of such instances and check them at the solver's own
+tolerance instead of hiding them.
+"""
+import numpy as np
+import pytest
+
+from util import (DENSE_CASES, DI2_L, DI2_V, DI2_Z, MPC_CASES, colmajor,
+                  component_ocp, dense_case, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+SOL_TOL = 1e-8  # relative, FP64 (north_star)
+
+
+def _same_traj(o_gpu, o_cpu):
+    return ((o_gpu["newton_iters"] == o_cpu["newton_iters"]) &
+            (o_gpu["prox_iters"] == o_cpu["prox_iters"]) &
+            (o_gpu["ls_backtracks"] == o_cpu["ls_backtracks"]))
+
+
+def _dense_data(fb, name):
+    H, f, G, h, A, b, flag = dense_case(name)
+    data = {"H": colmajor(H), "f": f, "G": colmajor(G), "h": h,
+            "A": colmajor(A), "b": b}
+    return data, (H, f, G, h, A, b), flag
+
+
+# ---- reference solver-level tests through the engine ------------------------
+@pytest.mark.parametrize("name", list(DENSE_CASES))
+def test_dense_reference_cases(fb, oracle, name):
+    """fbstab/test/fbstab_dense_unit_tests.cc:28-256 on the GPU."""
+    data, (H, f, G, h, A, b), flag = _dense_data(fb, name)
+    s = fb.FBstabDense(f.size, h.size, b.size)
+    s.update_options(fb.FBstabDense.default_options(abs_tol=1e-8, display_level=0))
+    out, (z, l, v, y) = s.solve(H, f, G, h, A, b)
+    assert fb.EXIT_FLAGS[int(out["eflag"])] == flag
+    assert out["status"] == 0
+    oo, (oz, ol, ov, oy), _ = oracle.Problem.dense(H, f, G, h, A, b).solve(
+        oracle.default_options(abs_tol=1e-8, display_level=0))
+    assert (out["newton_iters"], out["prox_iters"], out["ls_backtracks"]) == (
+        oo["newton_iters"], oo["prox_iters"], oo["ls_backtracks"])
+    if flag == "SUCCESS":
+        assert rel_err(z, oz) <= SOL_TOL and rel_err(v, ov) <= SOL_TOL
+        assert rel_err(y, oy) <= SOL_TOL
+        assert abs(out["residual"] - oo["residual"]) <= 1e-12
+    else:
+        # the certificate dx is returned (fbstab_algorithm-impl.h:209)
+        assert rel_err(z, oz) <= 1e-6 and rel_err(v, ov) <= 1e-6
+    if name == "FeasibleQP":
+        np.testing.assert_allclose(z, [0, -5], atol=1e-8)
+        np.testing.assert_allclose(v, [5, 0], atol=1e-8)
+    if name == "FeasibleQPwithEQ":
+        np.testing.assert_allclose(z, [0.25, 0.75], atol=1e-8)
+    if name == "DegenerateQP":
+        assert abs(z[0] - 1) <= 1e-8 and 1 <= z[1] <= 3
+        assert (np.linalg.norm(H @ z + f + A.T @ v) +
+                np.linalg.norm(np.minimum(y, v))) <= 1e-6
+
+
+@pytest.mark.parametrize("kind,N", MPC_CASES)
+def test_mpc_reference_cases(fb, oracle, kind, N):
+    """fbstab/test/fbstab_mpc_unit_tests.cc:15-148 on the GPU."""
+    dims, d = fb.problems.ocp_batch(kind, N)
+    s = fb.FBstabMpc(*dims)
+    s.update_options(fb.FBstabMpc.default_options(abs_tol=1e-8, display_level=0))
+    out, (z, l, v, y) = s.solve(d)
+    assert fb.EXIT_FLAGS[int(out["eflag"])] == "SUCCESS"
+    assert out["residual"] <= 1e-6
+    if (kind, N) == ("double_integrator", 2):
+        np.testing.assert_allclose(z, DI2_Z, atol=1e-8)
+        np.testing.assert_allclose(l, DI2_L, atol=1e-8)
+        np.testing.assert_allclose(v, DI2_V, atol=1e-8)
+    oo, (oz, ol, ov, oy), _ = oracle.Problem.mpc(
+        *dims, *[d[k] for k in fb.problems.MPC_FIELDS]).solve(
+            oracle.default_options(abs_tol=1e-8, display_level=0))
+    assert oo["flag"] == "SUCCESS"
+    # agreement at the solver tolerance always; 1e-8 when the trajectory matches
+    assert rel_err(z, oz) <= 1e-6 and rel_err(l, ol) <= 1e-6
+    if (out["newton_iters"], out["prox_iters"]) == (oo["newton_iters"], oo["prox_iters"]):
+        assert rel_err(z, oz) <= SOL_TOL
+    assert abs(int(out["newton_iters"]) - oo["newton_iters"]) <= 2
+    assert abs(int(out["prox_iters"]) - oo["prox_iters"]) <= 1
+
+
+# ---- component stages (per-kernel parity) -----------------------------------
+def test_dense_components_goldens(fb, oracle):
+    """Stale-but-valid component goldens, dense_unit_tests.h:100-213."""
+    H = np.array([[3., 1], [1, 1]])
+    A = np.array([[-1., 0], [0, 1]])
+    data = {"H": colmajor(H), "f": np.array([1., 6]), "G": np.zeros(0),
+            "h": np.zeros(0), "A": colmajor(A), "b": np.array([0., -1])}
+    s = fb.FBstabDense(2, 0, 2)
+    z, v = np.array([1., 5]), np.array([0.4, 2])
+    zb, vb = np.array([-5., 6]), np.array([-9., 1])
+    e = np.zeros(0)
+    y = np.zeros(2)
+    s.component(fb.capi.COMP_MARGIN, data, 1, z=z, dy=y)
+    np.testing.assert_array_equal(y, data["b"] - A @ z)
+    rz, rv, norms = np.zeros(2), np.zeros(2), np.zeros(8)
+    s.component(fb.capi.COMP_RESIDUAL, data, 1, z=z, l=e, v=v, y=y, zbar=zb,
+                lbar=e, vbar=vb, rz=rz, rl=e, rv=rv, norms=norms, sigma=0.5)
+    np.testing.assert_allclose(rz, [11.6, 13.5], atol=1e-14)
+    np.testing.assert_allclose(rv, [0.480683041678573, -8.88473245759182], atol=1e-14)
+    # natural residual norm of (8.6,14), (0.4,-6) -- dense_unit_tests.h:137-160
+    assert abs(norms[3] - np.hypot(8.6, 14.0)) <= 1e-13
+    r = (np.ones(2), e, np.ones(2))
+    dz, dv, dy = np.zeros(2), np.zeros(2), np.zeros(2)
+    gamma, mus = np.zeros(2), np.zeros(2)
+    st = np.zeros(1, dtype=np.int32)
+    s.component(fb.capi.COMP_NEWTON, data, 1, z=z, l=e, v=v, y=y, zbar=zb, lbar=e,
+                vbar=vb, rz=r[0].copy(), rl=e, rv=r[2].copy(), dz=dz, dl=e, dv=dv,
+                dy=dy, gamma=gamma, mus=mus, status=st, sigma=0.5)
+    assert st[0] == 0
+    K = np.block([[H + 0.5 * np.eye(2), A.T], [-np.diag(gamma) @ A, np.diag(mus)]])
+    assert np.linalg.norm(K @ np.concatenate([dz, dv]) - 1.0) <= 1e-12
+    np.testing.assert_allclose(dy, data["b"] - A @ dz, atol=1e-14)
+    rc, (odz, _, odv, ody), og, om = oracle.Problem.dense(
+        H, [1., 6], np.zeros((0, 2)), [], A, [0., -1]).linear_solve(
+            (z, e, v), (zb, e, vb), 0.5, r)
+    np.testing.assert_allclose(gamma, og, rtol=1e-15)
+    np.testing.assert_allclose(mus, om, rtol=1e-15)
+    np.testing.assert_allclose(dz, odz, rtol=1e-13)
+    np.testing.assert_allclose(dv, odv, rtol=1e-13)
+
+
+def test_dense_certificates(fb):
+    """dense_unit_tests.h:223-293."""
+    for name, dz, dv, want in (("InfeasibleQP", [0., 0], [1., 0, 0, 1, 1], 1),
+                               ("UnboundedQP", [0., 1], [0., 0, 0, 0], 2)):
+        data, (H, f, G, h, A, b), _ = _dense_data(fb, name)
+        s = fb.FBstabDense(f.size, h.size, b.size)
+        st = np.zeros(1, dtype=np.int32)
+        s.component(fb.capi.COMP_FEAS, data, 1, z=np.array(dz), l=np.zeros(0),
+                    v=np.array(dv), status=st, tol=1e-8)
+        assert st[0] == want
+
+
+def test_mpc_components_goldens(fb, oracle):
+    """mpc_component_unit_tests.h:316-461 on the GPU."""
+    dims, d = component_ocp(fb)
+    s = fb.FBstabMpc(*dims)
+    nz, nl, nv = s.nz, s.nl, s.nv
+    f = lambda n, a: a * np.ones(n)
+    p = oracle.Problem.mpc(*dims, *[d[k] for k in fb.problems.MPC_FIELDS])
+    # Variable margin / InnerResidual at sigma = 1  (:316-355)
+    y = np.zeros(nv)
+    s.component(fb.capi.COMP_MARGIN, d, 1, z=f(nz, 2), dy=y)
+    np.testing.assert_array_equal(y, p.margin(f(nz, 2)))
+    rz, rl, rv, norms = np.zeros(nz), np.zeros(nl), np.zeros(nv), np.zeros(8)
+    s.component(fb.capi.COMP_RESIDUAL, d, 1, z=f(nz, 2), l=f(nl, 2), v=f(nv, 2),
+                y=y, zbar=f(nz, -2), lbar=f(nl, -2), vbar=f(nv, -2), rz=rz, rl=rl,
+                rv=rv, norms=norms, sigma=1.0)
+    np.testing.assert_allclose(rz, [8, 8, 14, 8, 8, 14, 6, 4, 12], atol=1e-14)
+    np.testing.assert_allclose(rl, [6, 6, 2, 2, 2, 2], atol=1e-14)
+    np.testing.assert_allclose(
+        rv, [2.19167244568008, 2.19167244568008, 1.85147084275040,
+             1.85147084275040, 2.33389560518351, 1.62472628830921] * 3, atol=1e-14)
+    # Riccati recursion closes all KKT block rows (:386-461)
+    x = (f(nz, 1), f(nl, 2), f(nv, 4))
+    xb = (f(nz, 2), f(nl, 1), f(nv, 3))
+    r = (f(nz, 2.5), f(nl, 2.5), f(nv, 2.5))
+    yx = p.margin(x[0])
+    dz, dl, dv, dy = np.zeros(nz), np.zeros(nl), np.zeros(nv), np.zeros(nv)
+    gamma, mus = np.zeros(nv), np.zeros(nv)
+    st = np.zeros(1, dtype=np.int32)
+    s.component(fb.capi.COMP_NEWTON, d, 1, z=x[0], l=x[1], v=x[2], y=yx, zbar=xb[0],
+                lbar=xb[1], vbar=xb[2], rz=r[0].copy(), rl=r[1].copy(),
+                rv=r[2].copy(), dz=dz, dl=dl, dv=dv, dy=dy, gamma=gamma, mus=mus,
+                status=st, sigma=1.0)
+    assert st[0] == 0
+    r1 = p.gemv("H", dz, 1.0, 1.0, np.zeros(nz)) + dz
+    r1 = p.gemv("AT", dv, 1.0, 1.0, p.gemv("GT", dl, 1.0, 1.0, r1))
+    np.testing.assert_allclose(r[0] - r1, 0, atol=1e-13)
+    r2 = p.gemv("G", dz, -1.0, 1.0, np.zeros(nl)) + dl
+    np.testing.assert_allclose(r[1] - r2, 0, atol=1e-13)
+    r3 = gamma * p.gemv("A", dz, -1.0, 1.0, np.zeros(nv)) + mus * dv
+    np.testing.assert_allclose(r[2] - r3, 0, atol=1e-13)
+    r4 = p.axpy("b", 1.0, p.gemv("A", dz, -1.0, 1.0, np.zeros(nv)))
+    np.testing.assert_allclose(dy - r4, 0, atol=1e-13)
+    st[0] = 7
+    s.component(fb.capi.COMP_FEAS, d, 1, z=np.zeros(nz), l=np.zeros(nl),
+                v=np.zeros(nv), status=st, tol=1e-8)
+    assert st[0] == 0  # :359-373
+
+
+@pytest.mark.parametrize("sizes", [(32, 8, 64), (50, 10, 100), (5, 0, 7), (9, 3, 4)])
+def test_dense_component_parity_random(fb, oracle, sizes):
+    """Residual and Newton-step stages vs the oracle on random iterates."""
+    nz, nl, nv = sizes
+    B = 6
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=11)
+    rng = np.random.default_rng(5)
+    z, l, v = rng.normal(size=B * nz), rng.normal(size=B * nl), rng.normal(size=B * nv)
+    zb, lb, vb = rng.normal(size=B * nz), rng.normal(size=B * nl), rng.normal(size=B * nv)
+    s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+    y = np.zeros(B * nv)
+    s.component(fb.capi.COMP_MARGIN, d, B, z=z, dy=y)
+    rz, rl, rv, norms = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv), np.zeros(B * 8)
+    sigma = 1e-3
+    s.component(fb.capi.COMP_RESIDUAL, d, B, z=z, l=l, v=v, y=y, zbar=zb, lbar=lb,
+                vbar=vb, rz=rz, rl=rl, rv=rv, norms=norms, sigma=sigma)
+    dz, dl, dv, dy = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv), np.zeros(B * nv)
+    st = np.ones(B, dtype=np.int32)
+    s.component(fb.capi.COMP_NEWTON, d, B, z=z, l=l, v=v, y=y, zbar=zb, lbar=lb,
+                vbar=vb, rz=rz.copy(), rl=rl.copy(), rv=rv.copy(), dz=dz, dl=dl,
+                dv=dv, dy=dy, status=st, sigma=sigma)
+    assert (st == 0).all()
+    sz = s.field_sizes
+    for i in range(B):
+        sl = lambda a, n: a[i * n:(i + 1) * n]
+        p = oracle.Problem.dense(*[sl(d[k], sz[k]) for k in fb.problems.DENSE_FIELDS])
+        x = (sl(z, nz), sl(l, nl), sl(v, nv), sl(y, nv))
+        xb = (sl(zb, nz), sl(lb, nl), sl(vb, nv))
+        np.testing.assert_allclose(sl(y, nv), p.margin(x[0]), rtol=1e-13, atol=1e-13)
+        orz, orl, orv, on = p.residual("inner", x, xb, sigma=sigma)
+        np.testing.assert_allclose(sl(rz, nz), orz, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(sl(rl, nl), orl, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(sl(rv, nv), orv, rtol=1e-13, atol=1e-13)
+        _, _, _, onat = p.residual("penalized", x)
+        np.testing.assert_allclose(norms[i * 8:i * 8 + 3], on, rtol=1e-12)
+        np.testing.assert_allclose(norms[i * 8 + 7], np.sqrt((onat ** 2).sum()), rtol=1e-12)
+        rc, (odz, odl, odv, ody), _, _ = p.linear_solve(
+            x, xb, sigma, (sl(rz, nz), sl(rl, nl), sl(rv, nv)))
+        assert rc == 0
+        for a, b_ in ((sl(dz, nz), odz), (sl(dl, nl), odl), (sl(dv, nv), odv),
+                      (sl(dy, nv), ody)):
+            assert rel_err(a, b_) <= 1e-9
+
+
+# ---- batched solves vs the oracle ---------------------------------------------
+@pytest.mark.parametrize("sizes,B", [((32, 8, 64), 256), ((50, 10, 100), 32),
+                                     ((8, 0, 12), 64), ((20, 20, 5), 16)])
+def test_dense_batch_parity(fb, oracle, sizes, B):
+    nz, nl, nv = sizes
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=2)
+    s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+    z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, oz, ol, ov, oy = oracle.dense_solve_batch(
+        nz, nl, nv, *[d[k] for k in fb.problems.DENSE_FIELDS], nthreads=8)
+    assert (out["eflag"] == oo["eflag"]).all()
+    assert (out["eflag"] == 0).all() and (out["status"] == 0).all()
+    same = _same_traj(out, oo)
+    assert same.mean() >= 0.98, f"trajectory differs on {(~same).sum()} of {B}"
+    Z, OZ = z.reshape(B, nz), oz.reshape(B, nz)
+    V, OV = v.reshape(B, nv), ov.reshape(B, nv)
+    for i in range(B):
+        tol = SOL_TOL if same[i] else 1e-5
+        assert rel_err(Z[i], OZ[i]) <= tol, (i, rel_err(Z[i], OZ[i]))
+        assert rel_err(V[i], OV[i]) <= tol * 10
+    np.testing.assert_allclose(out["initial_residual"], oo["initial_residual"], rtol=1e-12)
+    # solve_time is stamped for host-buffer calls
+    assert (out["solve_time"] > 0).all()
+
+
+def test_dense_flag_masks(fb, oracle):
+    """Converged, infeasible and unbounded instances mixed in one batch: each
+    keeps its own exit flag (per-instance masks, no cross-talk)."""
+    nz, nl, nv = 16, 4, 24
+    kinds = [0, 1, 2, 0, 2, 1, 0, 0, 1, 2] * 3
+    parts = [fb.problems.random_dense_qp(nz, nl, nv, count=1, config=7, first=i, kind=k)
+             for i, k in enumerate(kinds)]
+    d = {k: np.concatenate([p[k] for p in parts]) for k in fb.problems.DENSE_FIELDS}
+    B = len(kinds)
+    s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+    z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, *_ = oracle.dense_solve_batch(nz, nl, nv, *[d[k] for k in fb.problems.DENSE_FIELDS])
+    want = {0: 0, 1: 3, 2: 4}
+    assert [int(e) for e in oo["eflag"]] == [want[k] for k in kinds]
+    assert [int(e) for e in out["eflag"]] == [want[k] for k in kinds]
+    assert (out["prox_iters"] == oo["prox_iters"]).all()
+
+
+def test_dense_batch_equals_looped_and_warm_start(fb):
+    """A batch of B equals B single solves bit for bit; a warm start at the
+    solution returns immediately (fbstab_algorithm-impl.h:162-169)."""
+    nz, nl, nv, B = 32, 8, 64, 24
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=2, first=1000)
+    s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+    z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+    out, y = s.solve_batch(d, z, l, v)
+    sz = s.field_sizes
+    s1 = fb.FBstabDense(nz, nl, nv, max_batch=1)
+    for i in (0, 7, B - 1):
+        di = {k: d[k][i * sz[k]:(i + 1) * sz[k]].copy() for k in d}
+        zi, li, vi = np.zeros(nz), np.zeros(nl), np.zeros(nv)
+        oi, yi = s1.solve_batch(di, zi, li, vi)
+        assert zi.tobytes() == z[i * nz:(i + 1) * nz].tobytes()
+        assert vi.tobytes() == v[i * nv:(i + 1) * nv].tobytes()
+        assert yi.tobytes() == y[i * nv:(i + 1) * nv].tobytes()
+        assert oi["newton_iters"][0] == out["newton_iters"][i]
+    z2, l2, v2 = z.copy(), l.copy(), v.copy()
+    out2, _ = s.solve_batch(d, z2, l2, v2)
+    assert (out2["eflag"] == 0).all()
+    assert (out2["newton_iters"] == 0).all() and (out2["prox_iters"] == 0).all()
+    assert z2.tobytes() == z.tobytes()
+
+
+def test_dense_options_and_iteration_caps(fb, oracle):
+    """max_newton_iters cap -> MAXITERATIONS with the better of xi/xk
+    (fbstab_algorithm-impl.h:188-199); reliable options; tight tolerance."""
+    nz, nl, nv, B = 12, 3, 20, 16
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=9)
+    s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+    for make in (lambda m: m.default_options(max_newton_iters=3),
+                 lambda m: m.reliable_options(),
+                 lambda m: m.default_options(abs_tol=1e-11, nonmonotone_linesearch=0,
+                                             check_feasibility=0)):
+        s.update_options(make(fb.FBstabDense))
+        z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+        out, y = s.solve_batch(d, z, l, v)
+        oo, oz, ol, ov, oy = oracle.dense_solve_batch(
+            nz, nl, nv, *[d[k] for k in fb.problems.DENSE_FIELDS], opts=make(oracle))
+        assert (out["eflag"] == oo["eflag"]).all()
+        assert (out["newton_iters"] == oo["newton_iters"]).all()
+        assert (out["prox_iters"] == oo["prox_iters"]).all()
+        # residuals agree to rounding: far below the tolerance they were solved to
+        np.testing.assert_allclose(out["residual"], oo["residual"], rtol=1e-5, atol=1e-11)
+        assert rel_err(z, oz) <= 1e-7
+
+
+@pytest.mark.parametrize("kind,N,B,rho", [("double_integrator", 50, 96, 0.1),
+                                         ("servo_motor", 50, 96, 0.02),
+                                         ("double_integrator", 10, 64, 0.6),
+                                         ("copolymerization", 20, 16, 0.05),
+                                         ("spacecraft", 12, 16, 0.0)])
+def test_mpc_batch_parity(fb, oracle, kind, N, B, rho):
+    dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=rho)
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    z, l, v = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, oz, ol, ov, oy = oracle.mpc_solve_batch(
+        *dims, [d[k] for k in fb.problems.MPC_FIELDS], nthreads=8)
+    assert (out["status"] == 0).all()
+    assert (out["eflag"] == oo["eflag"]).all(), (out["eflag"], oo["eflag"])
+    same = _same_traj(out, oo)
+    # see the module docstring: rounding-level trajectory sensitivity at sigma=1e-8
+    assert same.mean() >= 0.85, f"trajectory differs on {(~same).sum()} of {B}"
+    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 3
+    Z, OZ = z.reshape(B, -1), oz.reshape(B, -1)
+    ok = out["eflag"] == 0
+    for i in np.nonzero(ok)[0]:
+        tol = SOL_TOL if same[i] else 1e-4
+        assert rel_err(Z[i], OZ[i]) <= tol, (i, rel_err(Z[i], OZ[i]), same[i])
+
+
+def test_mpc_maxiter_matches_reference_behaviour(fb, oracle):
+    """Spacecraft N=100 with default options runs into the Newton cap in the
+    reference algorithm (SURVEY.md 8(d) open issue): the engine must report
+    the same MAXITERATIONS, not a made-up success."""
+    dims, d = fb.problems.ocp_batch("spacecraft", 100, count=2, config=4, rho=0.01)
+    s = fb.FBstabMpc(*dims, max_batch=2)
+    z, l, v = np.zeros(2 * s.nz), np.zeros(2 * s.nl), np.zeros(2 * s.nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, *_ = oracle.mpc_solve_batch(*dims, [d[k] for k in fb.problems.MPC_FIELDS])
+    assert (oo["eflag"] == 2).all() and (out["eflag"] == 2).all()
+    assert (out["newton_iters"] == 200).all()
+
+
+# ---- full-size configs through size-independent properties --------------------
+def _kkt_check_dense(d, nz, nl, nv, z, l, v, y, idx):
+    worst = 0.0
+    for i in idx:
+        H = d["H"][i * nz * nz:(i + 1) * nz * nz].reshape(nz, nz).T
+        G = d["G"][i * nl * nz:(i + 1) * nl * nz].reshape(nz, nl).T
+        A = d["A"][i * nv * nz:(i + 1) * nv * nz].reshape(nz, nv).T
+        f, h, b = (d["f"][i * nz:(i + 1) * nz], d["h"][i * nl:(i + 1) * nl],
+                   d["b"][i * nv:(i + 1) * nv])
+        zi, li, vi, yi = (z[i * nz:(i + 1) * nz], l[i * nl:(i + 1) * nl],
+                          v[i * nv:(i + 1) * nv], y[i * nv:(i + 1) * nv])
+        r = np.concatenate([H @ zi + f + G.T @ li + A.T @ vi, h - G @ zi,
+                            np.minimum(yi, vi), yi - (b - A @ zi)])
+        worst = max(worst, np.linalg.norm(r))
+    return worst
+
+
+def test_dense_config2_full_size(fb):
+    """BASELINE config 2: 65,536 QPs nz=32 nl=8 nv=64.  Every instance must
+    report SUCCESS with its own residual below tolerance, and the KKT
+    conditions are re-verified independently (numpy) on a sample."""
+    nz, nl, nv, B = 32, 8, 64, 65536
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=2)
+    s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+    z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+    out, y = s.solve_batch(d, z, l, v)
+    assert (out["eflag"] == 0).all() and (out["status"] == 0).all()
+    assert (out["residual"] <= 1e-6 * 1.01).all()
+    assert out["newton_iters"].min() >= 5 and out["newton_iters"].max() <= 60
+    assert (v >= 0).all()
+    idx = np.random.default_rng(0).choice(B, 200, replace=False)
+    assert _kkt_check_dense(d, nz, nl, nv, z, l, v, y, idx) <= 2e-6
+
+
+def test_dense_config5_sample(fb, oracle):
+    """BASELINE config 5 shape (nz=512 nl=128 nv=1024), a small batch vs the
+    oracle plus the independent KKT check."""
+    nz, nl, nv, B = 512, 128, 1024, 3
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=5)
+    s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+    z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+    out, y = s.solve_batch(d, z, l, v)
+    assert (out["eflag"] == 0).all()
+    assert _kkt_check_dense(d, nz, nl, nv, z, l, v, y, range(B)) <= 2e-6
+    oo, oz, *_ = oracle.dense_solve_batch(
+        nz, nl, nv, *[d[k][:sz] for k, sz in
+                      zip(fb.problems.DENSE_FIELDS,
+                          (nz * nz, nz, nl * nz, nl, nv * nz, nv))], variant=2)
+    assert out["newton_iters"][0] == oo["newton_iters"][0]
+    assert out["prox_iters"][0] == oo["prox_iters"][0]
+    assert rel_err(z[:nz], oz) <= SOL_TOL
+
+
+def test_device_pointers_and_stream(fb):
+    """Device-resident buffers (torch CUDA tensors) are used in place and the
+    call is asynchronous on the given stream; results equal the host path."""
+    import torch
+    nz, nl, nv, B = 32, 8, 64, 512
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=2, first=5000)
+    s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+    z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+    out, y = s.solve_batch(d, z, l, v)
+    dev = torch.device("cuda:0")
+    dd = {k: torch.from_numpy(a).to(dev) for k, a in d.items()}
+    zt = torch.zeros(B * nz, dtype=torch.float64, device=dev)
+    lt = torch.zeros(B * nl, dtype=torch.float64, device=dev)
+    vt = torch.zeros(B * nv, dtype=torch.float64, device=dev)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        out_t, yt = s.solve_batch(dd, zt, lt, vt, stream=st.cuda_stream)
+    st.synchronize()
+    assert zt.cpu().numpy().tobytes() == z.tobytes()
+    assert yt.cpu().numpy().tobytes() == y.tobytes()
+    got = np.frombuffer(out_t.cpu().numpy().tobytes(), dtype=fb.OUT_DTYPE)
+    assert (got["newton_iters"] == out["newton_iters"]).all()
+    assert (got["solve_time"] < 0).all()  # asynchronous call: not timed
