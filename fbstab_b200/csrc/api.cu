@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "dense_problem.cuh"
-#include "dense_small.cuh"
+#include "dense_small.h"
 #include "engine.cuh"
 #include "fbstab_b200.h"
 #include "mpc_problem.cuh"

@@ -1,0 +1,796 @@
+// dense_small.cu -- warp-per-problem FBstab for small dense QPs
+// (nz <= 32, nl <= 8, nv <= 64; BASELINE config 2 is exactly 32/8/64).
+//
+// One warp owns one QP instance for its whole solve:
+//  * the problem data (H, A, G, f, h, b: 26.8 KB) is staged ONCE into shared
+//    memory (zero padded to 32/8/64, rows contiguous + padded leading dimension
+//    34 so that row reads, column reads and the DMMA fragment reads are all
+//    bank-conflict free or at worst 2-way);
+//  * every iterate / residual vector lives in registers: lane j owns entry j
+//    of z-type vectors, lanes 0..7 own l, lane k owns rows k and k+32 of
+//    v-type vectors;
+//  * E = H + sigma I + A' Gamma A is accumulated on the FP64 tensor cores
+//    (mma.sync.m8n8k4.f64, 160 DMMAs for the 10 lower 8x8 blocks);
+//  * the KKT matrix K = [E G'; G -sigma I] is eliminated in registers: lane i
+//    holds the full symmetric row i of E (so after elimination it owns row i
+//    of L *and* column i of L'), the G block is held column-wise (lane j owns
+//    column j), pivot columns are broadcast through a 40-double shared buffer,
+//    and the right-hand side rides along as a ninth row, which fuses the
+//    forward substitution into the factorisation;
+//  * the 8x8 Schur complement -sigma I - X' D^-1 X is formed with 16 DMMAs and
+//    factored by lanes 0..7.
+// Converged instances retire and the warp pulls the next index from a global
+// atomic counter (persistent kernel, no host round trips).
+//
+// Follows the same reference code as engine.cuh / dense_problem.cuh
+// (fbstab_algorithm-impl.h:113-304, dense_cholesky_solver.cc:32-148,
+// full_residual.cc:49-118, full_feasibility.cc:25-88).
+#include "common.cuh"
+#include "dense_small.h"
+#include "engine.cuh"
+
+namespace fbs {
+
+namespace small {
+
+constexpr int NZ = 32;    // padded sizes
+constexpr int NL = 8;
+constexpr int NV = 64;
+constexpr int NVR = NV / 32;
+constexpr int LD = 34;    // leading dimension of Hs/As/Gs rows
+constexpr int kWarpsPerCta = 2;
+
+// shared-memory layout of one warp's slab (in doubles)
+constexpr int OFF_H = 0;                       // Hs[j + LD*i] = H(i,j)
+constexpr int OFF_A = OFF_H + NZ * LD;         // As[j + LD*k] = A(k,j)
+constexpr int OFF_G = OFF_A + NV * LD;         // Gs[j + LD*r] = G(r,j)
+constexpr int OFF_F = OFF_G + NL * LD;         // f(32) h(8) b(64)
+constexpr int OFF_HV = OFF_F + NZ;
+constexpr int OFF_B = OFF_HV + NL;
+constexpr int OFF_ZB = OFF_B + NV;             // broadcast copies: z(32) l(8) v(64)
+constexpr int OFF_LB = OFF_ZB + NZ;
+constexpr int OFF_VB = OFF_LB + NL;
+constexpr int OFF_COL = OFF_VB + NV;           // 2 x (32 + 10 [+pad]) pivot-column buffers
+constexpr int COL_STRIDE = 44;
+constexpr int OFF_SCR = OFF_COL + 2 * COL_STRIDE;  // transposition / Schur scratch
+constexpr int SCR_SIZE = 480;  // >= 8*LD (transposition), >= 472 (Schur: X 320, 1/d 32, S 64, T 8)
+constexpr int SLAB = OFF_SCR + SCR_SIZE;
+static_assert(SLAB % 2 == 0, "slab must keep 16-byte alignment");
+static_assert(OFF_A % 2 == 0 && OFF_G % 2 == 0 && OFF_ZB % 2 == 0 &&
+                  OFF_VB % 2 == 0 && OFF_COL % 2 == 0 && OFF_SCR % 2 == 0,
+              "LDS.128 targets must be 16-byte aligned");
+
+struct Args {
+  int nz, nl, nv, batch;
+  const double *H, *f, *G, *h, *A, *b;
+  double *z, *l, *v, *y;
+  fbstab_out* out;
+  int* counter;
+  fbstab_options opts;
+};
+
+struct V {  // primal-dual iterate in registers
+  double z, l, v[NVR], y[NVR];
+};
+struct R {  // residual in registers
+  double z, l, v[NVR];
+};
+
+__device__ __forceinline__ double2 lds2(const double* p) {
+  return *reinterpret_cast<const double2*>(p);
+}
+__device__ __forceinline__ void sts2(double* p, double a, double b) {
+  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double bcast(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+
+struct Warp {
+  double* s;  // this warp's slab
+  int lane;
+  int nz, nl, nv;
+  // linear-solver state kept between factor() and solve()
+  double gamma[NVR], mus[NVR];
+
+  // ---- products -------------------------------------------------------------
+  __device__ __forceinline__ void publish(const V& x) {
+    __syncwarp();
+    s[OFF_ZB + lane] = x.z;
+    if (lane < NL) s[OFF_LB + lane] = x.l;
+#pragma unroll
+    for (int m = 0; m < NVR; m++) s[OFF_VB + lane + 32 * m] = x.v[m];
+    __syncwarp();
+  }
+  // (H zb)[lane]
+  __device__ __forceinline__ double Hz() const {
+    const double* hr = s + OFF_H + LD * lane;
+    const double* zb = s + OFF_ZB;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NZ; j += 2) {
+      const double2 hh = lds2(hr + j);
+      const double2 zz = lds2(zb + j);
+      s0 = fma(hh.x, zz.x, s0);
+      s1 = fma(hh.y, zz.y, s1);
+    }
+    return s0 + s1;
+  }
+  // (G' lb)[lane]
+  __device__ __forceinline__ double GTl() const {
+    const double* g = s + OFF_G + lane;
+    const double* lb = s + OFF_LB;
+    double s0 = 0.0;
+#pragma unroll
+    for (int r = 0; r < NL; r += 2) {
+      const double2 ll = lds2(lb + r);
+      s0 = fma(g[LD * r], ll.x, s0);
+      s0 = fma(g[LD * (r + 1)], ll.y, s0);
+    }
+    return s0;
+  }
+  // (A' vb)[lane]
+  __device__ __forceinline__ double ATv() const {
+    const double* a = s + OFF_A + lane;
+    const double* vb = s + OFF_VB;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; k += 4) {
+      const double2 v0 = lds2(vb + k);
+      const double2 v1 = lds2(vb + k + 2);
+      s0 = fma(a[LD * k], v0.x, s0);
+      s1 = fma(a[LD * (k + 1)], v0.y, s1);
+      s2 = fma(a[LD * (k + 2)], v1.x, s2);
+      s3 = fma(a[LD * (k + 3)], v1.y, s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+  }
+  // (G zb)[lane % 8], same value in the four lanes sharing lane % 8
+  __device__ __forceinline__ double Gz() const {
+    const int r = lane & 7, g = lane >> 3;
+    const double* gr = s + OFF_G + LD * r + 8 * g;
+    const double* zb = s + OFF_ZB + 8 * g;
+    double s0 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const double2 gg = lds2(gr + j);
+      const double2 zz = lds2(zb + j);
+      s0 = fma(gg.x, zz.x, s0);
+      s0 = fma(gg.y, zz.y, s0);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    return s0;
+  }
+  // (A zb)[lane + 32 m]
+  __device__ __forceinline__ void Az(double (&o)[NVR]) const {
+    const double* zb = s + OFF_ZB;
+#pragma unroll
+    for (int m = 0; m < NVR; m++) {
+      const double* ar = s + OFF_A + LD * (lane + 32 * m);
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NZ; j += 2) {
+        const double2 aa = lds2(ar + j);
+        const double2 zz = lds2(zb + j);
+        s0 = fma(aa.x, zz.x, s0);
+        s1 = fma(aa.y, zz.y, s1);
+      }
+      o[m] = s0 + s1;
+    }
+  }
+
+  // ---- fused residual evaluation (see engine.cuh) ---------------------------
+  __device__ __forceinline__ EvalOut evaluate(const V& x, const V& xbar,
+                                              double sigma, double alpha, R* ri) {
+    publish(x);
+    double tz = s[OFF_F + lane] + Hz();
+    tz += GTl();
+    tz += ATv();
+    const double gz = Gz();
+    const double tl = (lane < NL) ? s[OFF_HV + lane] - gz : 0.0;
+    double si = 0.0, so = 0.0;
+    {
+      const double r = tz + sigma * (x.z - xbar.z);
+      ri->z = r;
+      si = r * r;
+      so = tz * tz;
+    }
+    {
+      const double r = tl + sigma * (x.l - xbar.l);
+      ri->l = r;
+      si = fma(r, r, si);
+      so = fma(tl, tl, so);
+    }
+#pragma unroll
+    for (int m = 0; m < NVR; m++) {
+      const double y = x.y[m], v = x.v[m];
+      const double ys = y + sigma * (v - xbar.v[m]);
+      const double r = pfb(ys, v, alpha);
+      ri->v[m] = r;
+      si = fma(r, r, si);
+      const double n = pnr(y, v, alpha);
+      so = fma(n, n, so);
+    }
+    EvalOut e;
+    e.Ei = sqrt(warp_sum(si));
+    e.Eo = sqrt(warp_sum(so));
+    return e;
+  }
+
+  // ---- Newton step: LinearSolver::Initialize + ::Solve fused -----------------
+  // Solves V(x,xbar,sigma) dx = -ri.  Returns false on a zero / NaN pivot.
+  __device__ __forceinline__ bool newton_step(const V& x, const V& xbar, double sigma,
+                              double alpha, const R& ri, V* dx) {
+    const int r8 = lane >> 2, c4 = lane & 3;
+    double Gam[NVR], r2[NVR];
+#pragma unroll
+    for (int m = 0; m < NVR; m++) {
+      const double ys = x.y[m] + sigma * (x.v[m] - xbar.v[m]);
+      pfb_barrier(ys, x.v[m], alpha, sigma, &gamma[m], &mus[m]);
+      Gam[m] = gamma[m] / mus[m];
+      r2[m] = (-ri.v[m]) / mus[m];
+    }
+    // r1z = -rz - A'(rv/mus) ; Gamma -> shared for the DMMA operand scaling
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < NVR; m++) {
+      s[OFF_VB + lane + 32 * m] = r2[m];
+      s[OFF_SCR + lane + 32 * m] = Gam[m];
+    }
+    __syncwarp();
+    double u = (-ri.z) - ATv();
+
+    // E (lower 8x8 blocks) on the FP64 tensor cores
+    double C[4][4][2];
+#pragma unroll
+    for (int I = 0; I < 4; I++)
+#pragma unroll
+      for (int J = 0; J <= I; J++) {
+        const double2 hh = lds2(s + OFF_H + LD * (8 * I + r8) + 8 * J + 2 * c4);
+        C[I][J][0] = hh.x + ((I == J && r8 == 2 * c4) ? sigma : 0.0);
+        C[I][J][1] = hh.y + ((I == J && r8 == 2 * c4 + 1) ? sigma : 0.0);
+      }
+#pragma unroll 4
+    for (int kc = 0; kc < NV / 4; kc++) {
+      const double* ar = s + OFF_A + LD * (4 * kc + c4) + r8;
+      const double gk = s[OFF_SCR + 4 * kc + c4];
+      double a[4], b[4];
+#pragma unroll
+      for (int X = 0; X < 4; X++) {
+        a[X] = ar[8 * X];
+        b[X] = gk * a[X];
+      }
+#pragma unroll
+      for (int I = 0; I < 4; I++)
+#pragma unroll
+        for (int J = 0; J <= I; J++) dmma(C[I][J][0], C[I][J][1], a[I], b[J]);
+    }
+    // fragments -> full symmetric rows: lane i gets a[j] = E(i,j) for all j
+    double a[NZ];
+#pragma unroll
+    for (int I = 0; I < 4; I++) {
+      __syncwarp();
+#pragma unroll
+      for (int J = 0; J <= I; J++)
+        sts2(s + OFF_SCR + LD * r8 + 8 * J + 2 * c4, C[I][J][0], C[I][J][1]);
+      __syncwarp();
+      if ((lane >> 3) == I) {
+        const double* row = s + OFF_SCR + LD * (lane & 7);
+#pragma unroll
+        for (int j = 0; j < NZ; j += 2) {
+          if (j < 8 * (I + 1)) {
+            const double2 t = lds2(row + j);
+            a[j] = t.x;
+            a[j + 1] = t.y;
+          }
+        }
+      } else if ((lane >> 3) < I) {
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) a[8 * I + rr] = s[OFF_SCR + LD * rr + lane];
+      }
+    }
+    // G block column-wise (lane j owns column j) + the rhs as a ninth row
+    double g[NL + 1];
+#pragma unroll
+    for (int r = 0; r < NL; r++) g[r] = s[OFF_G + LD * r + lane];
+    g[NL] = u;
+
+    // right-looking LDL' of [E G'; G .] with pivot-column broadcast
+    bool ok = true;
+    double dinv = 0.0;  // 1/d_lane
+#pragma unroll
+    for (int k = 0; k < NZ; k++) {
+      double* cb = s + OFF_COL + COL_STRIDE * (k & 1);
+      const double ck = a[k];
+      cb[lane] = ck;
+      if (lane == k) {
+#pragma unroll
+        for (int r = 0; r < NL + 1; r += 2)
+          sts2(cb + 32 + r, g[r], (r + 1 < NL + 1) ? g[r + 1] : 0.0);
+      }
+      __syncwarp();
+      const double d = cb[k];
+      if (!(fabs(d) > 0.0)) ok = false;
+      const double rd = 1.0 / d;
+      if (lane == k) dinv = rd;
+      const double lik = (lane > k) ? ck * rd : 0.0;
+      if ((k + 1) & 1) {  // odd start: one scalar load keeps the pairs aligned
+        if (k + 1 < NZ) a[k + 1] = fma(-lik, cb[k + 1], a[k + 1]);
+#pragma unroll
+        for (int j = k + 2; j < NZ; j += 2) {
+          const double2 cj = lds2(cb + j);
+          a[j] = fma(-lik, cj.x, a[j]);
+          a[j + 1] = fma(-lik, cj.y, a[j + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = k + 1; j < NZ; j += 2) {
+          const double2 cj = lds2(cb + j);
+          a[j] = fma(-lik, cj.x, a[j]);
+          a[j + 1] = fma(-lik, cj.y, a[j + 1]);
+        }
+      }
+      if (lane > k) a[k] = lik;
+#pragma unroll
+      for (int r = 0; r < NL + 1; r += 2) {
+        const double2 xr = lds2(cb + 32 + r);
+        g[r] = fma(-lik, xr.x, g[r]);
+        if (r + 1 < NL + 1) g[r + 1] = fma(-lik, xr.y, g[r + 1]);
+      }
+    }
+    // lane k now holds d_k (a[k]), x_k = (L^-1 G')(k,:) in g[0..7], u_k = g[8]
+    u = g[NL];
+
+    // Schur complement S = -sigma I - X' D^-1 X and rhs c - X' D^-1 u (DMMA)
+    __syncwarp();
+    {
+      double* xs = s + OFF_SCR;  // Xs[r + 10*k], r = 0..8 ; dinv at 320..351
+#pragma unroll
+      for (int r = 0; r < NL + 1; r += 2)
+        sts2(xs + 10 * lane + r, g[r], (r + 1 < NL + 1) ? g[r + 1] : 0.0);
+      xs[320 + lane] = dinv;
+    }
+    __syncwarp();
+    double S0 = 0.0, S1 = 0.0, T0 = 0.0, T1 = 0.0;
+#pragma unroll
+    for (int kc = 0; kc < NZ / 4; kc++) {
+      const double* xs = s + OFF_SCR;
+      const int k = 4 * kc + c4;
+      const double xe = xs[10 * k + r8];
+      const double ue = xs[10 * k + NL];
+      const double di = xs[320 + k];
+      const double ae = xe * di;
+      dmma(S0, S1, ae, xe);
+      dmma(T0, T1, ae, ue);
+    }
+    // lane (r8,c4) holds S(r8, 2c4+{0,1}) (before the sign/-sigma) and
+    // T(r8,*) = (X' D^-1 u)(r8).  Gather row r into lane r (r < 8).
+    __syncwarp();
+    {
+      double* sc = s + OFF_SCR;
+      sts2(sc + 400 + 8 * r8 + 2 * c4, S0, S1);
+      if (c4 == 0) sc[464 + r8] = T0;
+    }
+    __syncwarp();
+    double dl = 0.0;
+    {
+      // 8x8 LDL' by lanes 0..7 (lane r = row r); all lanes execute, rows >= 8 idle
+      const double* sc = s + OFF_SCR;
+      const int r = lane & 7;
+      double srow[NL];
+#pragma unroll
+      for (int j = 0; j < NL; j++) srow[j] = -sc[400 + 8 * r + j] - ((j == r) ? sigma : 0.0);
+      double rhs = ((lane < NL) ? ri.l : 0.0) - sc[464 + r];
+      // rows of padded equality constraints: identity block keeps them inert
+      double dsi = 0.0;
+#pragma unroll
+      for (int k = 0; k < NL; k++) {
+        const double dk = bcast(srow[k], k);
+        if (!(fabs(dk) > 0.0)) ok = false;
+        const double rdk = 1.0 / dk;
+        if (r == k) dsi = rdk;
+        const double lrk = (r > k) ? srow[k] * rdk : 0.0;
+#pragma unroll
+        for (int j = k + 1; j < NL; j++) {
+          const double cj = bcast(srow[k], j);  // S(j,k) by symmetry
+          srow[j] = fma(-lrk, cj, srow[j]);
+        }
+        const double rk = bcast(rhs, k);
+        rhs = fma(-lrk, rk, rhs);
+        if (r > k) srow[k] = lrk;
+      }
+      // backward: dl_r = (rhs_r - sum_{k>r} srow_r[k] dl_k) / d_r
+      // (srow_r[k], k>r, is d_r * L(k,r) thanks to the symmetric elimination)
+      double acc = rhs;
+#pragma unroll
+      for (int k = NL - 1; k >= 0; k--) {
+        const double fin = acc * dsi;
+        const double dk = bcast(fin, k);
+        if (r == k) dl = dk;
+        if (r < k) acc = fma(-srow[k], dk, acc);
+      }
+      if (lane >= NL) dl = 0.0;
+    }
+    // w = u - X dl ; backward substitution L' dz = D^-1 w with the upper part
+    // of the symmetric rows (a[k], k > lane, equals d_lane * L(k,lane)).
+    double acc = u;
+#pragma unroll
+    for (int r = 0; r < NL; r++) acc = fma(-g[r], bcast(dl, r), acc);
+    double dz = 0.0;
+#pragma unroll
+    for (int k = NZ - 1; k >= 0; k--) {
+      const double fin = acc * dinv;
+      const double dk = bcast(fin, k);
+      if (lane == k) dz = dk;
+      if (lane < k) acc = fma(-a[k], dk, acc);
+    }
+    dx->z = dz;
+    dx->l = dl;
+    // dv = (rv + gamma .* (A dz)) ./ mus ; dy = b - A dz
+    __syncwarp();
+    s[OFF_ZB + lane] = dz;
+    __syncwarp();
+    double adz[NVR];
+    Az(adz);
+#pragma unroll
+    for (int m = 0; m < NVR; m++) {
+      dx->v[m] = (gamma[m] * adz[m] + (-ri.v[m])) / mus[m];
+      dx->y[m] = s[OFF_B + lane + 32 * m] - adz[m];
+    }
+    return ok;
+  }
+
+  // FullFeasibility::CheckFeasibility on dx
+  __device__ __forceinline__ int feasibility(const V& dx, double tol) {
+    publish(dx);
+    double adz[NVR];
+    Az(adz);
+    double d1 = -INFINITY;
+#pragma unroll
+    for (int m = 0; m < NVR; m++)
+      if (lane + 32 * m < nv) d1 = fmax(d1, adz[m]);
+    const double gz = Gz();  // shuffles inside: every lane must call it
+    const double d2 = (lane < NL) ? fabs(gz) : 0.0;
+    const double d3 = fabs(Hz());
+    const double w = warp_max(fabs(dx.z));
+    const double d4 = warp_sum(s[OFF_F + lane] * dx.z);
+    const double p1 = warp_max(fabs(ATv() + GTl()));
+    double p2 = (lane < NL) ? s[OFF_HV + lane] * dx.l : 0.0;
+    double umax = fabs(dx.l);
+#pragma unroll
+    for (int m = 0; m < NVR; m++) {
+      p2 = fma(s[OFF_B + lane + 32 * m], dx.v[m], p2);
+      umax = fmax(umax, fabs(dx.v[m]));
+    }
+    p2 = warp_sum(p2);
+    umax = warp_max(umax);
+    const double D1 = warp_max(d1), D2 = warp_max(d2), D3 = warp_max(d3);
+    const bool dual_inf = (D1 <= w * tol) && (D2 <= tol * w) && (D3 <= tol * w) &&
+                          (d4 < 0.0) && (w > 1e-14);
+    const bool primal_inf = (p1 <= tol * umax) && (p2 < 0.0);
+    return (primal_inf ? 1 : 0) + (dual_inf ? 2 : 0);
+  }
+
+  // ---- data staging ----------------------------------------------------------
+  __device__ __forceinline__ void load(const Args& a, int inst) {
+    __syncwarp();
+    for (int e = lane; e < SLAB; e += 32) s[e] = 0.0;
+    __syncwarp();
+    const double* H = a.H + (size_t)inst * nz * nz;
+    for (int e = lane; e < nz * nz; e += 32) {
+      const int i = e % nz, j = e / nz;
+      s[OFF_H + LD * i + j] = H[e];
+    }
+    const double* A = a.A + (size_t)inst * nv * nz;
+    for (int e = lane; e < nv * nz; e += 32) {
+      const int k = e % nv, j = e / nv;
+      s[OFF_A + LD * k + j] = A[e];
+    }
+    const double* G = a.G + (size_t)inst * nl * nz;
+    for (int e = lane; e < nl * nz; e += 32) {
+      const int r = e % nl, j = e / nl;
+      s[OFF_G + LD * r + j] = G[e];
+    }
+    if (lane < nz) s[OFF_F + lane] = a.f[(size_t)inst * nz + lane];
+    if (lane < nl) s[OFF_HV + lane] = a.h[(size_t)inst * nl + lane];
+    for (int k = lane; k < nv; k += 32) s[OFF_B + k] = a.b[(size_t)inst * nv + k];
+    __syncwarp();
+  }
+};
+
+__device__ __forceinline__ void v_axpy(const Warp& w, const V& src, double a,
+                                       const V& dx, V* dst) {
+  dst->z = src.z + a * dx.z;
+  dst->l = src.l + a * dx.l;
+#pragma unroll
+  for (int m = 0; m < NVR; m++) {
+    dst->v[m] = src.v[m] + a * dx.v[m];
+    const double y = src.y[m] + a * dx.y[m];
+    dst->y[m] = y + (-a) * w.s[OFF_B + w.lane + 32 * m];
+  }
+}
+
+// FBstabAlgorithm::Solve for one instance, executed by one warp (the same
+// state machine as engine.cuh::solve_instance, with the iterates in registers).
+__device__ __forceinline__ void solve_one(Warp& w, const Args& A, int inst) {
+  const fbstab_options& o = A.opts;
+  const int lane = w.lane;
+  const double sigma = o.sigma0, alpha = o.alpha;
+  V xk, xi, xp, dx;
+  R ri;
+  xk.z = (lane < w.nz) ? A.z[(size_t)inst * w.nz + lane] : 0.0;
+  xk.l = (lane < w.nl) ? A.l[(size_t)inst * w.nl + lane] : 0.0;
+#pragma unroll
+  for (int m = 0; m < NVR; m++)
+    xk.v[m] = (lane + 32 * m < w.nv) ? A.v[(size_t)inst * w.nv + lane + 32 * m] : 0.0;
+  // forcing norm and margin y = b - A z
+  double fn = w.s[OFF_F + lane] * w.s[OFF_F + lane];
+  if (lane < NL) fn = fma(w.s[OFF_HV + lane], w.s[OFF_HV + lane], fn);
+#pragma unroll
+  for (int m = 0; m < NVR; m++)
+    fn = fma(w.s[OFF_B + lane + 32 * m], w.s[OFF_B + lane + 32 * m], fn);
+  const double combo_tol = o.abs_tol + o.rel_tol * (1.0 + sqrt(warp_sum(fn)));
+  w.publish(xk);
+  {
+    double az[NVR];
+    w.Az(az);
+#pragma unroll
+    for (int m = 0; m < NVR; m++) xk.y[m] = w.s[OFF_B + lane + 32 * m] - az[m];
+  }
+  double dx_norm = sqrt((double)w.nz + (double)w.nl + (double)w.nv);
+  int eflag = FBSTAB_MAXITERATIONS, status = FBSTAB_STATUS_OK;
+  int newton = 0, prox = 0, backtracks = 0, evals = 0;
+  double E0 = 0.0, Ek = 0.0, last_rk = 0.0, inner_tol = 0.0;
+  int which = 0;  // 0: xk, 1: xi, 2: dx is the result
+  bool done = false;
+
+  for (int k = 0; k < o.max_prox_iters && !done; k++) {
+    EvalOut e = w.evaluate(xk, xk, sigma, alpha, &ri);
+    evals++;
+    Ek = e.Eo;
+    last_rk = Ek;
+    if (k == 0) {
+      E0 = Ek;
+      bool bad = false;
+      inner_tol = saturate(E0, o.inner_tol_min, o.inner_tol_max, &bad);
+      if (bad) {
+        status = FBSTAB_STATUS_SATURATE;
+        break;
+      }
+    }
+    if (Ek <= combo_tol || dx_norm <= o.stall_tol) {
+      eflag = FBSTAB_SUCCESS;
+      which = 0;
+      break;
+    }
+    {
+      bool bad = false;
+      inner_tol = saturate(inner_tol * o.delta, o.inner_tol_min, Ek, &bad);
+      if (bad) {
+        status = FBSTAB_STATUS_SATURATE;
+        break;
+      }
+    }
+    xi = xk;
+    double merit[5] = {0, 0, 0, 0, 0};
+    double Eo = 0.0;
+    bool have = true;
+    double Ei_c = e.Ei, Eo_c = e.Eo;
+    for (int i = 0; i < o.max_inner_iters; i++) {
+      if (!have) {
+        EvalOut ee = w.evaluate(xi, xk, sigma, alpha, &ri);
+        evals++;
+        Ei_c = ee.Ei;
+        Eo_c = ee.Eo;
+        have = true;
+      }
+      const double Ei = Ei_c;
+      Eo = Eo_c;
+      last_rk = Eo;
+      if ((Ei <= inner_tol && Eo < Ek) || (Ei <= o.inner_tol_min)) break;
+      if (newton >= o.max_newton_iters) break;
+      if (!w.newton_step(xi, xk, sigma, alpha, ri, &dx)) {
+        status = FBSTAB_STATUS_FACTOR_FAILED;
+        done = true;
+        break;
+      }
+      newton++;
+      const double current_merit = 0.5 * Ei * Ei;
+#pragma unroll
+      for (int m = 4; m > 0; m--) merit[m] = merit[m - 1];
+      merit[0] = current_merit;
+      double m0 = current_merit;
+      if (o.nonmonotone_linesearch) {
+#pragma unroll
+        for (int m = 1; m < 5; m++) m0 = fmax(m0, merit[m]);
+      }
+      double tstep = 1.0;
+      bool accepted = false;
+      EvalOut et;
+      for (int j = 0; j < o.max_linesearch_iters; j++) {
+        v_axpy(w, xi, tstep, dx, &xp);
+        et = w.evaluate(xp, xk, sigma, alpha, &ri);
+        evals++;
+        const double mp = 0.5 * et.Ei * et.Ei;
+        if (mp <= m0 - 2.0 * tstep * o.eta * current_merit) {
+          accepted = true;
+          break;
+        }
+        tstep *= o.beta;
+        backtracks++;
+      }
+      if (accepted) {
+        xi = xp;
+        Ei_c = et.Ei;
+        Eo_c = et.Eo;
+      } else {
+        v_axpy(w, xi, tstep, dx, &xi);
+        have = false;
+      }
+    }
+    if (done) break;
+#pragma unroll
+    for (int m = 0; m < NVR; m++) xi.v[m] = fmax(xi.v[m], 0.0);  // ProjectDuals
+
+    if (newton >= o.max_newton_iters) {
+      const bool pick_xi = Eo < Ek;
+      V pick;
+      pick.z = pick_xi ? xi.z : xk.z;
+      pick.l = pick_xi ? xi.l : xk.l;
+#pragma unroll
+      for (int m = 0; m < NVR; m++) {
+        pick.v[m] = pick_xi ? xi.v[m] : xk.v[m];
+        pick.y[m] = pick_xi ? xi.y[m] : xk.y[m];
+      }
+      EvalOut ef = w.evaluate(pick, pick, sigma, alpha, &ri);
+      evals++;
+      last_rk = ef.Eo;
+      eflag = FBSTAB_MAXITERATIONS;
+      which = pick_xi ? 1 : 0;
+      break;
+    }
+    // dx = xi - xk (y-aware)
+    {
+      dx.z = xi.z + (-1.0) * xk.z;
+      dx.l = xi.l + (-1.0) * xk.l;
+      double sq = dx.z * dx.z;
+      sq = fma(dx.l, dx.l, sq);
+#pragma unroll
+      for (int m = 0; m < NVR; m++) {
+        dx.v[m] = xi.v[m] + (-1.0) * xk.v[m];
+        sq = fma(dx.v[m], dx.v[m], sq);
+        const double y = xi.y[m] + (-1.0) * xk.y[m];
+        dx.y[m] = y + w.s[OFF_B + lane + 32 * m];
+      }
+      dx_norm = sqrt(warp_sum(sq));
+    }
+    if (o.check_feasibility) {
+      const int feas = w.feasibility(dx, o.infeas_tol);
+      if (feas != 0) {
+        eflag = (feas == 1)   ? FBSTAB_PRIMAL_INFEASIBLE
+                : (feas == 2) ? FBSTAB_DUAL_INFEASIBLE
+                              : FBSTAB_PRIMAL_DUAL_INFEASIBLE;
+        which = 2;
+        break;
+      }
+    }
+    xk = xi;
+    prox++;
+  }
+  V r;
+  r.z = (which == 0) ? xk.z : (which == 1) ? xi.z : dx.z;
+  r.l = (which == 0) ? xk.l : (which == 1) ? xi.l : dx.l;
+#pragma unroll
+  for (int m = 0; m < NVR; m++) {
+    r.v[m] = (which == 0) ? xk.v[m] : (which == 1) ? xi.v[m] : dx.v[m];
+    r.y[m] = (which == 0) ? xk.y[m] : (which == 1) ? xi.y[m] : dx.y[m];
+  }
+  if (lane < w.nz) A.z[(size_t)inst * w.nz + lane] = r.z;
+  if (lane < w.nl) A.l[(size_t)inst * w.nl + lane] = r.l;
+#pragma unroll
+  for (int m = 0; m < NVR; m++)
+    if (lane + 32 * m < w.nv) {
+      A.v[(size_t)inst * w.nv + lane + 32 * m] = r.v[m];
+      A.y[(size_t)inst * w.nv + lane + 32 * m] = r.y[m];
+    }
+  if (lane == 0) {
+    fbstab_out* out = A.out + inst;
+    out->eflag = eflag;
+    out->newton_iters = newton;
+    out->prox_iters = prox;
+    out->status = status;
+    out->residual = last_rk;
+    out->initial_residual = E0;
+    out->solve_time = -1.0;
+    out->ls_backtracks = backtracks;
+    out->residual_evals = evals;
+  }
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 1)
+dense_small_kernel(const __grid_constant__ Args a) {
+  extern __shared__ __align__(16) double smem[];
+  Warp w;
+  w.lane = threadIdx.x & 31;
+  w.s = smem + (size_t)(threadIdx.x >> 5) * SLAB;
+  w.nz = a.nz;
+  w.nl = a.nl;
+  w.nv = a.nv;
+  for (;;) {
+    int inst = 0;
+    if (w.lane == 0) inst = atomicAdd(a.counter, 1);
+    inst = __shfl_sync(0xffffffffu, inst, 0);
+    if (inst >= a.batch) break;
+    w.load(a, inst);
+    solve_one(w, a, inst);
+  }
+}
+
+}  // namespace small
+
+int DenseSmallInit(DenseSmallPlan* p, int nz, int nl, int nv, int sm_count,
+                          int* counter) {
+  p->enabled = false;
+  if (nz > small::NZ || nl > small::NL || nv > small::NV) return 0;
+  p->nz = nz;
+  p->nl = nl;
+  p->nv = nv;
+  p->counter = counter;
+  p->smem = sizeof(double) * small::SLAB * small::kWarpsPerCta;
+  if (cudaFuncSetAttribute(small::dense_small_kernel,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)p->smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;  // fall back to the generic kernel
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &occ, small::dense_small_kernel, 32 * small::kWarpsPerCta, p->smem) !=
+          cudaSuccess ||
+      occ < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  p->grid = sm_count * occ;
+  p->enabled = true;
+  p->name = "dense-small-warp (smem-resident data, DMMA SYRK, register LDL')";
+  return 0;
+}
+
+int DenseSmallLaunch(const DenseSmallPlan& p, int batch, const double* H,
+                            const double* f, const double* G, const double* h,
+                            const double* A, const double* b, double* z, double* l,
+                            double* v, double* y, fbstab_out* out,
+                            const fbstab_options& opts, cudaStream_t stream) {
+  small::Args a;
+  a.nz = p.nz;
+  a.nl = p.nl;
+  a.nv = p.nv;
+  a.batch = batch;
+  a.H = H;
+  a.f = f;
+  a.G = G;
+  a.h = h;
+  a.A = A;
+  a.b = b;
+  a.z = z;
+  a.l = l;
+  a.v = v;
+  a.y = y;
+  a.out = out;
+  a.counter = p.counter;
+  a.opts = opts;
+  const int warps = (batch + small::kWarpsPerCta - 1) / small::kWarpsPerCta;
+  const int grid = warps < p.grid ? warps : p.grid;
+  small::dense_small_kernel<<<grid, 32 * small::kWarpsPerCta, p.smem, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace fbs

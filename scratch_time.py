@@ -1,26 +1,15 @@
 import sys, time, numpy as np
 sys.path.insert(0, '.')
 import fbstab_b200 as fb, torch
-for (nz,nl,nv,B) in [(32,8,64,8192)]:
-    d = fb.problems.random_dense_qp(nz,nl,nv,count=B,config=2)
-    s = fb.FBstabDense(nz,nl,nv,max_batch=B)
-    dev=torch.device('cuda:0')
-    dd={k:torch.from_numpy(a).to(dev) for k,a in d.items()}
-    for it in range(3):
-        zt=torch.zeros(B*nz,dtype=torch.float64,device=dev); lt=torch.zeros(B*nl,dtype=torch.float64,device=dev); vt=torch.zeros(B*nv,dtype=torch.float64,device=dev)
-        torch.cuda.synchronize(); t=time.time()
-        out,y=s.solve_batch(dd,zt,lt,vt)
-        torch.cuda.synchronize(); t=time.time()-t
-        print('dense',nz,nl,nv,B,s.path,'%.2f ms'%(t*1e3),'%.0f solves/s'%(B/t))
-for kind,N,B in [('servo_motor',50,4096),('double_integrator',50,4096),('copolymerization',100,512),('spacecraft',100,256)]:
-    dims,d=fb.problems.ocp_batch(kind,N,count=B,config=3,rho=0.01)
-    s=fb.FBstabMpc(*dims,max_batch=B)
-    dev=torch.device('cuda:0')
-    dd={k:torch.from_numpy(a).to(dev) for k,a in d.items()}
-    for it in range(2):
-        zt=torch.zeros(B*s.nz,dtype=torch.float64,device=dev); lt=torch.zeros(B*s.nl,dtype=torch.float64,device=dev); vt=torch.zeros(B*s.nv,dtype=torch.float64,device=dev)
-        torch.cuda.synchronize(); t=time.time()
-        out,y=s.solve_batch(dd,zt,lt,vt)
-        torch.cuda.synchronize(); t=time.time()-t
-        o=np.frombuffer(out.cpu().numpy().tobytes(),dtype=fb.OUT_DTYPE)
-        print(kind,N,B,s.path,'%.2f ms'%(t*1e3),'%.0f solves/s'%(B/t),'flags',np.bincount(o['eflag'],minlength=6),'newton mean',o['newton_iters'].mean())
+nz,nl,nv,B=32,8,64,65536
+d = fb.problems.random_dense_qp(nz,nl,nv,count=B,config=2)
+s = fb.FBstabDense(nz,nl,nv,max_batch=B)
+dev=torch.device('cuda:0')
+dd={k:torch.from_numpy(a).to(dev) for k,a in d.items()}
+for it in range(4):
+    zt=torch.zeros(B*nz,dtype=torch.float64,device=dev); lt=torch.zeros(B*nl,dtype=torch.float64,device=dev); vt=torch.zeros(B*nv,dtype=torch.float64,device=dev)
+    torch.cuda.synchronize(); t=time.time()
+    out,y=s.solve_batch(dd,zt,lt,vt)
+    torch.cuda.synchronize(); t=time.time()-t
+    o=np.frombuffer(out.cpu().numpy().tobytes(),dtype=fb.OUT_DTYPE)
+    print('dense',nz,nl,nv,B,s.path[:20],'%.2f ms'%(t*1e3),'%.0f solves/s'%(B/t), 'flags',np.bincount(o['eflag'],minlength=6),'newton',o['newton_iters'].mean())
