@@ -748,8 +748,8 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
   CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
   if (h->small.enabled) {
     rc = fbs::DenseSmallLaunch(h->small, batch, a.H, a.f, a.G, a.h, a.A, a.b,
-                               a.c.z, a.c.l, a.c.v, a.c.y, a.c.out, h->opts,
-                               st.stream);
+                               a.c.z, a.c.l, a.c.v, a.c.y, a.c.out, h->opts, -1,
+                               nullptr, st.stream);
     if (rc) return Fail(FBSTAB_ERR_CUDA, "dense small-path launch failed");
   } else {
     const int grid = std::min(batch, h->grid_max);
@@ -787,8 +787,15 @@ int fbstab_dense_batch_component(fbstab_dense_batch* h, int comp, int batch,
   a.c.comp = comp;
   if ((rc = StageComponentIo(h, &st, batch, io, &a.c.io))) return rc;
   CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
-  const int grid = std::min(batch, h->grid_max);
-  dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+  if (h->small.enabled) {
+    rc = fbs::DenseSmallLaunch(h->small, batch, a.H, a.f, a.G, a.h, a.A, a.b,
+                               nullptr, nullptr, nullptr, nullptr, nullptr,
+                               h->opts, comp, &a.c.io, st.stream);
+    if (rc) return Fail(FBSTAB_ERR_CUDA, "dense small-path launch failed");
+  } else {
+    const int grid = std::min(batch, h->grid_max);
+    dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+  }
   CUDA_TRY(cudaGetLastError());
   h->last_launches = 1;
   return st.Finish();

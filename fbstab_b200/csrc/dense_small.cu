@@ -25,6 +25,8 @@
 // Follows the same reference code as engine.cuh / dense_problem.cuh
 // (fbstab_algorithm-impl.h:113-304, dense_cholesky_solver.cc:32-148,
 // full_residual.cc:49-118, full_feasibility.cc:25-88).
+#include <cstring>
+
 #include "common.cuh"
 #include "dense_small.h"
 #include "engine.cuh"
@@ -50,10 +52,10 @@ constexpr int OFF_B = OFF_HV + NL;
 constexpr int OFF_ZB = OFF_B + NV;             // broadcast copies: z(32) l(8) v(64)
 constexpr int OFF_LB = OFF_ZB + NZ;
 constexpr int OFF_VB = OFF_LB + NL;
-constexpr int OFF_COL = OFF_VB + NV;           // 2 x (32 + 10 [+pad]) pivot-column buffers
+constexpr int OFF_COL = OFF_VB + NV;           // 2 x (32 shifted row + pivot + 10 aug) buffers
 constexpr int COL_STRIDE = 44;
 constexpr int OFF_SCR = OFF_COL + 2 * COL_STRIDE;  // transposition / Schur scratch
-constexpr int SCR_SIZE = 480;  // >= 8*LD (transposition), >= 472 (Schur: X 320, 1/d 32, S 64, T 8)
+constexpr int SCR_SIZE = 392;  // >= 8*LD (transposition), >= 392 (Schur: Y 320, S 64, T 8)
 constexpr int SLAB = OFF_SCR + SCR_SIZE;
 static_assert(SLAB % 2 == 0, "slab must keep 16-byte alignment");
 static_assert(OFF_A % 2 == 0 && OFF_G % 2 == 0 && OFF_ZB % 2 == 0 &&
@@ -67,6 +69,8 @@ struct Args {
   fbstab_out* out;
   int* counter;
   fbstab_options opts;
+  int comp;  // < 0: full solve; otherwise one FBSTAB_COMP_* stage
+  fbstab_component_io io;
 };
 
 struct V {  // primal-dual iterate in registers
@@ -96,8 +100,12 @@ struct Warp {
   double* s;  // this warp's slab
   int lane;
   int nz, nl, nv;
-  // linear-solver state kept between factor() and solve()
+  // Newton-step state
   double gamma[NVR], mus[NVR];
+  double a[NZ];      // row `lane` of E, rotated left once per elimination step
+  double g[NL + 1];  // column `lane` of G (rows 0..7) and the rhs (row 8)
+  double dinv;       // 1 / pivot of row `lane`
+  bool ok;
 
   // ---- products -------------------------------------------------------------
   __device__ __forceinline__ void publish(const V& x) {
@@ -108,54 +116,54 @@ struct Warp {
     for (int m = 0; m < NVR; m++) s[OFF_VB + lane + 32 * m] = x.v[m];
     __syncwarp();
   }
-  // (H zb)[lane]
-  __device__ __forceinline__ double Hz() const {
-    const double* hr = s + OFF_H + LD * lane;
+  // (M zb)[row] for a row-contiguous 32-wide matrix row
+  __device__ __forceinline__ double row_dot(const double* row) const {
     const double* zb = s + OFF_ZB;
     double s0 = 0.0, s1 = 0.0;
-#pragma unroll
+#pragma unroll 4
     for (int j = 0; j < NZ; j += 2) {
-      const double2 hh = lds2(hr + j);
+      const double2 hh = lds2(row + j);
       const double2 zz = lds2(zb + j);
       s0 = fma(hh.x, zz.x, s0);
       s1 = fma(hh.y, zz.y, s1);
     }
     return s0 + s1;
   }
+  __device__ __forceinline__ double Hz() const { return row_dot(s + OFF_H + LD * lane); }
   // (G' lb)[lane]
   __device__ __forceinline__ double GTl() const {
-    const double* g = s + OFF_G + lane;
+    const double* gc = s + OFF_G + lane;
     const double* lb = s + OFF_LB;
     double s0 = 0.0;
 #pragma unroll
     for (int r = 0; r < NL; r += 2) {
       const double2 ll = lds2(lb + r);
-      s0 = fma(g[LD * r], ll.x, s0);
-      s0 = fma(g[LD * (r + 1)], ll.y, s0);
+      s0 = fma(gc[LD * r], ll.x, s0);
+      s0 = fma(gc[LD * (r + 1)], ll.y, s0);
     }
     return s0;
   }
   // (A' vb)[lane]
   __device__ __forceinline__ double ATv() const {
-    const double* a = s + OFF_A + lane;
+    const double* ac = s + OFF_A + lane;
     const double* vb = s + OFF_VB;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
+#pragma unroll 2
     for (int k = 0; k < NV; k += 4) {
       const double2 v0 = lds2(vb + k);
       const double2 v1 = lds2(vb + k + 2);
-      s0 = fma(a[LD * k], v0.x, s0);
-      s1 = fma(a[LD * (k + 1)], v0.y, s1);
-      s2 = fma(a[LD * (k + 2)], v1.x, s2);
-      s3 = fma(a[LD * (k + 3)], v1.y, s3);
+      s0 = fma(ac[LD * k], v0.x, s0);
+      s1 = fma(ac[LD * (k + 1)], v0.y, s1);
+      s2 = fma(ac[LD * (k + 2)], v1.x, s2);
+      s3 = fma(ac[LD * (k + 3)], v1.y, s3);
     }
     return (s0 + s1) + (s2 + s3);
   }
   // (G zb)[lane % 8], same value in the four lanes sharing lane % 8
   __device__ __forceinline__ double Gz() const {
-    const int r = lane & 7, g = lane >> 3;
-    const double* gr = s + OFF_G + LD * r + 8 * g;
-    const double* zb = s + OFF_ZB + 8 * g;
+    const int r = lane & 7, q = lane >> 3;
+    const double* gr = s + OFF_G + LD * r + 8 * q;
+    const double* zb = s + OFF_ZB + 8 * q;
     double s0 = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
@@ -170,20 +178,8 @@ struct Warp {
   }
   // (A zb)[lane + 32 m]
   __device__ __forceinline__ void Az(double (&o)[NVR]) const {
-    const double* zb = s + OFF_ZB;
 #pragma unroll
-    for (int m = 0; m < NVR; m++) {
-      const double* ar = s + OFF_A + LD * (lane + 32 * m);
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int j = 0; j < NZ; j += 2) {
-        const double2 aa = lds2(ar + j);
-        const double2 zz = lds2(zb + j);
-        s0 = fma(aa.x, zz.x, s0);
-        s1 = fma(aa.y, zz.y, s1);
-      }
-      o[m] = s0 + s1;
-    }
+    for (int m = 0; m < NVR; m++) o[m] = row_dot(s + OFF_A + LD * (lane + 32 * m));
   }
 
   // ---- fused residual evaluation (see engine.cuh) ---------------------------
@@ -224,171 +220,176 @@ struct Warp {
     return e;
   }
 
-  // ---- Newton step: LinearSolver::Initialize + ::Solve fused -----------------
-  // Solves V(x,xbar,sigma) dx = -ri.  Returns false on a zero / NaN pivot.
-  __device__ __forceinline__ bool newton_step(const V& x, const V& xbar, double sigma,
-                              double alpha, const R& ri, V* dx) {
-    const int r8 = lane >> 2, c4 = lane & 3;
-    double Gam[NVR], r2[NVR];
-#pragma unroll
-    for (int m = 0; m < NVR; m++) {
-      const double ys = x.y[m] + sigma * (x.v[m] - xbar.v[m]);
-      pfb_barrier(ys, x.v[m], alpha, sigma, &gamma[m], &mus[m]);
-      Gam[m] = gamma[m] / mus[m];
-      r2[m] = (-ri.v[m]) / mus[m];
-    }
-    // r1z = -rz - A'(rv/mus) ; Gamma -> shared for the DMMA operand scaling
-    __syncwarp();
-#pragma unroll
-    for (int m = 0; m < NVR; m++) {
-      s[OFF_VB + lane + 32 * m] = r2[m];
-      s[OFF_SCR + lane + 32 * m] = Gam[m];
-    }
-    __syncwarp();
-    double u = (-ri.z) - ATv();
-
-    // E (lower 8x8 blocks) on the FP64 tensor cores
-    double C[4][4][2];
-#pragma unroll
-    for (int I = 0; I < 4; I++)
-#pragma unroll
-      for (int J = 0; J <= I; J++) {
-        const double2 hh = lds2(s + OFF_H + LD * (8 * I + r8) + 8 * J + 2 * c4);
-        C[I][J][0] = hh.x + ((I == J && r8 == 2 * c4) ? sigma : 0.0);
-        C[I][J][1] = hh.y + ((I == J && r8 == 2 * c4 + 1) ? sigma : 0.0);
-      }
-#pragma unroll 4
-    for (int kc = 0; kc < NV / 4; kc++) {
-      const double* ar = s + OFF_A + LD * (4 * kc + c4) + r8;
-      const double gk = s[OFF_SCR + 4 * kc + c4];
-      double a[4], b[4];
-#pragma unroll
-      for (int X = 0; X < 4; X++) {
-        a[X] = ar[8 * X];
-        b[X] = gk * a[X];
-      }
-#pragma unroll
-      for (int I = 0; I < 4; I++)
-#pragma unroll
-        for (int J = 0; J <= I; J++) dmma(C[I][J][0], C[I][J][1], a[I], b[J]);
-    }
-    // fragments -> full symmetric rows: lane i gets a[j] = E(i,j) for all j
-    double a[NZ];
-#pragma unroll
-    for (int I = 0; I < 4; I++) {
-      __syncwarp();
-#pragma unroll
-      for (int J = 0; J <= I; J++)
-        sts2(s + OFF_SCR + LD * r8 + 8 * J + 2 * c4, C[I][J][0], C[I][J][1]);
-      __syncwarp();
-      if ((lane >> 3) == I) {
-        const double* row = s + OFF_SCR + LD * (lane & 7);
-#pragma unroll
-        for (int j = 0; j < NZ; j += 2) {
-          if (j < 8 * (I + 1)) {
-            const double2 t = lds2(row + j);
-            a[j] = t.x;
-            a[j + 1] = t.y;
-          }
-        }
-      } else if ((lane >> 3) < I) {
-#pragma unroll
-        for (int rr = 0; rr < 8; rr++) a[8 * I + rr] = s[OFF_SCR + LD * rr + lane];
-      }
-    }
-    // G block column-wise (lane j owns column j) + the rhs as a ninth row
-    double g[NL + 1];
-#pragma unroll
-    for (int r = 0; r < NL; r++) g[r] = s[OFF_G + LD * r + lane];
-    g[NL] = u;
-
-    // right-looking LDL' of [E G'; G .] with pivot-column broadcast
-    bool ok = true;
-    double dinv = 0.0;  // 1/d_lane
-#pragma unroll
-    for (int k = 0; k < NZ; k++) {
+  // One segment of the Gauss-Jordan elimination of E: steps k0..k1-1, during
+  // which at most W trailing columns are still non-zero.  Every step the row
+  // registers rotate left by one, so a[0] is always the entry in the pivot
+  // column and the loop body is the same for every k (compact code, static
+  // register indices).  Lane k broadcasts its (already rotated) pivot row
+  // through shared memory, so it is read from fixed addresses.
+  template <int W>
+  __device__ __forceinline__ void eliminate(int k0, int k1) {
+#pragma unroll 1
+    for (int k = k0; k < k1; k++) {
       double* cb = s + OFF_COL + COL_STRIDE * (k & 1);
-      const double ck = a[k];
-      cb[lane] = ck;
       if (lane == k) {
+        // the pivot row itself (NOT the pivot column taken from the other
+        // lanes: after the 1e8-scale cancellations of A' Gamma A the (k,j) and
+        // (j,k) entries differ at the 1e-8 relative level, and mixing them
+        // ruins the accuracy of dz along the active-constraint normals)
+        cb[32] = a[0];
+#pragma unroll
+        for (int m = 1; m + 1 <= W; m += 2) sts2(cb + m - 1, a[m], a[m + 1]);
+        if (W & 1) cb[W - 1] = a[W];
 #pragma unroll
         for (int r = 0; r < NL + 1; r += 2)
-          sts2(cb + 32 + r, g[r], (r + 1 < NL + 1) ? g[r + 1] : 0.0);
+          sts2(cb + 34 + r, g[r], (r + 1 < NL + 1) ? g[r + 1] : 0.0);
       }
       __syncwarp();
-      const double d = cb[k];
+      const double d = cb[32];
       if (!(fabs(d) > 0.0)) ok = false;
       const double rd = 1.0 / d;
       if (lane == k) dinv = rd;
-      const double lik = (lane > k) ? ck * rd : 0.0;
-      if ((k + 1) & 1) {  // odd start: one scalar load keeps the pairs aligned
-        if (k + 1 < NZ) a[k + 1] = fma(-lik, cb[k + 1], a[k + 1]);
+      const double lik = (lane != k) ? a[0] * rd : 0.0;
 #pragma unroll
-        for (int j = k + 2; j < NZ; j += 2) {
-          const double2 cj = lds2(cb + j);
-          a[j] = fma(-lik, cj.x, a[j]);
-          a[j + 1] = fma(-lik, cj.y, a[j + 1]);
-        }
-      } else {
-#pragma unroll
-        for (int j = k + 1; j < NZ; j += 2) {
-          const double2 cj = lds2(cb + j);
-          a[j] = fma(-lik, cj.x, a[j]);
-          a[j + 1] = fma(-lik, cj.y, a[j + 1]);
-        }
+      for (int m = 1; m <= W; m += 2) {
+        const double2 c = lds2(cb + m - 1);
+        a[m - 1] = fma(-lik, c.x, a[m]);
+        if (m + 1 < NZ) a[m] = fma(-lik, c.y, a[m + 1]);
       }
-      if (lane > k) a[k] = lik;
+      if (W < NZ - 1) a[W] = 0.0; else a[NZ - 1] = 0.0;
 #pragma unroll
       for (int r = 0; r < NL + 1; r += 2) {
-        const double2 xr = lds2(cb + 32 + r);
+        const double2 xr = lds2(cb + 34 + r);
         g[r] = fma(-lik, xr.x, g[r]);
         if (r + 1 < NL + 1) g[r + 1] = fma(-lik, xr.y, g[r + 1]);
       }
     }
-    // lane k now holds d_k (a[k]), x_k = (L^-1 G')(k,:) in g[0..7], u_k = g[8]
-    u = g[NL];
+  }
 
-    // Schur complement S = -sigma I - X' D^-1 X and rhs c - X' D^-1 u (DMMA)
+  // ---- Newton step: LinearSolver::Initialize + ::Solve fused -----------------
+  // Solves V(x,xbar,sigma) dx = -ri.  Returns false on a zero / NaN pivot.
+  __device__ __forceinline__ bool newton_step(const V& x, const V& xbar,
+                                              double sigma, double alpha,
+                                              const R& ri, V* dx) {
+    const int r8 = lane >> 2, c4 = lane & 3;
+    ok = true;
+    {
+      double r2[NVR], Gam[NVR];
+#pragma unroll
+      for (int m = 0; m < NVR; m++) {
+        const double ys = x.y[m] + sigma * (x.v[m] - xbar.v[m]);
+        pfb_barrier(ys, x.v[m], alpha, sigma, &gamma[m], &mus[m]);
+        Gam[m] = gamma[m] / mus[m];
+        r2[m] = (-ri.v[m]) / mus[m];
+      }
+      // r1z = -rz - A'(rv/mus) ; Gamma -> shared for the DMMA operand scaling
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < NVR; m++) {
+        s[OFF_VB + lane + 32 * m] = r2[m];
+        s[OFF_SCR + lane + 32 * m] = Gam[m];
+      }
+      __syncwarp();
+    }
+    g[NL] = (-ri.z) - ATv();
+
+    // E (lower 8x8 blocks) on the FP64 tensor cores
+    {
+      double C[4][4][2];
+#pragma unroll
+      for (int I = 0; I < 4; I++)
+#pragma unroll
+        for (int J = 0; J <= I; J++) {
+          const double2 hh = lds2(s + OFF_H + LD * (8 * I + r8) + 8 * J + 2 * c4);
+          C[I][J][0] = hh.x + ((I == J && r8 == 2 * c4) ? sigma : 0.0);
+          C[I][J][1] = hh.y + ((I == J && r8 == 2 * c4 + 1) ? sigma : 0.0);
+        }
+#pragma unroll 1
+      for (int kc = 0; kc < NV / 4; kc++) {
+        const double* ar = s + OFF_A + LD * (4 * kc + c4) + r8;
+        const double gk = s[OFF_SCR + 4 * kc + c4];
+        double af[4], bf[4];
+#pragma unroll
+        for (int X = 0; X < 4; X++) {
+          af[X] = ar[8 * X];
+          bf[X] = gk * af[X];
+        }
+#pragma unroll
+        for (int I = 0; I < 4; I++)
+#pragma unroll
+          for (int J = 0; J <= I; J++) dmma(C[I][J][0], C[I][J][1], af[I], bf[J]);
+      }
+      // fragments -> full symmetric rows: lane i gets a[j] = E(i,j) for all j
+#pragma unroll
+      for (int I = 0; I < 4; I++) {
+        __syncwarp();
+#pragma unroll
+        for (int J = 0; J <= I; J++)
+          sts2(s + OFF_SCR + LD * r8 + 8 * J + 2 * c4, C[I][J][0], C[I][J][1]);
+        __syncwarp();
+        if ((lane >> 3) == I) {
+          const double* row = s + OFF_SCR + LD * (lane & 7);
+#pragma unroll
+          for (int j = 0; j < NZ; j += 2) {
+            if (j < 8 * (I + 1)) {
+              const double2 t = lds2(row + j);
+              a[j] = t.x;
+              a[j + 1] = t.y;
+            }
+          }
+        } else if ((lane >> 3) < I) {
+#pragma unroll
+          for (int rr = 0; rr < 8; rr++) a[8 * I + rr] = s[OFF_SCR + LD * rr + lane];
+        }
+      }
+    }
+    // G block column-wise (lane j owns column j); the rhs is already in g[8]
+#pragma unroll
+    for (int r = 0; r < NL; r++) g[r] = s[OFF_G + LD * r + lane];
+
+    // Gauss-Jordan elimination of the E block (4 segments of 8 steps)
+    eliminate<31>(0, 8);
+    eliminate<23>(8, 16);
+    eliminate<15>(16, 24);
+    eliminate<7>(24, 32);
+    // lane i now holds d_i * (E^-1 [G' a])(i,:) in g[0..8] and dinv = 1/d_i
+
+    // Schur complement S = -sigma I - G Y, rhs c - G t  with [Y t] = E^-1 [G' a]
     __syncwarp();
     {
-      double* xs = s + OFF_SCR;  // Xs[r + 10*k], r = 0..8 ; dinv at 320..351
+      double* xs = s + OFF_SCR;  // Ys[r + 10*i], r = 0..8
 #pragma unroll
       for (int r = 0; r < NL + 1; r += 2)
-        sts2(xs + 10 * lane + r, g[r], (r + 1 < NL + 1) ? g[r + 1] : 0.0);
-      xs[320 + lane] = dinv;
+        sts2(xs + 10 * lane + r, g[r] * dinv, (r + 1 < NL + 1) ? g[r + 1] * dinv : 0.0);
     }
     __syncwarp();
     double S0 = 0.0, S1 = 0.0, T0 = 0.0, T1 = 0.0;
-#pragma unroll
+#pragma unroll 2
     for (int kc = 0; kc < NZ / 4; kc++) {
       const double* xs = s + OFF_SCR;
-      const int k = 4 * kc + c4;
-      const double xe = xs[10 * k + r8];
-      const double ue = xs[10 * k + NL];
-      const double di = xs[320 + k];
-      const double ae = xe * di;
-      dmma(S0, S1, ae, xe);
-      dmma(T0, T1, ae, ue);
+      const int i = 4 * kc + c4;
+      const double ge = s[OFF_G + LD * r8 + i];  // G(r8, i)
+      const double ye = xs[10 * i + r8];         // Y(i, r8)
+      const double te = xs[10 * i + NL];         // t(i)
+      dmma(S0, S1, ge, ye);
+      dmma(T0, T1, ge, te);
     }
-    // lane (r8,c4) holds S(r8, 2c4+{0,1}) (before the sign/-sigma) and
-    // T(r8,*) = (X' D^-1 u)(r8).  Gather row r into lane r (r < 8).
     __syncwarp();
     {
       double* sc = s + OFF_SCR;
-      sts2(sc + 400 + 8 * r8 + 2 * c4, S0, S1);
-      if (c4 == 0) sc[464 + r8] = T0;
+      sts2(sc + 320 + 8 * r8 + 2 * c4, S0, S1);
+      if (c4 == 0) sc[384 + r8] = T0;
     }
     __syncwarp();
     double dl = 0.0;
     {
-      // 8x8 LDL' by lanes 0..7 (lane r = row r); all lanes execute, rows >= 8 idle
+      // 8x8 elimination by lanes 0..7 (lane r = row r)
       const double* sc = s + OFF_SCR;
       const int r = lane & 7;
       double srow[NL];
 #pragma unroll
-      for (int j = 0; j < NL; j++) srow[j] = -sc[400 + 8 * r + j] - ((j == r) ? sigma : 0.0);
-      double rhs = ((lane < NL) ? ri.l : 0.0) - sc[464 + r];
-      // rows of padded equality constraints: identity block keeps them inert
+      for (int j = 0; j < NL; j++) srow[j] = -sc[320 + 8 * r + j] - ((j == r) ? sigma : 0.0);
+      double rhs = ((lane < NL) ? ri.l : 0.0) - sc[384 + r];
       double dsi = 0.0;
 #pragma unroll
       for (int k = 0; k < NL; k++) {
@@ -396,41 +397,23 @@ struct Warp {
         if (!(fabs(dk) > 0.0)) ok = false;
         const double rdk = 1.0 / dk;
         if (r == k) dsi = rdk;
-        const double lrk = (r > k) ? srow[k] * rdk : 0.0;
+        // Gauss-Jordan here as well: no back substitution
+        const double lrk = (r != k) ? srow[k] * rdk : 0.0;
 #pragma unroll
         for (int j = k + 1; j < NL; j++) {
-          const double cj = bcast(srow[k], j);  // S(j,k) by symmetry
+          const double cj = bcast(srow[j], k);  // S(k,j): pivot row
           srow[j] = fma(-lrk, cj, srow[j]);
         }
         const double rk = bcast(rhs, k);
         rhs = fma(-lrk, rk, rhs);
-        if (r > k) srow[k] = lrk;
       }
-      // backward: dl_r = (rhs_r - sum_{k>r} srow_r[k] dl_k) / d_r
-      // (srow_r[k], k>r, is d_r * L(k,r) thanks to the symmetric elimination)
-      double acc = rhs;
-#pragma unroll
-      for (int k = NL - 1; k >= 0; k--) {
-        const double fin = acc * dsi;
-        const double dk = bcast(fin, k);
-        if (r == k) dl = dk;
-        if (r < k) acc = fma(-srow[k], dk, acc);
-      }
-      if (lane >= NL) dl = 0.0;
+      dl = (lane < NL) ? rhs * dsi : 0.0;
     }
-    // w = u - X dl ; backward substitution L' dz = D^-1 w with the upper part
-    // of the symmetric rows (a[k], k > lane, equals d_lane * L(k,lane)).
-    double acc = u;
+    // dz = t - Y dl = (g[8] - sum_r g[r] dl_r) / d
+    double acc = g[NL];
 #pragma unroll
     for (int r = 0; r < NL; r++) acc = fma(-g[r], bcast(dl, r), acc);
-    double dz = 0.0;
-#pragma unroll
-    for (int k = NZ - 1; k >= 0; k--) {
-      const double fin = acc * dinv;
-      const double dk = bcast(fin, k);
-      if (lane == k) dz = dk;
-      if (lane < k) acc = fma(-a[k], dk, acc);
-    }
+    const double dz = acc * dinv;
     dx->z = dz;
     dx->l = dl;
     // dv = (rv + gamma .* (A dz)) ./ mus ; dy = b - A dz
@@ -479,28 +462,28 @@ struct Warp {
   }
 
   // ---- data staging ----------------------------------------------------------
-  __device__ __forceinline__ void load(const Args& a, int inst) {
+  __device__ __forceinline__ void load(const Args& a_, int inst) {
     __syncwarp();
     for (int e = lane; e < SLAB; e += 32) s[e] = 0.0;
     __syncwarp();
-    const double* H = a.H + (size_t)inst * nz * nz;
+    const double* H = a_.H + (size_t)inst * nz * nz;
     for (int e = lane; e < nz * nz; e += 32) {
       const int i = e % nz, j = e / nz;
       s[OFF_H + LD * i + j] = H[e];
     }
-    const double* A = a.A + (size_t)inst * nv * nz;
+    const double* A = a_.A + (size_t)inst * nv * nz;
     for (int e = lane; e < nv * nz; e += 32) {
       const int k = e % nv, j = e / nv;
       s[OFF_A + LD * k + j] = A[e];
     }
-    const double* G = a.G + (size_t)inst * nl * nz;
+    const double* G = a_.G + (size_t)inst * nl * nz;
     for (int e = lane; e < nl * nz; e += 32) {
       const int r = e % nl, j = e / nl;
       s[OFF_G + LD * r + j] = G[e];
     }
-    if (lane < nz) s[OFF_F + lane] = a.f[(size_t)inst * nz + lane];
-    if (lane < nl) s[OFF_HV + lane] = a.h[(size_t)inst * nl + lane];
-    for (int k = lane; k < nv; k += 32) s[OFF_B + k] = a.b[(size_t)inst * nv + k];
+    if (lane < nz) s[OFF_F + lane] = a_.f[(size_t)inst * nz + lane];
+    if (lane < nl) s[OFF_HV + lane] = a_.h[(size_t)inst * nl + lane];
+    for (int k = lane; k < nv; k += 32) s[OFF_B + k] = a_.b[(size_t)inst * nv + k];
     __syncwarp();
   }
 };
@@ -517,13 +500,30 @@ __device__ __forceinline__ void v_axpy(const Warp& w, const V& src, double a,
   }
 }
 
-// FBstabAlgorithm::Solve for one instance, executed by one warp (the same
-// state machine as engine.cuh::solve_instance, with the iterates in registers).
+__device__ __forceinline__ V v_select(bool c, const V& a, const V& b) {
+  V r;
+  r.z = c ? a.z : b.z;
+  r.l = c ? a.l : b.l;
+#pragma unroll
+  for (int m = 0; m < NVR; m++) {
+    r.v[m] = c ? a.v[m] : b.v[m];
+    r.y[m] = c ? a.y[m] : b.y[m];
+  }
+  return r;
+}
+
+// FBstabAlgorithm::Solve for one instance, executed by one warp.  Same
+// semantics as engine.cuh::solve_instance; written as a phase machine so that
+// the (large) residual evaluation and Newton step each have ONE call site:
+// the instruction footprint of the hot loop has to stay inside the
+// instruction cache.
+enum Phase { P_TOP = 0, P_TRIAL = 1, P_REEVAL = 2, P_FINAL = 3 };
+
 __device__ __forceinline__ void solve_one(Warp& w, const Args& A, int inst) {
   const fbstab_options& o = A.opts;
   const int lane = w.lane;
   const double sigma = o.sigma0, alpha = o.alpha;
-  V xk, xi, xp, dx;
+  V xk, xi, xp, dx, xe;
   R ri;
   xk.z = (lane < w.nz) ? A.z[(size_t)inst * w.nz + lane] : 0.0;
   xk.l = (lane < w.nl) ? A.l[(size_t)inst * w.nl + lane] : 0.0;
@@ -544,120 +544,136 @@ __device__ __forceinline__ void solve_one(Warp& w, const Args& A, int inst) {
 #pragma unroll
     for (int m = 0; m < NVR; m++) xk.y[m] = w.s[OFF_B + lane + 32 * m] - az[m];
   }
+  xi = xk;
+  xp = xk;
+  dx = xk;
   double dx_norm = sqrt((double)w.nz + (double)w.nl + (double)w.nv);
   int eflag = FBSTAB_MAXITERATIONS, status = FBSTAB_STATUS_OK;
   int newton = 0, prox = 0, backtracks = 0, evals = 0;
   double E0 = 0.0, Ek = 0.0, last_rk = 0.0, inner_tol = 0.0;
   int which = 0;  // 0: xk, 1: xi, 2: dx is the result
-  bool done = false;
+  int k = 0, inner_i = 0, ls_j = 0;
+  double merit[5] = {0, 0, 0, 0, 0};
+  double Eo = 0.0, Ei_c = 0.0, Eo_c = 0.0, tstep = 1.0, m0 = 0.0, current_merit = 0.0;
+  int phase = P_TOP;
+  bool need_eval = true, pick_xi = false;
+  xe = xk;
 
-  for (int k = 0; k < o.max_prox_iters && !done; k++) {
-    EvalOut e = w.evaluate(xk, xk, sigma, alpha, &ri);
-    evals++;
-    Ek = e.Eo;
-    last_rk = Ek;
-    if (k == 0) {
-      E0 = Ek;
+  for (;;) {
+    EvalOut e;
+    e.Ei = 0.0;
+    e.Eo = 0.0;
+    if (need_eval) {
+      const bool self_bar = (phase == P_TOP) || (phase == P_FINAL);
+      const V bar = v_select(self_bar, xe, xk);
+      e = w.evaluate(xe, bar, sigma, alpha, &ri);
+      evals++;
+    }
+    need_eval = true;
+    if (phase == P_TOP) {
+      // top of the proximal loop, fbstab_algorithm-impl.h:158-185
+      Ek = e.Eo;
+      last_rk = Ek;
       bool bad = false;
-      inner_tol = saturate(E0, o.inner_tol_min, o.inner_tol_max, &bad);
+      if (k == 0) {
+        E0 = Ek;
+        inner_tol = saturate(E0, o.inner_tol_min, o.inner_tol_max, &bad);
+      }
+      if (!bad && (Ek <= combo_tol || dx_norm <= o.stall_tol)) {
+        eflag = FBSTAB_SUCCESS;
+        which = 0;
+        break;
+      }
+      if (!bad) inner_tol = saturate(inner_tol * o.delta, o.inner_tol_min, Ek, &bad);
       if (bad) {
         status = FBSTAB_STATUS_SATURATE;
         break;
       }
-    }
-    if (Ek <= combo_tol || dx_norm <= o.stall_tol) {
-      eflag = FBSTAB_SUCCESS;
-      which = 0;
-      break;
-    }
-    {
-      bool bad = false;
-      inner_tol = saturate(inner_tol * o.delta, o.inner_tol_min, Ek, &bad);
-      if (bad) {
-        status = FBSTAB_STATUS_SATURATE;
-        break;
-      }
-    }
-    xi = xk;
-    double merit[5] = {0, 0, 0, 0, 0};
-    double Eo = 0.0;
-    bool have = true;
-    double Ei_c = e.Ei, Eo_c = e.Eo;
-    for (int i = 0; i < o.max_inner_iters; i++) {
-      if (!have) {
-        EvalOut ee = w.evaluate(xi, xk, sigma, alpha, &ri);
-        evals++;
-        Ei_c = ee.Ei;
-        Eo_c = ee.Eo;
-        have = true;
-      }
-      const double Ei = Ei_c;
-      Eo = Eo_c;
-      last_rk = Eo;
-      if ((Ei <= inner_tol && Eo < Ek) || (Ei <= o.inner_tol_min)) break;
-      if (newton >= o.max_newton_iters) break;
-      if (!w.newton_step(xi, xk, sigma, alpha, ri, &dx)) {
-        status = FBSTAB_STATUS_FACTOR_FAILED;
-        done = true;
-        break;
-      }
-      newton++;
-      const double current_merit = 0.5 * Ei * Ei;
+      xi = xk;
 #pragma unroll
-      for (int m = 4; m > 0; m--) merit[m] = merit[m - 1];
-      merit[0] = current_merit;
-      double m0 = current_merit;
-      if (o.nonmonotone_linesearch) {
-#pragma unroll
-        for (int m = 1; m < 5; m++) m0 = fmax(m0, merit[m]);
-      }
-      double tstep = 1.0;
-      bool accepted = false;
-      EvalOut et;
-      for (int j = 0; j < o.max_linesearch_iters; j++) {
-        v_axpy(w, xi, tstep, dx, &xp);
-        et = w.evaluate(xp, xk, sigma, alpha, &ri);
-        evals++;
-        const double mp = 0.5 * et.Ei * et.Ei;
-        if (mp <= m0 - 2.0 * tstep * o.eta * current_merit) {
-          accepted = true;
-          break;
-        }
+      for (int m = 0; m < 5; m++) merit[m] = 0.0;
+      Ei_c = e.Ei;
+      Eo_c = e.Eo;
+      inner_i = 0;
+    } else if (phase == P_TRIAL) {
+      // Armijo test, impl:286-296
+      const double mp = 0.5 * e.Ei * e.Ei;
+      if (mp <= m0 - 2.0 * tstep * o.eta * current_merit) {
+        xi = xp;
+        Ei_c = e.Ei;
+        Eo_c = e.Eo;
+        inner_i++;
+        } else {
         tstep *= o.beta;
         backtracks++;
-      }
-      if (accepted) {
-        xi = xp;
-        Ei_c = et.Ei;
-        Eo_c = et.Eo;
-      } else {
+        ls_j++;
+        if (ls_j < o.max_linesearch_iters) {
+          v_axpy(w, xi, tstep, dx, &xp);
+          xe = xp;
+          continue;
+        }
+        // every trial failed: the step is still taken (impl:295-298)
         v_axpy(w, xi, tstep, dx, &xi);
-        have = false;
+        inner_i++;
+        if (inner_i < o.max_inner_iters) {
+          xe = xi;
+          phase = P_REEVAL;
+          continue;
+        }
+        // falls straight into "inner loop exhausted"
       }
-    }
-    if (done) break;
-#pragma unroll
-    for (int m = 0; m < NVR; m++) xi.v[m] = fmax(xi.v[m], 0.0);  // ProjectDuals
-
-    if (newton >= o.max_newton_iters) {
-      const bool pick_xi = Eo < Ek;
-      V pick;
-      pick.z = pick_xi ? xi.z : xk.z;
-      pick.l = pick_xi ? xi.l : xk.l;
-#pragma unroll
-      for (int m = 0; m < NVR; m++) {
-        pick.v[m] = pick_xi ? xi.v[m] : xk.v[m];
-        pick.y[m] = pick_xi ? xi.y[m] : xk.y[m];
-      }
-      EvalOut ef = w.evaluate(pick, pick, sigma, alpha, &ri);
-      evals++;
-      last_rk = ef.Eo;
+    } else if (phase == P_REEVAL) {
+      Ei_c = e.Ei;
+      Eo_c = e.Eo;
+    } else {  // P_FINAL
+      last_rk = e.Eo;
       eflag = FBSTAB_MAXITERATIONS;
       which = pick_xi ? 1 : 0;
       break;
     }
-    // dx = xi - xk (y-aware)
-    {
+
+    // ---- top of an inner (Newton) iteration, impl:237-260
+    bool inner_done = (inner_i >= o.max_inner_iters);
+    if (!inner_done) {
+      const double Ei = Ei_c;
+      Eo = Eo_c;
+      last_rk = Eo;
+      if ((Ei <= inner_tol && Eo < Ek) || (Ei <= o.inner_tol_min)) inner_done = true;
+      if (newton >= o.max_newton_iters) inner_done = true;
+      if (!inner_done) {
+        if (!w.newton_step(xi, xk, sigma, alpha, ri, &dx)) {
+          status = FBSTAB_STATUS_FACTOR_FAILED;
+          which = 0;
+          break;
+        }
+        newton++;
+        current_merit = 0.5 * Ei * Ei;
+#pragma unroll
+        for (int m = 4; m > 0; m--) merit[m] = merit[m - 1];
+        merit[0] = current_merit;
+        m0 = current_merit;
+        if (o.nonmonotone_linesearch) {
+#pragma unroll
+          for (int m = 1; m < 5; m++) m0 = fmax(m0, merit[m]);
+        }
+        tstep = 1.0;
+        ls_j = 0;
+        v_axpy(w, xi, tstep, dx, &xp);
+        xe = xp;
+        phase = P_TRIAL;
+        continue;
+      }
+    }
+    // ---- subproblem finished, impl:300-216
+#pragma unroll
+    for (int m = 0; m < NVR; m++) xi.v[m] = fmax(xi.v[m], 0.0);  // ProjectDuals
+    if (newton >= o.max_newton_iters) {  // impl:188-199
+      pick_xi = Eo < Ek;
+      xe = v_select(pick_xi, xi, xk);
+      phase = P_FINAL;
+      continue;
+    }
+    {  // dx = xi - xk (y-aware)
       dx.z = xi.z + (-1.0) * xk.z;
       dx.l = xi.l + (-1.0) * xk.l;
       double sq = dx.z * dx.z;
@@ -683,7 +699,16 @@ __device__ __forceinline__ void solve_one(Warp& w, const Args& A, int inst) {
     }
     xk = xi;
     prox++;
+    k++;
+    if (k >= o.max_prox_iters) {
+      eflag = FBSTAB_MAXITERATIONS;
+      which = 0;
+      break;
+    }
+    xe = xk;
+    phase = P_TOP;
   }
+
   V r;
   r.z = (which == 0) ? xk.z : (which == 1) ? xi.z : dx.z;
   r.l = (which == 0) ? xk.l : (which == 1) ? xi.l : dx.l;
@@ -714,6 +739,94 @@ __device__ __forceinline__ void solve_one(Warp& w, const Args& A, int inst) {
   }
 }
 
+// One engine stage on caller-supplied iterates (per-kernel parity tests).
+__device__ __noinline__ void run_component(Warp& w, const Args& A, int inst) {
+  const fbstab_component_io& io = A.io;
+  const int lane = w.lane;
+  const size_t oz = (size_t)inst * w.nz, ol = (size_t)inst * w.nl,
+               ov = (size_t)inst * w.nv;
+  const double alpha = A.opts.alpha;
+  V x, xb, dx;
+  R ri;
+  x.z = (lane < w.nz) ? io.z[oz + lane] : 0.0;
+  x.l = (lane < w.nl && io.l) ? io.l[ol + lane] : 0.0;
+  xb.z = (lane < w.nz) ? (io.zbar ? io.zbar[oz + lane] : x.z) : 0.0;
+  xb.l = (lane < w.nl) ? (io.lbar ? io.lbar[ol + lane] : x.l) : 0.0;
+#pragma unroll
+  for (int m = 0; m < NVR; m++) {
+    const int k = lane + 32 * m;
+    const bool in = k < w.nv;
+    x.v[m] = (in && io.v) ? io.v[ov + k] : 0.0;
+    x.y[m] = (in && io.y) ? io.y[ov + k] : 0.0;
+    xb.v[m] = in ? (io.vbar ? io.vbar[ov + k] : x.v[m]) : 0.0;
+    xb.y[m] = 0.0;
+  }
+  if (A.comp == FBSTAB_COMP_MARGIN) {
+    w.publish(x);
+    double az[NVR];
+    w.Az(az);
+#pragma unroll
+    for (int m = 0; m < NVR; m++)
+      if (lane + 32 * m < w.nv)
+        io.dy[ov + lane + 32 * m] = w.s[OFF_B + lane + 32 * m] - az[m];
+  } else if (A.comp == FBSTAB_COMP_RESIDUAL) {
+    EvalOut e = w.evaluate(x, xb, io.sigma, alpha, &ri);
+    double sq[6];
+    sq[0] = ri.z * ri.z;
+    sq[1] = ri.l * ri.l;
+    const double nzr = ri.z - io.sigma * (x.z - xb.z);
+    const double nlr = ri.l - io.sigma * (x.l - xb.l);
+    sq[3] = nzr * nzr;
+    sq[4] = nlr * nlr;
+    sq[2] = 0.0;
+    sq[5] = 0.0;
+#pragma unroll
+    for (int m = 0; m < NVR; m++) {
+      sq[2] = fma(ri.v[m], ri.v[m], sq[2]);
+      const double n = pnr(x.y[m], x.v[m], alpha);
+      sq[5] = fma(n, n, sq[5]);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; q++) sq[q] = sqrt(warp_sum(sq[q]));
+    if (lane < w.nz) io.rz[oz + lane] = ri.z;
+    if (lane < w.nl) io.rl[ol + lane] = ri.l;
+#pragma unroll
+    for (int m = 0; m < NVR; m++)
+      if (lane + 32 * m < w.nv) io.rv[ov + lane + 32 * m] = ri.v[m];
+    if (lane == 0 && io.norms) {
+#pragma unroll
+      for (int q = 0; q < 6; q++) io.norms[(size_t)inst * 8 + q] = sq[q];
+      io.norms[(size_t)inst * 8 + 6] = e.Ei;
+      io.norms[(size_t)inst * 8 + 7] = e.Eo;
+    }
+  } else if (A.comp == FBSTAB_COMP_NEWTON) {
+    // the component API passes the right-hand side r; newton_step solves for -ri
+    ri.z = (lane < w.nz) ? -io.rz[oz + lane] : 0.0;
+    ri.l = (lane < w.nl) ? -io.rl[ol + lane] : 0.0;
+#pragma unroll
+    for (int m = 0; m < NVR; m++)
+      ri.v[m] = (lane + 32 * m < w.nv) ? -io.rv[ov + lane + 32 * m] : 0.0;
+    const bool okk = w.newton_step(x, xb, io.sigma, alpha, ri, &dx);
+    if (lane < w.nz) io.dz[oz + lane] = dx.z;
+    if (lane < w.nl) io.dl[ol + lane] = dx.l;
+#pragma unroll
+    for (int m = 0; m < NVR; m++) {
+      const int k = lane + 32 * m;
+      if (k < w.nv) {
+        io.dv[ov + k] = dx.v[m];
+        io.dy[ov + k] = dx.y[m];
+        if (io.gamma) io.gamma[ov + k] = w.gamma[m];
+        if (io.mus) io.mus[ov + k] = w.mus[m];
+      }
+    }
+    if (lane == 0 && io.status)
+      io.status[inst] = okk ? FBSTAB_STATUS_OK : FBSTAB_STATUS_FACTOR_FAILED;
+  } else if (A.comp == FBSTAB_COMP_FEAS) {
+    const int feas = w.feasibility(x, io.tol);
+    if (lane == 0 && io.status) io.status[inst] = feas;
+  }
+}
+
 __global__ void __launch_bounds__(32 * kWarpsPerCta, 1)
 dense_small_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(16) double smem[];
@@ -729,7 +842,10 @@ dense_small_kernel(const __grid_constant__ Args a) {
     inst = __shfl_sync(0xffffffffu, inst, 0);
     if (inst >= a.batch) break;
     w.load(a, inst);
-    solve_one(w, a, inst);
+    if (a.comp < 0)
+      solve_one(w, a, inst);
+    else
+      run_component(w, a, inst);
   }
 }
 
@@ -768,8 +884,14 @@ int DenseSmallLaunch(const DenseSmallPlan& p, int batch, const double* H,
                             const double* f, const double* G, const double* h,
                             const double* A, const double* b, double* z, double* l,
                             double* v, double* y, fbstab_out* out,
-                            const fbstab_options& opts, cudaStream_t stream) {
+                            const fbstab_options& opts, int comp,
+                     const fbstab_component_io* io, cudaStream_t stream) {
   small::Args a;
+  a.comp = comp;
+  if (io)
+    a.io = *io;
+  else
+    memset(&a.io, 0, sizeof(a.io));
   a.nz = p.nz;
   a.nl = p.nl;
   a.nv = p.nv;

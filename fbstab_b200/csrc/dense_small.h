@@ -23,6 +23,7 @@ int DenseSmallLaunch(const DenseSmallPlan& p, int batch, const double* H,
                      const double* f, const double* G, const double* h,
                      const double* A, const double* b, double* z, double* l,
                      double* v, double* y, fbstab_out* out,
-                     const fbstab_options& opts, cudaStream_t stream);
+                     const fbstab_options& opts, int comp,
+                     const fbstab_component_io* io, cudaStream_t stream);
 
 }  // namespace fbs

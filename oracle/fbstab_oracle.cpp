@@ -537,6 +537,8 @@ struct DenseSolver : LinearSolver {
   std::vector<int> transp;
   // variant 2 storage
   Vec LE, W, LS;
+  // variant 3 storage (Gauss-Jordan of E, as the warp kernel does it)
+  Vec Ygj, dgj, Egj;
 
   DenseSolver(const DenseData* d, int variant_)
       : data(d), variant(variant_), nz(d->nz), nl(d->nl), nv(d->nv),
@@ -722,6 +724,67 @@ struct DenseSolver : LinearSolver {
     for (int i = 0; i < nl; i++) c[i] = s[i];
   }
 
+  // variant 3: unpivoted Gauss-Jordan on the symmetric E with the columns of
+  // G' and the rhs riding along, then the Schur complement in the equality
+  // block.  [E G';G -sigma I][dz;dl] = [a;c].
+  void GaussJordanSolve(double* x) {
+    const int m = nl + 1;
+    Vec M((size_t)nz * nz), Y((size_t)nz * m);
+    for (int i = 0; i < nz; i++)
+      for (int j = 0; j < nz; j++)
+        M[(size_t)i * nz + j] = (j <= i) ? Egj[(size_t)j * nz + i] : Egj[(size_t)i * nz + j];
+    for (int i = 0; i < nz; i++) {
+      for (int r = 0; r < nl; r++) Y[(size_t)i * m + r] = data->G[(size_t)i * nl + r];
+      Y[(size_t)i * m + nl] = x[i];
+    }
+    for (int k = 0; k < nz; k++) {
+      const double rd = 1.0 / M[(size_t)k * nz + k];
+      for (int i = 0; i < nz; i++) {
+        if (i == k) continue;
+        const double lik = M[(size_t)i * nz + k] * rd;
+        for (int j = k + 1; j < nz; j++)
+          M[(size_t)i * nz + j] -= lik * M[(size_t)k * nz + j];
+        for (int r = 0; r < m; r++) Y[(size_t)i * m + r] -= lik * Y[(size_t)k * m + r];
+      }
+    }
+    for (int i = 0; i < nz; i++) {
+      const double rd = 1.0 / M[(size_t)i * nz + i];
+      for (int r = 0; r < m; r++) Y[(size_t)i * m + r] *= rd;
+    }
+    // S = -sigma I - G Y ; rhs = c - G t
+    Vec S((size_t)nl * nl), rhs(nl);
+    for (int r = 0; r < nl; r++) {
+      for (int q = 0; q < nl; q++) {
+        double acc = 0.0;
+        for (int i = 0; i < nz; i++) acc += data->G[(size_t)i * nl + r] * Y[(size_t)i * m + q];
+        S[(size_t)q * nl + r] = -acc;
+      }
+      double acc = 0.0;
+      for (int i = 0; i < nz; i++) acc += data->G[(size_t)i * nl + r] * Y[(size_t)i * m + nl];
+      rhs[r] = x[nz + r] - acc;
+    }
+    for (int r = 0; r < nl; r++) S[(size_t)r * nl + r] -= sigma_gj;
+    // unpivoted Gaussian elimination on the small negative definite S
+    for (int k = 0; k < nl; k++)
+      for (int i = k + 1; i < nl; i++) {
+        const double l = S[(size_t)k * nl + i] / S[(size_t)k * nl + k];
+        for (int j = k + 1; j < nl; j++) S[(size_t)j * nl + i] -= l * S[(size_t)j * nl + k];
+        rhs[i] -= l * rhs[k];
+      }
+    for (int i = nl - 1; i >= 0; i--) {
+      double acc = rhs[i];
+      for (int j = i + 1; j < nl; j++) acc -= S[(size_t)j * nl + i] * rhs[j];
+      rhs[i] = acc / S[(size_t)i * nl + i];
+    }
+    for (int i = 0; i < nz; i++) {
+      double acc = Y[(size_t)i * m + nl];
+      for (int r = 0; r < nl; r++) acc -= Y[(size_t)i * m + r] * rhs[r];
+      x[i] = acc;
+    }
+    for (int r = 0; r < nl; r++) x[nz + r] = rhs[r];
+  }
+  double sigma_gj = 0.0;
+
   // dense_cholesky_solver.cc:32-79
   bool Initialize(const Variable& x, const Variable& xbar,
                   double sigma) override {
@@ -741,6 +804,11 @@ struct DenseSolver : LinearSolver {
         E[(size_t)j * nz + i] +=
             dot(A + (size_t)i * nv, B.data() + (size_t)j * nv, nv);
     if (variant == 2) return CholSchurFactor(sigma);
+    if (variant == 3) {
+      Egj = E;
+      sigma_gj = sigma;
+      return true;
+    }
     // K lower blocks (upper-right block is never written nor read)
     for (int j = 0; j < nz; j++) {
       for (int i = 0; i < nz; i++) k(i, j) = E[(size_t)j * nz + i];
@@ -762,6 +830,8 @@ struct DenseSolver : LinearSolver {
 
     if (variant == 2)
       CholSchurSolve(r1.data());
+    else if (variant == 3)
+      GaussJordanSolve(r1.data());
     else
       LdltSolve(r1.data());
     for (int i = 0; i < nz; i++) x->z[i] = r1[i];

@@ -93,7 +93,9 @@ void oracle_residual(const oracle_problem* p, int kind, double alpha,
 /* LinearSolver::Initialize(x,xbar,sigma) then ::Solve(r,&dx).
  * variant (dense only): 0 = Eigen-style diagonally pivoted LDLT on K (reference),
  *                       1 = same LDLT without pivoting,
- *                       2 = Cholesky of E + Cholesky of the Schur complement.
+ *                       2 = Cholesky of E + Cholesky of the Schur complement,
+ *                       3 = unpivoted Gauss-Jordan of E + Schur complement
+ *                           (the elimination order of the warp kernel).
  * returns 0 ok, 1 factor failed. gamma/mus may be NULL. */
 int oracle_linear_solve(const oracle_problem* p, int variant, double alpha,
                         double sigma, const double* z, const double* l,
