@@ -2,25 +2,28 @@
 // (nz <= 32, nl <= 8, nv <= 64; BASELINE config 2 is exactly 32/8/64).
 //
 // One warp owns one QP instance for its whole solve:
-//  * the problem data (H, A, G, f, h, b: 26.8 KB) is staged ONCE into shared
-//    memory (zero padded to 32/8/64, rows contiguous + padded leading dimension
-//    34 so that row reads, column reads and the DMMA fragment reads are all
-//    bank-conflict free or at worst 2-way);
-//  * every iterate / residual vector lives in registers: lane j owns entry j
-//    of z-type vectors, lanes 0..7 own l, lane k owns rows k and k+32 of
-//    v-type vectors;
+//  * the problem matrices (H, A, G: 26 KB) are staged ONCE into the warp's slab
+//    of shared memory (zero padded to 32/8/64, rows contiguous with a padded
+//    leading dimension of 34 so that row reads, column reads and the DMMA
+//    fragment reads are all bank-conflict free or at worst 2-way); every
+//    access uses explicit shared-space instructions (LDS/STS);
+//  * every iterate / residual vector and f, h, b live in registers: lane j owns
+//    entry j of z-type vectors, lanes 0..7 own l, lane k owns rows k and k+32
+//    of v-type vectors;
 //  * E = H + sigma I + A' Gamma A is accumulated on the FP64 tensor cores
 //    (mma.sync.m8n8k4.f64, 160 DMMAs for the 10 lower 8x8 blocks);
 //  * the KKT matrix K = [E G'; G -sigma I] is eliminated in registers: lane i
-//    holds the full symmetric row i of E (so after elimination it owns row i
-//    of L *and* column i of L'), the G block is held column-wise (lane j owns
-//    column j), pivot columns are broadcast through a 40-double shared buffer,
-//    and the right-hand side rides along as a ninth row, which fuses the
-//    forward substitution into the factorisation;
-//  * the 8x8 Schur complement -sigma I - X' D^-1 X is formed with 16 DMMAs and
-//    factored by lanes 0..7.
-// Converged instances retire and the warp pulls the next index from a global
-// atomic counter (persistent kernel, no host round trips).
+//    holds the full symmetric row i of E, the G block is held column-wise
+//    (lane j owns column j), pivot rows are broadcast through a small shared
+//    buffer, and the right-hand side rides along as a ninth augmented column,
+//    which fuses the forward substitution into the factorisation;
+//  * the 8x8 Schur complement -sigma I - G E^-1 G' is formed with 16 DMMAs and
+//    eliminated by lanes 0..7.
+// The kernel is persistent: one CTA of kWarps independent warps per SM; a warp
+// that finishes an instance pulls the next index from a global atomic counter
+// (no host round trips, natural load balance over the 9..28-iteration spread)
+// and prefetches that instance's data into L2 while it is still solving the
+// current one.
 //
 // Follows the same reference code as engine.cuh / dense_problem.cuh
 // (fbstab_algorithm-impl.h:113-304, dense_cholesky_solver.cc:32-148,
@@ -35,32 +38,33 @@ namespace fbs {
 
 namespace small {
 
-constexpr int NZ = 32;    // padded sizes
+constexpr int NZ = 32;  // padded sizes
 constexpr int NL = 8;
 constexpr int NV = 64;
 constexpr int NVR = NV / 32;
-constexpr int LD = 34;    // leading dimension of Hs/As/Gs rows
-constexpr int kWarpsPerCta = 2;
+constexpr int LD = 34;  // leading dimension of Hs/As/Gs rows
+constexpr int kWarps = 7;  // independent warps (= instances in flight) per CTA
 
 // shared-memory layout of one warp's slab (in doubles)
-constexpr int OFF_H = 0;                       // Hs[j + LD*i] = H(i,j)
-constexpr int OFF_A = OFF_H + NZ * LD;         // As[j + LD*k] = A(k,j)
-constexpr int OFF_G = OFF_A + NV * LD;         // Gs[j + LD*r] = G(r,j)
-constexpr int OFF_F = OFF_G + NL * LD;         // f(32) h(8) b(64)
-constexpr int OFF_HV = OFF_F + NZ;
-constexpr int OFF_B = OFF_HV + NL;
-constexpr int OFF_ZB = OFF_B + NV;             // broadcast copies: z(32) l(8) v(64)
+constexpr int OFF_H = 0;                 // Hs[j + LD*i] = H(i,j)
+constexpr int OFF_A = OFF_H + NZ * LD;   // As[j + LD*k] = A(k,j)
+constexpr int OFF_G = OFF_A + NV * LD;   // Gs[j + LD*r] = G(r,j)
+constexpr int OFF_ZB = OFF_G + NL * LD;  // broadcast copies: z(32) l(8) v(64)
 constexpr int OFF_LB = OFF_ZB + NZ;
 constexpr int OFF_VB = OFF_LB + NL;
-constexpr int OFF_COL = OFF_VB + NV;           // 2 x (32 shifted row + pivot + 10 aug) buffers
+constexpr int OFF_SCR = OFF_VB + NV;  // scratch shared by the phases of a Newton step
+constexpr int SCR_SIZE = 392;  // Gamma (64) | transposition (8*LD) | pivot rows | Schur
+// pivot-row buffers of the elimination live in the scratch (free at that time):
+// 2 x (32 shifted row entries + pivot + pad + 10 augmented)
+constexpr int OFF_COL = OFF_SCR;
 constexpr int COL_STRIDE = 44;
-constexpr int OFF_SCR = OFF_COL + 2 * COL_STRIDE;  // transposition / Schur scratch
-constexpr int SCR_SIZE = 392;  // >= 8*LD (transposition), >= 392 (Schur: Y 320, S 64, T 8)
 constexpr int SLAB = OFF_SCR + SCR_SIZE;
 static_assert(SLAB % 2 == 0, "slab must keep 16-byte alignment");
 static_assert(OFF_A % 2 == 0 && OFF_G % 2 == 0 && OFF_ZB % 2 == 0 &&
                   OFF_VB % 2 == 0 && OFF_COL % 2 == 0 && OFF_SCR % 2 == 0,
               "LDS.128 targets must be 16-byte aligned");
+static_assert((size_t)SLAB * kWarps * sizeof(double) <= 232448,
+              "slabs must fit the 227 KB of shared memory of one SM");
 
 struct Args {
   int nz, nl, nv, batch;
@@ -80,11 +84,25 @@ struct R {  // residual in registers
   double z, l, v[NVR];
 };
 
-__device__ __forceinline__ double2 lds2(const double* p) {
-  return *reinterpret_cast<const double2*>(p);
+// ---- explicit shared-space accessors (32-bit shared byte addresses) ---------
+__device__ __forceinline__ double lds(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
 }
-__device__ __forceinline__ void sts2(double* p, double a, double b) {
-  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+__device__ __forceinline__ double2 lds2(unsigned a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts(unsigned a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts2(unsigned a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile(
@@ -95,11 +113,14 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 __device__ __forceinline__ double bcast(double v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
 }
+// byte address of double index i in a slab at shared address sb
+__device__ __forceinline__ constexpr unsigned D(int i) { return 8u * (unsigned)i; }
 
 struct Warp {
-  double* s;  // this warp's slab
+  unsigned sb;  // shared-space byte address of this warp's slab
   int lane;
   int nz, nl, nv;
+  double fr, hr, br[NVR];  // f(lane), h(lane), b(lane + 32 m)
   // Newton-step state
   double gamma[NVR], mus[NVR];
   double a[NZ];      // row `lane` of E, rotated left once per elimination step
@@ -110,65 +131,65 @@ struct Warp {
   // ---- products -------------------------------------------------------------
   __device__ __forceinline__ void publish(const V& x) {
     __syncwarp();
-    s[OFF_ZB + lane] = x.z;
-    if (lane < NL) s[OFF_LB + lane] = x.l;
+    sts(sb + D(OFF_ZB + lane), x.z);
+    if (lane < NL) sts(sb + D(OFF_LB + lane), x.l);
 #pragma unroll
-    for (int m = 0; m < NVR; m++) s[OFF_VB + lane + 32 * m] = x.v[m];
+    for (int m = 0; m < NVR; m++) sts(sb + D(OFF_VB + lane + 32 * m), x.v[m]);
     __syncwarp();
   }
-  // (M zb)[row] for a row-contiguous 32-wide matrix row
-  __device__ __forceinline__ double row_dot(const double* row) const {
-    const double* zb = s + OFF_ZB;
+  // (M zb)[row] for a row-contiguous 32-wide matrix row at shared address `row`
+  __device__ __forceinline__ double row_dot(unsigned row) const {
+    const unsigned zb = sb + D(OFF_ZB);
     double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
+#pragma unroll
     for (int j = 0; j < NZ; j += 2) {
-      const double2 hh = lds2(row + j);
-      const double2 zz = lds2(zb + j);
+      const double2 hh = lds2(row + D(j));
+      const double2 zz = lds2(zb + D(j));
       s0 = fma(hh.x, zz.x, s0);
       s1 = fma(hh.y, zz.y, s1);
     }
     return s0 + s1;
   }
-  __device__ __forceinline__ double Hz() const { return row_dot(s + OFF_H + LD * lane); }
+  __device__ __forceinline__ double Hz() const { return row_dot(sb + D(OFF_H + LD * lane)); }
   // (G' lb)[lane]
   __device__ __forceinline__ double GTl() const {
-    const double* gc = s + OFF_G + lane;
-    const double* lb = s + OFF_LB;
+    const unsigned gc = sb + D(OFF_G + lane);
+    const unsigned lb = sb + D(OFF_LB);
     double s0 = 0.0;
 #pragma unroll
     for (int r = 0; r < NL; r += 2) {
-      const double2 ll = lds2(lb + r);
-      s0 = fma(gc[LD * r], ll.x, s0);
-      s0 = fma(gc[LD * (r + 1)], ll.y, s0);
+      const double2 ll = lds2(lb + D(r));
+      s0 = fma(lds(gc + D(LD * r)), ll.x, s0);
+      s0 = fma(lds(gc + D(LD * (r + 1))), ll.y, s0);
     }
     return s0;
   }
   // (A' vb)[lane]
   __device__ __forceinline__ double ATv() const {
-    const double* ac = s + OFF_A + lane;
-    const double* vb = s + OFF_VB;
+    const unsigned ac = sb + D(OFF_A + lane);
+    const unsigned vb = sb + D(OFF_VB);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < NV; k += 4) {
-      const double2 v0 = lds2(vb + k);
-      const double2 v1 = lds2(vb + k + 2);
-      s0 = fma(ac[LD * k], v0.x, s0);
-      s1 = fma(ac[LD * (k + 1)], v0.y, s1);
-      s2 = fma(ac[LD * (k + 2)], v1.x, s2);
-      s3 = fma(ac[LD * (k + 3)], v1.y, s3);
+      const double2 v0 = lds2(vb + D(k));
+      const double2 v1 = lds2(vb + D(k + 2));
+      s0 = fma(lds(ac + D(LD * k)), v0.x, s0);
+      s1 = fma(lds(ac + D(LD * (k + 1))), v0.y, s1);
+      s2 = fma(lds(ac + D(LD * (k + 2))), v1.x, s2);
+      s3 = fma(lds(ac + D(LD * (k + 3))), v1.y, s3);
     }
     return (s0 + s1) + (s2 + s3);
   }
   // (G zb)[lane % 8], same value in the four lanes sharing lane % 8
   __device__ __forceinline__ double Gz() const {
     const int r = lane & 7, q = lane >> 3;
-    const double* gr = s + OFF_G + LD * r + 8 * q;
-    const double* zb = s + OFF_ZB + 8 * q;
+    const unsigned gr = sb + D(OFF_G + LD * r + 8 * q);
+    const unsigned zb = sb + D(OFF_ZB + 8 * q);
     double s0 = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-      const double2 gg = lds2(gr + j);
-      const double2 zz = lds2(zb + j);
+      const double2 gg = lds2(gr + D(j));
+      const double2 zz = lds2(zb + D(j));
       s0 = fma(gg.x, zz.x, s0);
       s0 = fma(gg.y, zz.y, s0);
     }
@@ -179,18 +200,18 @@ struct Warp {
   // (A zb)[lane + 32 m]
   __device__ __forceinline__ void Az(double (&o)[NVR]) const {
 #pragma unroll
-    for (int m = 0; m < NVR; m++) o[m] = row_dot(s + OFF_A + LD * (lane + 32 * m));
+    for (int m = 0; m < NVR; m++) o[m] = row_dot(sb + D(OFF_A + LD * (lane + 32 * m)));
   }
 
   // ---- fused residual evaluation (see engine.cuh) ---------------------------
   __device__ __forceinline__ EvalOut evaluate(const V& x, const V& xbar,
                                               double sigma, double alpha, R* ri) {
     publish(x);
-    double tz = s[OFF_F + lane] + Hz();
+    double tz = fr + Hz();
     tz += GTl();
     tz += ATv();
     const double gz = Gz();
-    const double tl = (lane < NL) ? s[OFF_HV + lane] - gz : 0.0;
+    const double tl = (lane < NL) ? hr - gz : 0.0;
     double si = 0.0, so = 0.0;
     {
       const double r = tz + sigma * (x.z - xbar.z);
@@ -220,46 +241,46 @@ struct Warp {
     return e;
   }
 
-  // One segment of the Gauss-Jordan elimination of E: steps k0..k1-1, during
-  // which at most W trailing columns are still non-zero.  Every step the row
-  // registers rotate left by one, so a[0] is always the entry in the pivot
-  // column and the loop body is the same for every k (compact code, static
-  // register indices).  Lane k broadcasts its (already rotated) pivot row
-  // through shared memory, so it is read from fixed addresses.
-  template <int W>
-  __device__ __forceinline__ void eliminate(int k0, int k1) {
-#pragma unroll 1
-    for (int k = k0; k < k1; k++) {
-      double* cb = s + OFF_COL + COL_STRIDE * (k & 1);
+  // Gauss-Jordan elimination of E with the [G' rhs] columns riding along,
+  // fully unrolled: every register index is static and step k touches exactly
+  // the 31-k trailing columns.  Lane k broadcasts its pivot row through one of
+  // two alternating shared buffers (cb[j] = E(k,j) for j > k, cb[32] = pivot,
+  // cb[34..42] = augmented columns), so one __syncwarp per step suffices.
+  __device__ __forceinline__ void eliminate() {
+#pragma unroll
+    for (int k = 0; k < NZ; k++) {
+      const unsigned cb = sb + D(OFF_COL + COL_STRIDE * (k & 1));
+      const int j0 = k + 1;             // first trailing column
+      const int je = (j0 + 1) & ~1;     // first even trailing column
       if (lane == k) {
         // the pivot row itself (NOT the pivot column taken from the other
         // lanes: after the 1e8-scale cancellations of A' Gamma A the (k,j) and
         // (j,k) entries differ at the 1e-8 relative level, and mixing them
         // ruins the accuracy of dz along the active-constraint normals)
-        cb[32] = a[0];
+        sts(cb + D(32), a[k]);
+        if ((j0 & 1) && j0 < NZ) sts(cb + D(j0), a[j0]);
 #pragma unroll
-        for (int m = 1; m + 1 <= W; m += 2) sts2(cb + m - 1, a[m], a[m + 1]);
-        if (W & 1) cb[W - 1] = a[W];
+        for (int j = je; j + 1 < NZ; j += 2) sts2(cb + D(j), a[j], a[j + 1]);
 #pragma unroll
         for (int r = 0; r < NL + 1; r += 2)
-          sts2(cb + 34 + r, g[r], (r + 1 < NL + 1) ? g[r + 1] : 0.0);
+          sts2(cb + D(34 + r), g[r], (r + 1 < NL + 1) ? g[r + 1] : 0.0);
       }
       __syncwarp();
-      const double d = cb[32];
+      const double d = lds(cb + D(32));
       if (!(fabs(d) > 0.0)) ok = false;
       const double rd = 1.0 / d;
       if (lane == k) dinv = rd;
-      const double lik = (lane != k) ? a[0] * rd : 0.0;
+      const double lik = (lane != k) ? a[k] * rd : 0.0;
+      if ((j0 & 1) && j0 < NZ) a[j0] = fma(-lik, lds(cb + D(j0)), a[j0]);
 #pragma unroll
-      for (int m = 1; m <= W; m += 2) {
-        const double2 c = lds2(cb + m - 1);
-        a[m - 1] = fma(-lik, c.x, a[m]);
-        if (m + 1 < NZ) a[m] = fma(-lik, c.y, a[m + 1]);
+      for (int j = je; j + 1 < NZ; j += 2) {
+        const double2 c = lds2(cb + D(j));
+        a[j] = fma(-lik, c.x, a[j]);
+        a[j + 1] = fma(-lik, c.y, a[j + 1]);
       }
-      if (W < NZ - 1) a[W] = 0.0; else a[NZ - 1] = 0.0;
 #pragma unroll
       for (int r = 0; r < NL + 1; r += 2) {
-        const double2 xr = lds2(cb + 34 + r);
+        const double2 xr = lds2(cb + D(34 + r));
         g[r] = fma(-lik, xr.x, g[r]);
         if (r + 1 < NL + 1) g[r + 1] = fma(-lik, xr.y, g[r + 1]);
       }
@@ -272,6 +293,7 @@ struct Warp {
                                               double sigma, double alpha,
                                               const R& ri, V* dx) {
     const int r8 = lane >> 2, c4 = lane & 3;
+    const unsigned scr = sb + D(OFF_SCR);
     ok = true;
     {
       double r2[NVR], Gam[NVR];
@@ -286,8 +308,8 @@ struct Warp {
       __syncwarp();
 #pragma unroll
       for (int m = 0; m < NVR; m++) {
-        s[OFF_VB + lane + 32 * m] = r2[m];
-        s[OFF_SCR + lane + 32 * m] = Gam[m];
+        sts(sb + D(OFF_VB + lane + 32 * m), r2[m]);
+        sts(scr + D(lane + 32 * m), Gam[m]);
       }
       __syncwarp();
     }
@@ -300,18 +322,18 @@ struct Warp {
       for (int I = 0; I < 4; I++)
 #pragma unroll
         for (int J = 0; J <= I; J++) {
-          const double2 hh = lds2(s + OFF_H + LD * (8 * I + r8) + 8 * J + 2 * c4);
+          const double2 hh = lds2(sb + D(OFF_H + LD * (8 * I + r8) + 8 * J + 2 * c4));
           C[I][J][0] = hh.x + ((I == J && r8 == 2 * c4) ? sigma : 0.0);
           C[I][J][1] = hh.y + ((I == J && r8 == 2 * c4 + 1) ? sigma : 0.0);
         }
 #pragma unroll 1
       for (int kc = 0; kc < NV / 4; kc++) {
-        const double* ar = s + OFF_A + LD * (4 * kc + c4) + r8;
-        const double gk = s[OFF_SCR + 4 * kc + c4];
+        const unsigned ar = sb + D(OFF_A + LD * (4 * kc + c4) + r8);
+        const double gk = lds(scr + D(4 * kc + c4));
         double af[4], bf[4];
 #pragma unroll
         for (int X = 0; X < 4; X++) {
-          af[X] = ar[8 * X];
+          af[X] = lds(ar + D(8 * X));
           bf[X] = gk * af[X];
         }
 #pragma unroll
@@ -325,71 +347,70 @@ struct Warp {
         __syncwarp();
 #pragma unroll
         for (int J = 0; J <= I; J++)
-          sts2(s + OFF_SCR + LD * r8 + 8 * J + 2 * c4, C[I][J][0], C[I][J][1]);
+          sts2(scr + D(LD * r8 + 8 * J + 2 * c4), C[I][J][0], C[I][J][1]);
         __syncwarp();
         if ((lane >> 3) == I) {
-          const double* row = s + OFF_SCR + LD * (lane & 7);
+          const unsigned row = scr + D(LD * (lane & 7));
 #pragma unroll
           for (int j = 0; j < NZ; j += 2) {
             if (j < 8 * (I + 1)) {
-              const double2 t = lds2(row + j);
+              const double2 t = lds2(row + D(j));
               a[j] = t.x;
               a[j + 1] = t.y;
             }
           }
         } else if ((lane >> 3) < I) {
 #pragma unroll
-          for (int rr = 0; rr < 8; rr++) a[8 * I + rr] = s[OFF_SCR + LD * rr + lane];
+          for (int rr = 0; rr < 8; rr++) a[8 * I + rr] = lds(scr + D(LD * rr + lane));
         }
       }
     }
     // G block column-wise (lane j owns column j); the rhs is already in g[8]
 #pragma unroll
-    for (int r = 0; r < NL; r++) g[r] = s[OFF_G + LD * r + lane];
+    for (int r = 0; r < NL; r++) g[r] = lds(sb + D(OFF_G + LD * r + lane));
 
-    // Gauss-Jordan elimination of the E block (4 segments of 8 steps)
-    eliminate<31>(0, 8);
-    eliminate<23>(8, 16);
-    eliminate<15>(16, 24);
-    eliminate<7>(24, 32);
+    // Gauss-Jordan elimination of the E block; the
+    // pivot-row buffers alias the transposition scratch read just above
+    __syncwarp();
+    eliminate();
     // lane i now holds d_i * (E^-1 [G' a])(i,:) in g[0..8] and dinv = 1/d_i
 
     // Schur complement S = -sigma I - G Y, rhs c - G t  with [Y t] = E^-1 [G' a]
     __syncwarp();
     {
-      double* xs = s + OFF_SCR;  // Ys[r + 10*i], r = 0..8
+      // Ys[r + 10*i], r = 0..8
 #pragma unroll
       for (int r = 0; r < NL + 1; r += 2)
-        sts2(xs + 10 * lane + r, g[r] * dinv, (r + 1 < NL + 1) ? g[r + 1] * dinv : 0.0);
+        sts2(scr + D(10 * lane + r), g[r] * dinv,
+             (r + 1 < NL + 1) ? g[r + 1] * dinv : 0.0);
     }
     __syncwarp();
     double S0 = 0.0, S1 = 0.0, T0 = 0.0, T1 = 0.0;
 #pragma unroll 2
     for (int kc = 0; kc < NZ / 4; kc++) {
-      const double* xs = s + OFF_SCR;
       const int i = 4 * kc + c4;
-      const double ge = s[OFF_G + LD * r8 + i];  // G(r8, i)
-      const double ye = xs[10 * i + r8];         // Y(i, r8)
-      const double te = xs[10 * i + NL];         // t(i)
+      const double ge = lds(sb + D(OFF_G + LD * r8 + i));  // G(r8, i)
+      const double ye = lds(scr + D(10 * i + r8));         // Y(i, r8)
+      const double te = lds(scr + D(10 * i + NL));         // t(i)
       dmma(S0, S1, ge, ye);
       dmma(T0, T1, ge, te);
     }
     __syncwarp();
-    {
-      double* sc = s + OFF_SCR;
-      sts2(sc + 320 + 8 * r8 + 2 * c4, S0, S1);
-      if (c4 == 0) sc[384 + r8] = T0;
-    }
+    sts2(scr + D(320 + 8 * r8 + 2 * c4), S0, S1);
+    if (c4 == 0) sts(scr + D(384 + r8), T0);
     __syncwarp();
     double dl = 0.0;
     {
       // 8x8 elimination by lanes 0..7 (lane r = row r)
-      const double* sc = s + OFF_SCR;
       const int r = lane & 7;
       double srow[NL];
 #pragma unroll
-      for (int j = 0; j < NL; j++) srow[j] = -sc[320 + 8 * r + j] - ((j == r) ? sigma : 0.0);
-      double rhs = ((lane < NL) ? ri.l : 0.0) - sc[384 + r];
+      for (int j = 0; j < NL; j += 2) {
+        const double2 t = lds2(scr + D(320 + 8 * r + j));
+        srow[j] = -t.x - ((j == r) ? sigma : 0.0);
+        srow[j + 1] = -t.y - ((j + 1 == r) ? sigma : 0.0);
+      }
+      double rhs = ((lane < NL) ? ri.l : 0.0) - lds(scr + D(384 + r));
       double dsi = 0.0;
 #pragma unroll
       for (int k = 0; k < NL; k++) {
@@ -418,14 +439,14 @@ struct Warp {
     dx->l = dl;
     // dv = (rv + gamma .* (A dz)) ./ mus ; dy = b - A dz
     __syncwarp();
-    s[OFF_ZB + lane] = dz;
+    sts(sb + D(OFF_ZB + lane), dz);
     __syncwarp();
     double adz[NVR];
     Az(adz);
 #pragma unroll
     for (int m = 0; m < NVR; m++) {
       dx->v[m] = (gamma[m] * adz[m] + (-ri.v[m])) / mus[m];
-      dx->y[m] = s[OFF_B + lane + 32 * m] - adz[m];
+      dx->y[m] = br[m] - adz[m];
     }
     return ok;
   }
@@ -443,13 +464,13 @@ struct Warp {
     const double d2 = (lane < NL) ? fabs(gz) : 0.0;
     const double d3 = fabs(Hz());
     const double w = warp_max(fabs(dx.z));
-    const double d4 = warp_sum(s[OFF_F + lane] * dx.z);
+    const double d4 = warp_sum(fr * dx.z);
     const double p1 = warp_max(fabs(ATv() + GTl()));
-    double p2 = (lane < NL) ? s[OFF_HV + lane] * dx.l : 0.0;
+    double p2 = (lane < NL) ? hr * dx.l : 0.0;
     double umax = fabs(dx.l);
 #pragma unroll
     for (int m = 0; m < NVR; m++) {
-      p2 = fma(s[OFF_B + lane + 32 * m], dx.v[m], p2);
+      p2 = fma(br[m], dx.v[m], p2);
       umax = fmax(umax, fabs(dx.v[m]));
     }
     p2 = warp_sum(p2);
@@ -462,29 +483,53 @@ struct Warp {
   }
 
   // ---- data staging ----------------------------------------------------------
+  // Transposes one column-major rows x cols matrix into the row-contiguous
+  // padded layout; loads are issued in batches of 8 per lane so that the
+  // global-memory latency is paid once per batch, not once per element.
+  __device__ __forceinline__ void stage_matrix(const double* src, int rows, int cols,
+                                               int off) {
+    const int n = rows * cols;
+    for (int e0 = 0; e0 < n; e0 += 256) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + lane + 32 * u;
+        t[u] = (e < n) ? __ldg(src + e) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + lane + 32 * u;
+        if (e < n) {
+          const int c = e / rows, r = e - c * rows;
+          sts(sb + D(off + LD * r + c), t[u]);
+        }
+      }
+    }
+  }
   __device__ __forceinline__ void load(const Args& a_, int inst) {
     __syncwarp();
-    for (int e = lane; e < SLAB; e += 32) s[e] = 0.0;
+    if (nz < NZ || nl < NL || nv < NV) {  // zero padding of the unused part
+      for (int e = 2 * lane; e < OFF_ZB; e += 64) sts2(sb + D(e), 0.0, 0.0);
+      __syncwarp();
+    }
+    stage_matrix(a_.H + (size_t)inst * nz * nz, nz, nz, OFF_H);
+    stage_matrix(a_.A + (size_t)inst * nv * nz, nv, nz, OFF_A);
+    stage_matrix(a_.G + (size_t)inst * nl * nz, nl, nz, OFF_G);
+    fr = (lane < nz) ? __ldg(a_.f + (size_t)inst * nz + lane) : 0.0;
+    hr = (lane < nl) ? __ldg(a_.h + (size_t)inst * nl + lane) : 0.0;
+#pragma unroll
+    for (int m = 0; m < NVR; m++)
+      br[m] = (lane + 32 * m < nv) ? __ldg(a_.b + (size_t)inst * nv + lane + 32 * m) : 0.0;
     __syncwarp();
-    const double* H = a_.H + (size_t)inst * nz * nz;
-    for (int e = lane; e < nz * nz; e += 32) {
-      const int i = e % nz, j = e / nz;
-      s[OFF_H + LD * i + j] = H[e];
-    }
-    const double* A = a_.A + (size_t)inst * nv * nz;
-    for (int e = lane; e < nv * nz; e += 32) {
-      const int k = e % nv, j = e / nv;
-      s[OFF_A + LD * k + j] = A[e];
-    }
-    const double* G = a_.G + (size_t)inst * nl * nz;
-    for (int e = lane; e < nl * nz; e += 32) {
-      const int r = e % nl, j = e / nl;
-      s[OFF_G + LD * r + j] = G[e];
-    }
-    if (lane < nz) s[OFF_F + lane] = a_.f[(size_t)inst * nz + lane];
-    if (lane < nl) s[OFF_HV + lane] = a_.h[(size_t)inst * nl + lane];
-    for (int k = lane; k < nv; k += 32) s[OFF_B + k] = a_.b[(size_t)inst * nv + k];
-    __syncwarp();
+  }
+  // Pulls instance `inst`'s matrices towards L2 (one 128-byte line per request).
+  __device__ __forceinline__ void prefetch(const Args& a_, int inst) const {
+    const char* H = (const char*)(a_.H + (size_t)inst * nz * nz);
+    const char* A = (const char*)(a_.A + (size_t)inst * nv * nz);
+    const char* G = (const char*)(a_.G + (size_t)inst * nl * nz);
+    for (int o = 128 * lane; o < 8 * nz * nz; o += 128 * 32) prefetch_l2(H + o);
+    for (int o = 128 * lane; o < 8 * nv * nz; o += 128 * 32) prefetch_l2(A + o);
+    for (int o = 128 * lane; o < 8 * nl * nz; o += 128 * 32) prefetch_l2(G + o);
   }
 };
 
@@ -496,7 +541,7 @@ __device__ __forceinline__ void v_axpy(const Warp& w, const V& src, double a,
   for (int m = 0; m < NVR; m++) {
     dst->v[m] = src.v[m] + a * dx.v[m];
     const double y = src.y[m] + a * dx.y[m];
-    dst->y[m] = y + (-a) * w.s[OFF_B + w.lane + 32 * m];
+    dst->y[m] = y + (-a) * w.br[m];
   }
 }
 
@@ -531,18 +576,17 @@ __device__ __forceinline__ void solve_one(Warp& w, const Args& A, int inst) {
   for (int m = 0; m < NVR; m++)
     xk.v[m] = (lane + 32 * m < w.nv) ? A.v[(size_t)inst * w.nv + lane + 32 * m] : 0.0;
   // forcing norm and margin y = b - A z
-  double fn = w.s[OFF_F + lane] * w.s[OFF_F + lane];
-  if (lane < NL) fn = fma(w.s[OFF_HV + lane], w.s[OFF_HV + lane], fn);
+  double fn = w.fr * w.fr;
+  if (lane < NL) fn = fma(w.hr, w.hr, fn);
 #pragma unroll
-  for (int m = 0; m < NVR; m++)
-    fn = fma(w.s[OFF_B + lane + 32 * m], w.s[OFF_B + lane + 32 * m], fn);
+  for (int m = 0; m < NVR; m++) fn = fma(w.br[m], w.br[m], fn);
   const double combo_tol = o.abs_tol + o.rel_tol * (1.0 + sqrt(warp_sum(fn)));
   w.publish(xk);
   {
     double az[NVR];
     w.Az(az);
 #pragma unroll
-    for (int m = 0; m < NVR; m++) xk.y[m] = w.s[OFF_B + lane + 32 * m] - az[m];
+    for (int m = 0; m < NVR; m++) xk.y[m] = w.br[m] - az[m];
   }
   xi = xk;
   xp = xk;
@@ -603,7 +647,7 @@ __device__ __forceinline__ void solve_one(Warp& w, const Args& A, int inst) {
         Ei_c = e.Ei;
         Eo_c = e.Eo;
         inner_i++;
-        } else {
+      } else {
         tstep *= o.beta;
         backtracks++;
         ls_j++;
@@ -683,7 +727,7 @@ __device__ __forceinline__ void solve_one(Warp& w, const Args& A, int inst) {
         dx.v[m] = xi.v[m] + (-1.0) * xk.v[m];
         sq = fma(dx.v[m], dx.v[m], sq);
         const double y = xi.y[m] + (-1.0) * xk.y[m];
-        dx.y[m] = y + w.s[OFF_B + lane + 32 * m];
+        dx.y[m] = y + w.br[m];
       }
       dx_norm = sqrt(warp_sum(sq));
     }
@@ -740,7 +784,7 @@ __device__ __forceinline__ void solve_one(Warp& w, const Args& A, int inst) {
 }
 
 // One engine stage on caller-supplied iterates (per-kernel parity tests).
-__device__ __noinline__ void run_component(Warp& w, const Args& A, int inst) {
+__device__ __forceinline__ void run_component(Warp& w, const Args& A, int inst) {
   const fbstab_component_io& io = A.io;
   const int lane = w.lane;
   const size_t oz = (size_t)inst * w.nz, ol = (size_t)inst * w.nl,
@@ -767,8 +811,7 @@ __device__ __noinline__ void run_component(Warp& w, const Args& A, int inst) {
     w.Az(az);
 #pragma unroll
     for (int m = 0; m < NVR; m++)
-      if (lane + 32 * m < w.nv)
-        io.dy[ov + lane + 32 * m] = w.s[OFF_B + lane + 32 * m] - az[m];
+      if (lane + 32 * m < w.nv) io.dy[ov + lane + 32 * m] = w.br[m] - az[m];
   } else if (A.comp == FBSTAB_COMP_RESIDUAL) {
     EvalOut e = w.evaluate(x, xb, io.sigma, alpha, &ri);
     double sq[6];
@@ -827,48 +870,60 @@ __device__ __noinline__ void run_component(Warp& w, const Args& A, int inst) {
   }
 }
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 1)
+// COMPONENT = false: the solver.  COMPONENT = true: one stage per instance
+// (parity tests); a separate instantiation keeps the solver's code compact.
+template <bool COMPONENT>
+__global__ void __launch_bounds__(32 * kWarps, 1)
 dense_small_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(16) double smem[];
   Warp w;
   w.lane = threadIdx.x & 31;
-  w.s = smem + (size_t)(threadIdx.x >> 5) * SLAB;
+  w.sb = (unsigned)__cvta_generic_to_shared(smem) +
+         (unsigned)(threadIdx.x >> 5) * (unsigned)(SLAB * sizeof(double));
   w.nz = a.nz;
   w.nl = a.nl;
   w.nv = a.nv;
-  for (;;) {
-    int inst = 0;
-    if (w.lane == 0) inst = atomicAdd(a.counter, 1);
-    inst = __shfl_sync(0xffffffffu, inst, 0);
-    if (inst >= a.batch) break;
+  int inst = 0;
+  if (w.lane == 0) inst = atomicAdd(a.counter, 1);
+  inst = __shfl_sync(0xffffffffu, inst, 0);
+  while (inst < a.batch) {
     w.load(a, inst);
-    if (a.comp < 0)
-      solve_one(w, a, inst);
-    else
+    // reserve the next instance now and pull its data towards L2 meanwhile
+    int next = 0;
+    if (w.lane == 0) next = atomicAdd(a.counter, 1);
+    next = __shfl_sync(0xffffffffu, next, 0);
+    if (next < a.batch) w.prefetch(a, next);
+    if (COMPONENT)
       run_component(w, a, inst);
+    else
+      solve_one(w, a, inst);
+    inst = next;
   }
 }
 
 }  // namespace small
 
 int DenseSmallInit(DenseSmallPlan* p, int nz, int nl, int nv, int sm_count,
-                          int* counter) {
+                   int* counter) {
   p->enabled = false;
   if (nz > small::NZ || nl > small::NL || nv > small::NV) return 0;
   p->nz = nz;
   p->nl = nl;
   p->nv = nv;
   p->counter = counter;
-  p->smem = sizeof(double) * small::SLAB * small::kWarpsPerCta;
-  if (cudaFuncSetAttribute(small::dense_small_kernel,
+  p->smem = sizeof(double) * small::SLAB * small::kWarps;
+  if (cudaFuncSetAttribute(small::dense_small_kernel<false>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)p->smem) != cudaSuccess ||
+      cudaFuncSetAttribute(small::dense_small_kernel<true>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)p->smem) != cudaSuccess) {
     cudaGetLastError();
-    return 0;  // fall back to the generic kernel
+    return 0;  // the generic kernel takes over
   }
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &occ, small::dense_small_kernel, 32 * small::kWarpsPerCta, p->smem) !=
+          &occ, small::dense_small_kernel<false>, 32 * small::kWarps, p->smem) !=
           cudaSuccess ||
       occ < 1) {
     cudaGetLastError();
@@ -881,10 +936,10 @@ int DenseSmallInit(DenseSmallPlan* p, int nz, int nl, int nv, int sm_count,
 }
 
 int DenseSmallLaunch(const DenseSmallPlan& p, int batch, const double* H,
-                            const double* f, const double* G, const double* h,
-                            const double* A, const double* b, double* z, double* l,
-                            double* v, double* y, fbstab_out* out,
-                            const fbstab_options& opts, int comp,
+                     const double* f, const double* G, const double* h,
+                     const double* A, const double* b, double* z, double* l,
+                     double* v, double* y, fbstab_out* out,
+                     const fbstab_options& opts, int comp,
                      const fbstab_component_io* io, cudaStream_t stream) {
   small::Args a;
   a.comp = comp;
@@ -909,9 +964,12 @@ int DenseSmallLaunch(const DenseSmallPlan& p, int batch, const double* H,
   a.out = out;
   a.counter = p.counter;
   a.opts = opts;
-  const int warps = (batch + small::kWarpsPerCta - 1) / small::kWarpsPerCta;
-  const int grid = warps < p.grid ? warps : p.grid;
-  small::dense_small_kernel<<<grid, 32 * small::kWarpsPerCta, p.smem, stream>>>(a);
+  const int ctas = (batch + small::kWarps - 1) / small::kWarps;
+  const int grid = ctas < p.grid ? ctas : p.grid;
+  if (comp < 0)
+    small::dense_small_kernel<false><<<grid, 32 * small::kWarps, p.smem, stream>>>(a);
+  else
+    small::dense_small_kernel<true><<<grid, 32 * small::kWarps, p.smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

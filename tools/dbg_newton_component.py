@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0,'.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import fbstab_b200 as fb
 from oracle import binding as ob
 nz,nl,nv=32,8,64; B=8

@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import fbstab_b200 as fb, torch
 nz,nl,nv,B=32,8,64,int(sys.argv[1]) if len(sys.argv)>1 else 16384
 d = fb.problems.random_dense_qp(nz,nl,nv,count=B,config=2)

@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import fbstab_b200 as fb, torch
 nz,nl,nv,B=32,8,64,65536
 d = fb.problems.random_dense_qp(nz,nl,nv,count=B,config=2)
