@@ -33,6 +33,7 @@ SYMBOLS = [
     "fbstab_mpc_batch_path", "fbstab_mpc_batch_component",
     "fbstab_ocp_dims", "fbstab_ocp_generate", "fbstab_ocp_generate_batch",
     "fbstab_random_dense_qp", "fbstab_fp64_peak",
+    "fbstab_fp64_peak_concurrent",
 ]
 
 
@@ -167,3 +168,12 @@ def fp64_peak(device=0):
     a, b = C.c_double(), C.c_double()
     check(lib().fbstab_fp64_peak(device, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def fp64_peak_concurrent(device=0):
+    """Combined TFLOP/s with DFMA and DMMA warps running at the same time."""
+    a = C.c_double()
+    L = lib()
+    L.fbstab_fp64_peak_concurrent.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    check(L.fbstab_fp64_peak_concurrent(device, C.byref(a)))
+    return a.value

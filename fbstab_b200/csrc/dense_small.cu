@@ -241,26 +241,29 @@ struct Warp {
     return e;
   }
 
-  // Gauss-Jordan elimination of E with the [G' rhs] columns riding along,
-  // fully unrolled: every register index is static and step k touches exactly
-  // the 31-k trailing columns.  Lane k broadcasts its pivot row through one of
-  // two alternating shared buffers (cb[j] = E(k,j) for j > k, cb[32] = pivot,
-  // cb[34..42] = augmented columns), so one __syncwarp per step suffices.
-  __device__ __forceinline__ void eliminate() {
-#pragma unroll
-    for (int k = 0; k < NZ; k++) {
+  // One segment of the Gauss-Jordan elimination of E: steps k0..k1-1, during
+  // which at most W trailing columns are still non-zero.  Every step the row
+  // registers rotate left by one, so a[0] is always the entry in the pivot
+  // column and the loop body is the same for every k.  The loop is kept
+  // ROLLED on purpose: seven warps run different instances at different
+  // program counters, and a fully unrolled elimination (10.5k SASS
+  // instructions) measured 43% of all stall samples on instruction fetch
+  // (profiles/r1_dense_small_unrolled_elimination.txt).  Lane k broadcasts its
+  // (already rotated) pivot row through shared memory.
+  template <int W>
+  __device__ __forceinline__ void eliminate(int k0, int k1) {
+#pragma unroll 1
+    for (int k = k0; k < k1; k++) {
       const unsigned cb = sb + D(OFF_COL + COL_STRIDE * (k & 1));
-      const int j0 = k + 1;             // first trailing column
-      const int je = (j0 + 1) & ~1;     // first even trailing column
       if (lane == k) {
         // the pivot row itself (NOT the pivot column taken from the other
         // lanes: after the 1e8-scale cancellations of A' Gamma A the (k,j) and
         // (j,k) entries differ at the 1e-8 relative level, and mixing them
         // ruins the accuracy of dz along the active-constraint normals)
-        sts(cb + D(32), a[k]);
-        if ((j0 & 1) && j0 < NZ) sts(cb + D(j0), a[j0]);
+        sts(cb + D(32), a[0]);
 #pragma unroll
-        for (int j = je; j + 1 < NZ; j += 2) sts2(cb + D(j), a[j], a[j + 1]);
+        for (int m = 1; m + 1 <= W; m += 2) sts2(cb + D(m - 1), a[m], a[m + 1]);
+        if (W & 1) sts(cb + D(W - 1), a[W]);
 #pragma unroll
         for (int r = 0; r < NL + 1; r += 2)
           sts2(cb + D(34 + r), g[r], (r + 1 < NL + 1) ? g[r + 1] : 0.0);
@@ -270,14 +273,14 @@ struct Warp {
       if (!(fabs(d) > 0.0)) ok = false;
       const double rd = 1.0 / d;
       if (lane == k) dinv = rd;
-      const double lik = (lane != k) ? a[k] * rd : 0.0;
-      if ((j0 & 1) && j0 < NZ) a[j0] = fma(-lik, lds(cb + D(j0)), a[j0]);
+      const double lik = (lane != k) ? a[0] * rd : 0.0;
 #pragma unroll
-      for (int j = je; j + 1 < NZ; j += 2) {
-        const double2 c = lds2(cb + D(j));
-        a[j] = fma(-lik, c.x, a[j]);
-        a[j + 1] = fma(-lik, c.y, a[j + 1]);
+      for (int m = 1; m <= W; m += 2) {
+        const double2 c = lds2(cb + D(m - 1));
+        a[m - 1] = fma(-lik, c.x, a[m]);
+        if (m + 1 < NZ) a[m] = fma(-lik, c.y, a[m + 1]);
       }
+      if (W < NZ - 1) a[W] = 0.0; else a[NZ - 1] = 0.0;
 #pragma unroll
       for (int r = 0; r < NL + 1; r += 2) {
         const double2 xr = lds2(cb + D(34 + r));
@@ -372,7 +375,10 @@ struct Warp {
     // Gauss-Jordan elimination of the E block; the
     // pivot-row buffers alias the transposition scratch read just above
     __syncwarp();
-    eliminate();
+    eliminate<31>(0, 8);
+    eliminate<23>(8, 16);
+    eliminate<15>(16, 24);
+    eliminate<7>(24, 32);
     // lane i now holds d_i * (E^-1 [G' a])(i,:) in g[0..8] and dinv = 1/d_i
 
     // Schur complement S = -sigma I - G Y, rhs c - G t  with [Y t] = E^-1 [G' a]

@@ -53,7 +53,77 @@ __global__ void __launch_bounds__(256) dmma_kernel(double* out, int iters, doubl
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Even warps run the DFMA loop, odd warps the DMMA loop: shows whether the
+// FP64 vector pipe and the FP64 tensor path overlap or share one datapath.
+__global__ void __launch_bounds__(256) mixed_kernel(double* out, int iters_fma, int iters_mma,
+                                                    double a, double b) {
+  double s = 0;
+  if ((threadIdx.x >> 5) & 1) {
+    double c[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k][0] = c[k][1] = threadIdx.x + k;
+    for (int i = 0; i < iters_mma; i++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) dmma884(c[k][0], c[k][1], a, b);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += c[k][0] + c[k][1];
+  } else {
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = threadIdx.x + k;
+    for (int i = 0; i < iters_fma; i++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = fma(x[k], a, b);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += x[k];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
+
+extern "C" int fbstab_fp64_peak_concurrent(int device, double* total_tflops) {
+  if (cudaSetDevice(device) != cudaSuccess) return FBSTAB_ERR_NOGPU;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FBSTAB_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  double* out = nullptr;
+  if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess)
+    return FBSTAB_ERR_ALLOC;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  // per-warp work sized so that both halves take about equally long when the
+  // two paths run at their stand-alone peaks (64*64 DFMA flops vs 32*512 DMMA
+  // flops per outer iteration at ~equal TFLOP/s)
+  const int iters_fma = 4096, iters_mma = 1024;
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0);
+    mixed_kernel<<<blocks, threads>>>(out, iters_fma, iters_mma, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double warps = (double)blocks * (threads / 32) / 2.0;
+  const double flops = 2.0 * 64.0 * iters_fma * warps * 32.0 +
+                       2.0 * 256.0 * 32.0 * iters_mma * warps;
+  *total_tflops = flops / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return cudaGetLastError() == cudaSuccess ? FBSTAB_OK : FBSTAB_ERR_CUDA;
+}
 
 extern "C" int fbstab_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops) {
   if (cudaSetDevice(device) != cudaSuccess) return FBSTAB_ERR_NOGPU;

@@ -123,6 +123,9 @@ int fbstab_device_count(void);
  * and an FP64 mma.sync (DMMA) loop over all SMs (roofline denominators; the
  * driver's MEASURED_PEAKS.json has no FP64 figure). */
 int fbstab_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
+/* Combined TFLOP/s when half the warps of every SM run the DFMA loop and the
+ * other half the DMMA loop at the same time (do the two FP64 paths overlap?). */
+int fbstab_fp64_peak_concurrent(int device, double* total_tflops);
 
 /* ---- dense QPs ----------------------------------------------------------- */
 typedef struct fbstab_dense_batch fbstab_dense_batch;
