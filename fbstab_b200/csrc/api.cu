@@ -19,10 +19,14 @@
 #include "dense_problem.cuh"
 #include "dense_small.h"
 #include "engine.cuh"
+#include "engine_args.cuh"
 #include "fbstab_b200.h"
-#include "mpc_problem.cuh"
+#include "mpc_riccati.h"
 
 namespace {
+
+using fbs::CommonArgs;
+using fbs::RunComponent;
 
 thread_local std::string g_last_error;
 
@@ -142,30 +146,9 @@ bool Sat(double* x, double a, double b) {
   return true;
 }
 
-// ---- kernel argument blocks ------------------------------------------------
-struct CommonArgs {
-  int batch;
-  double *z, *l, *v, *y;
-  fbstab_out* out;
-  double* ws;        // per-CTA workspace base
-  size_t ws_stride;  // doubles per CTA
-  int* counter;
-  int vec_in_smem;
-  fbstab_options opts;
-  // component mode
-  int comp;
-  fbstab_component_io io;
-};
-
 struct DenseArgs {
   int nz, nl, nv;
   const double *H, *f, *G, *h, *A, *b;
-  CommonArgs c;
-};
-
-struct MpcArgs {
-  int N, nx, nu, nc;
-  const double *Q, *R, *S, *q, *r, *A, *B, *cc, *E, *L, *d, *x0;
   CommonArgs c;
 };
 
@@ -218,149 +201,6 @@ size_t DenseWsDoubles(int nz, int nl, int nv) {
   return n * n + 2 * n + 3 * (size_t)nv + nz;
 }
 
-__device__ inline void SetupMpc(const MpcArgs& a, int inst, double*& ws,
-                                fbs::MpcProblem* p) {
-  const int N = a.N, nx = a.nx, nu = a.nu, nc = a.nc;
-  const size_t K = N + 1;
-  p->N = N;
-  p->nx = nx;
-  p->nu = nu;
-  p->nc = nc;
-  p->nz = (int)(K * (nx + nu));
-  p->nl = (int)(K * nx);
-  p->nv = (int)(K * nc);
-  p->Q = a.Q + inst * K * nx * nx;
-  p->R = a.R + inst * K * nu * nu;
-  p->S = a.S + inst * K * nu * nx;
-  p->q = a.q + inst * K * nx;
-  p->r = a.r + inst * K * nu;
-  p->A = a.A + (size_t)inst * N * nx * nx;
-  p->B = a.B + (size_t)inst * N * nx * nu;
-  p->c = a.cc + (size_t)inst * N * nx;
-  p->E = a.E + inst * K * nc * nx;
-  p->L = a.L + inst * K * nc * nu;
-  p->d = a.d + inst * K * nc;
-  p->x0 = a.x0 + (size_t)inst * nx;
-  p->gamma = Carve(ws, p->nv);
-  p->mus = Carve(ws, p->nv);
-  p->Gam = Carve(ws, p->nv);
-  p->tv = Carve(ws, p->nv);
-  p->Ls = Carve(ws, K * nx * nx);
-  p->Ms = Carve(ws, K * nx * nx);
-  p->AMs = Carve(ws, K * nx * nx);
-  p->SMs = Carve(ws, K * nu * nx);
-  p->SGs = Carve(ws, K * nu * nu);
-  p->Ps = Carve(ws, K * nu * nx);
-  p->Qt = Carve(ws, nx * nx);
-  p->Rt = Carve(ws, nu * nu);
-  p->St = Carve(ws, nu * nx);
-  p->Linv = Carve(ws, nx * nx);
-  p->r1 = Carve(ws, p->nz);
-  p->r2 = Carve(ws, p->nl);
-  p->hs = Carve(ws, p->nl);
-  p->ths = Carve(ws, p->nl);
-  p->txs = Carve(ws, p->nl);
-  p->tus = Carve(ws, K * nu);
-  const int m = nx > nu ? nx : nu;
-  p->sa = Carve(ws, m);
-  p->sb = Carve(ws, m);
-  p->sc = Carve(ws, m);
-  p->tzs = Carve(ws, p->nz);
-}
-size_t MpcWsDoubles(int N, int nx, int nu, int nc) {
-  const size_t K = N + 1;
-  const size_t nz = K * (nx + nu), nl = K * nx, nv = K * nc;
-  const size_t m = nx > nu ? nx : nu;
-  return 4 * nv + 3 * K * nx * nx + 2 * K * nu * nx + K * nu * nu +
-         2 * (size_t)nx * nx + (size_t)nu * nu + (size_t)nu * nx + 2 * nz +
-         4 * nl + K * nu + 3 * m;
-}
-
-// One component stage on caller-supplied iterates (per-kernel parity tests).
-template <class P>
-__device__ void RunComponent(const fbs::Team& t, P& p, const CommonArgs& c,
-                             int inst, fbs::Buffers& w) {
-  const fbstab_component_io& io = c.io;
-  const size_t oz = (size_t)inst * p.nz, ol = (size_t)inst * p.nl,
-               ov = (size_t)inst * p.nv;
-  const double alpha = c.opts.alpha;
-  if (c.comp == FBSTAB_COMP_MARGIN) {
-    p.margin(t, io.z + oz, io.dy + ov);
-    return;
-  }
-  // load x (and xbar) into the work buffers
-  for (int i = t.rank(); i < p.nz; i += t.size()) {
-    w.xi.z[i] = io.z[oz + i];
-    w.xk.z[i] = io.zbar ? io.zbar[oz + i] : io.z[oz + i];
-  }
-  for (int i = t.rank(); i < p.nl; i += t.size()) {
-    w.xi.l[i] = io.l[ol + i];
-    w.xk.l[i] = io.lbar ? io.lbar[ol + i] : io.l[ol + i];
-  }
-  for (int i = t.rank(); i < p.nv; i += t.size()) {
-    w.xi.v[i] = io.v[ov + i];
-    w.xk.v[i] = io.vbar ? io.vbar[ov + i] : io.v[ov + i];
-    w.xi.y[i] = io.y ? io.y[ov + i] : 0.0;
-  }
-  t.sync();
-  if (c.comp == FBSTAB_COMP_RESIDUAL) {
-    fbs::EvalOut e = fbs::evaluate(t, p, w.xi, w.xk, io.sigma, alpha, w.ri);
-    (void)e;
-    double s[6] = {0, 0, 0, 0, 0, 0};
-    // recompute component norms for reporting (evaluate() returns the totals)
-    for (int i = t.rank(); i < p.nz; i += t.size()) {
-      const double r = w.ri.z[i];
-      io.rz[oz + i] = r;
-      s[0] += r * r;
-      const double n = r - io.sigma * (w.xi.z[i] - w.xk.z[i]);
-      s[3] += n * n;
-    }
-    for (int i = t.rank(); i < p.nl; i += t.size()) {
-      const double r = w.ri.l[i];
-      io.rl[ol + i] = r;
-      s[1] += r * r;
-      const double n = r - io.sigma * (w.xi.l[i] - w.xk.l[i]);
-      s[4] += n * n;
-    }
-    for (int i = t.rank(); i < p.nv; i += t.size()) {
-      const double r = w.ri.v[i];
-      io.rv[ov + i] = r;
-      s[2] += r * r;
-      const double n = fbs::pnr(w.xi.y[i], w.xi.v[i], alpha);
-      s[5] += n * n;
-    }
-    fbs::team_sum(t, s);
-    if (t.rank() == 0 && io.norms) {
-      for (int k = 0; k < 6; k++) io.norms[(size_t)inst * 8 + k] = sqrt(s[k]);
-      io.norms[(size_t)inst * 8 + 6] = e.Ei;
-      io.norms[(size_t)inst * 8 + 7] = e.Eo;
-    }
-  } else if (c.comp == FBSTAB_COMP_NEWTON) {
-    const bool ok = p.factor(t, w.xi, w.xk, io.sigma, alpha);
-    // engine convention: solve() receives the residual and solves for -r; the
-    // component API takes the right-hand side r itself, so negate on load.
-    for (int i = t.rank(); i < p.nz; i += t.size()) w.ri.z[i] = -io.rz[oz + i];
-    for (int i = t.rank(); i < p.nl; i += t.size()) w.ri.l[i] = -io.rl[ol + i];
-    for (int i = t.rank(); i < p.nv; i += t.size()) w.ri.v[i] = -io.rv[ov + i];
-    t.sync();
-    p.solve(t, w.ri.z, w.ri.l, w.ri.v, w.dx);
-    for (int i = t.rank(); i < p.nz; i += t.size()) io.dz[oz + i] = w.dx.z[i];
-    for (int i = t.rank(); i < p.nl; i += t.size()) io.dl[ol + i] = w.dx.l[i];
-    for (int i = t.rank(); i < p.nv; i += t.size()) {
-      io.dv[ov + i] = w.dx.v[i];
-      io.dy[ov + i] = w.dx.y[i];
-      if (io.gamma) io.gamma[ov + i] = p.gamma[i];
-      if (io.mus) io.mus[ov + i] = p.mus[i];
-    }
-    if (t.rank() == 0 && io.status)
-      io.status[inst] = ok ? FBSTAB_STATUS_OK : FBSTAB_STATUS_FACTOR_FAILED;
-  } else if (c.comp == FBSTAB_COMP_FEAS) {
-    const int feas = p.feasibility(t, w.xi, io.tol);
-    if (t.rank() == 0 && io.status) io.status[inst] = feas;
-  }
-  t.sync();
-}
-
 template <class Args, class P, void (*Setup)(const Args&, int, double*&, P*)>
 __device__ void PersistentLoop(const Args& a, int nz, int nl, int nv) {
   extern __shared__ double dyn_smem[];
@@ -397,13 +237,6 @@ dense_generic_kernel(const __grid_constant__ DenseArgs a) {
   PersistentLoop<DenseArgs, fbs::DenseProblem, SetupDense>(a, a.nz, a.nl, a.nv);
 }
 
-__global__ void __launch_bounds__(64, 12)
-mpc_generic_kernel(const __grid_constant__ MpcArgs a) {
-  const int K = a.N + 1;
-  PersistentLoop<MpcArgs, fbs::MpcProblem, SetupMpc>(a, K * (a.nx + a.nu),
-                                                     K * a.nx, K * a.nc);
-}
-
 // ---- handles ----------------------------------------------------------------
 struct HandleBase {
   int device = 0;
@@ -436,8 +269,7 @@ struct HandleBase {
   }
 };
 
-int InitCommon(HandleBase* h, int device, int max_batch, const void* kernel,
-               size_t ws_doubles_no_vec, int block) {
+int InitDevice(HandleBase* h, int device, int max_batch) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -454,6 +286,14 @@ int InitCommon(HandleBase* h, int device, int max_batch, const void* kernel,
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaMalloc(&h->counter, sizeof(int)));
+  return FBSTAB_OK;
+}
+
+int InitCommon(HandleBase* h, int device, int max_batch, const void* kernel,
+               size_t ws_doubles_no_vec, int block) {
+  int rc = InitDevice(h, device, max_batch);
+  if (rc) return rc;
   h->block = EnvInt("FBSTAB_BLOCK", block);
   const size_t vec_bytes = VecDoubles(h->nz, h->nl, h->nv) * sizeof(double);
   const size_t smem_max = (size_t)EnvInt("FBSTAB_VEC_SMEM_MAX", 12 * 1024);
@@ -479,7 +319,6 @@ int InitCommon(HandleBase* h, int device, int max_batch, const void* kernel,
     cudaGetLastError();
     return Fail(FBSTAB_ERR_ALLOC, "cudaMalloc of the solver workspace failed");
   }
-  CUDA_TRY(cudaMalloc(&h->counter, sizeof(int)));
   return FBSTAB_OK;
 }
 
@@ -499,6 +338,7 @@ struct fbstab_dense_batch : HandleBase {
 };
 struct fbstab_mpc_batch : HandleBase {
   int N = 0, nx = 0, nu = 0, nc = 0;
+  fbs::MpcPlan plan;
 };
 
 namespace {
@@ -818,23 +658,29 @@ int fbstab_mpc_batch_create(int N, int nx, int nu, int nc, int max_batch,
   h->nz = (N + 1) * (nx + nu);
   h->nl = (N + 1) * nx;
   h->nv = (N + 1) * nc;
-  const int block = (nx + nu) <= 12 ? 32 : 64;
-  int rc = InitCommon(h, device, max_batch, (const void*)mpc_generic_kernel,
-                      MpcWsDoubles(N, nx, nu, nc), block);
+  int rc = InitDevice(h, device, max_batch);
+  if (rc == FBSTAB_OK) {
+    const char* err = "";
+    rc = fbs::MpcPlanInit(&h->plan, N, nx, nu, nc, max_batch, h->sm_count, &err);
+    if (rc) Fail(rc, err);
+  }
   if (rc) {
     std::string keep = g_last_error;
+    fbs::MpcPlanFree(&h->plan);
     h->FreeAll();
     delete h;
     g_last_error = keep;
     return rc;
   }
-  h->path = "mpc-riccati-team";
+  h->path = h->plan.name;
   *handle = h;
   return FBSTAB_OK;
 }
 
 int fbstab_mpc_batch_destroy(fbstab_mpc_batch* h) {
   if (!h) return FBSTAB_OK;
+  cudaSetDevice(h->device);
+  fbs::MpcPlanFree(&h->plan);
   h->FreeAll();
   delete h;
   return FBSTAB_OK;
@@ -855,18 +701,14 @@ const char* fbstab_mpc_batch_path(const fbstab_mpc_batch* h) {
 }
 
 static int MpcStageData(fbstab_mpc_batch* h, Stager* st, int batch,
-                        const double* const* user, MpcArgs* a) {
+                        const double* const* user, fbs::MpcData* a) {
   const size_t N = h->N, nx = h->nx, nu = h->nu, nc = h->nc, K = N + 1,
                B = batch, D = sizeof(double);
   const size_t sizes[12] = {K * nx * nx, K * nu * nu, K * nu * nx, K * nx,
                             K * nu,      N * nx * nx, N * nx * nu, N * nx,
                             K * nc * nx, K * nc * nu, K * nc,      nx};
   const double** dst[12] = {&a->Q, &a->R, &a->S, &a->q, &a->r, &a->A,
-                            &a->B, &a->cc, &a->E, &a->L, &a->d, &a->x0};
-  a->N = h->N;
-  a->nx = h->nx;
-  a->nu = h->nu;
-  a->nc = h->nc;
+                            &a->B, &a->c, &a->E, &a->L, &a->d, &a->x0};
   for (int k = 0; k < 12; k++) {
     int rc = st->In(&h->in[k], user[k], B * sizes[k] * D, (const void**)dst[k]);
     if (rc) return rc;
@@ -891,22 +733,23 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
   const auto t0 = std::chrono::steady_clock::now();
   Stager st;
   st.stream = (cudaStream_t)stream;
-  MpcArgs a;
+  fbs::MpcData a;
   const double* user[12] = {Q, R, S, q, r, A, B, c, E, L, d, x0};
   int rc = MpcStageData(h, &st, batch, user, &a);
   if (rc) return rc;
   const size_t nz = h->nz, nl = h->nl, nv = h->nv, Bn = batch, D = sizeof(double);
-  FillCommon(h, &a.c, batch);
-  if ((rc = st.InOut(&h->io[0], z, Bn * nz * D, true, (void**)&a.c.z))) return rc;
-  if ((rc = st.InOut(&h->io[1], l, Bn * nl * D, true, (void**)&a.c.l))) return rc;
-  if ((rc = st.InOut(&h->io[2], v, Bn * nv * D, true, (void**)&a.c.v))) return rc;
-  if ((rc = st.InOut(&h->io[3], y, Bn * nv * D, false, (void**)&a.c.y))) return rc;
-  if ((rc = st.InOut(&h->out_buf, out, Bn * sizeof(fbstab_out), false,
-                     (void**)&a.c.out)))
+  double *dz, *dl, *dv, *dy;
+  fbstab_out* dout;
+  if ((rc = st.InOut(&h->io[0], z, Bn * nz * D, true, (void**)&dz))) return rc;
+  if ((rc = st.InOut(&h->io[1], l, Bn * nl * D, true, (void**)&dl))) return rc;
+  if ((rc = st.InOut(&h->io[2], v, Bn * nv * D, true, (void**)&dv))) return rc;
+  if ((rc = st.InOut(&h->io[3], y, Bn * nv * D, false, (void**)&dy))) return rc;
+  if ((rc = st.InOut(&h->out_buf, out, Bn * sizeof(fbstab_out), false, (void**)&dout)))
     return rc;
   CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
-  const int grid = std::min(batch, h->grid_max);
-  mpc_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+  if (fbs::MpcLaunch(h->plan, batch, a, dz, dl, dv, dy, dout, h->opts, -1, nullptr,
+                     h->counter, st.stream))
+    return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
   CUDA_TRY(cudaGetLastError());
   h->last_launches = 1;
   if ((rc = st.Finish())) return rc;
@@ -935,16 +778,16 @@ int fbstab_mpc_batch_component(fbstab_mpc_batch* h, int comp, int batch,
   CUDA_TRY(cudaSetDevice(h->device));
   Stager st;
   st.stream = (cudaStream_t)stream;
-  MpcArgs a;
+  fbs::MpcData a;
   const double* user[12] = {Q, R, S, q, r, A, B, c, E, L, d, x0};
   int rc = MpcStageData(h, &st, batch, user, &a);
   if (rc) return rc;
-  FillCommon(h, &a.c, batch);
-  a.c.comp = comp;
-  if ((rc = StageComponentIo(h, &st, batch, io, &a.c.io))) return rc;
+  fbstab_component_io dio;
+  if ((rc = StageComponentIo(h, &st, batch, io, &dio))) return rc;
   CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
-  const int grid = std::min(batch, h->grid_max);
-  mpc_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+  if (fbs::MpcLaunch(h->plan, batch, a, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     h->opts, comp, &dio, h->counter, st.stream))
+    return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
   CUDA_TRY(cudaGetLastError());
   h->last_launches = 1;
   return st.Finish();

@@ -63,10 +63,14 @@ def run(name, scale, reps=3):
 
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:]]
-    scale = 1.0
+    scale, reps = 1.0, 3
     if "--scale" in args:
         i = args.index("--scale")
         scale = float(args[i + 1])
         del args[i:i + 2]
+    if "--reps" in args:
+        i = args.index("--reps")
+        reps = int(args[i + 1])
+        del args[i:i + 2]
     for n in (args or list(CONFIGS)):
-        run(n, scale)
+        run(n, scale, reps)
