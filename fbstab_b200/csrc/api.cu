@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "dense_large.cuh"
 #include "dense_problem.cuh"
 #include "dense_small.h"
 #include "engine.cuh"
@@ -237,6 +238,19 @@ dense_generic_kernel(const __grid_constant__ DenseArgs a) {
   PersistentLoop<DenseArgs, fbs::DenseProblem, SetupDense>(a, a.nz, a.nl, a.nv);
 }
 
+// Large dense QPs (BASELINE config 5): 512 threads per instance, DMMA SYRK and
+// blocked Cholesky (dense_large.cuh); the dynamic shared memory is its scratch.
+__device__ inline void SetupDenseLarge(const DenseArgs& a, int inst, double*& ws,
+                                       fbs::DenseLargeProblem* p) {
+  extern __shared__ double dyn_smem[];
+  SetupDense(a, inst, ws, p);
+  p->sm = dyn_smem;
+}
+__global__ void __launch_bounds__(fbs::dl::kThreads, 1)
+dense_large_kernel(const __grid_constant__ DenseArgs a) {
+  PersistentLoop<DenseArgs, fbs::DenseLargeProblem, SetupDenseLarge>(a, a.nz, a.nl, a.nv);
+}
+
 // ---- handles ----------------------------------------------------------------
 struct HandleBase {
   int device = 0;
@@ -290,15 +304,17 @@ int InitDevice(HandleBase* h, int device, int max_batch) {
   return FBSTAB_OK;
 }
 
+// scratch_smem > 0: the kernel uses the dynamic shared memory as scratch and
+// keeps the iterate vectors in the global workspace.
 int InitCommon(HandleBase* h, int device, int max_batch, const void* kernel,
-               size_t ws_doubles_no_vec, int block) {
+               size_t ws_doubles_no_vec, int block, size_t scratch_smem = 0) {
   int rc = InitDevice(h, device, max_batch);
   if (rc) return rc;
-  h->block = EnvInt("FBSTAB_BLOCK", block);
+  h->block = scratch_smem ? block : EnvInt("FBSTAB_BLOCK", block);
   const size_t vec_bytes = VecDoubles(h->nz, h->nl, h->nv) * sizeof(double);
   const size_t smem_max = (size_t)EnvInt("FBSTAB_VEC_SMEM_MAX", 12 * 1024);
-  h->vec_in_smem = vec_bytes <= smem_max ? 1 : 0;
-  h->dyn_smem = h->vec_in_smem ? vec_bytes : 0;
+  h->vec_in_smem = (!scratch_smem && vec_bytes <= smem_max) ? 1 : 0;
+  h->dyn_smem = h->vec_in_smem ? vec_bytes : scratch_smem;
   if (h->dyn_smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)h->dyn_smem));
@@ -335,6 +351,7 @@ int SetOptions(HandleBase* h, const fbstab_options* o) {
 
 struct fbstab_dense_batch : HandleBase {
   fbs::DenseSmallPlan small;
+  bool large = false;
 };
 struct fbstab_mpc_batch : HandleBase {
   int N = 0, nx = 0, nu = 0, nc = 0;
@@ -502,8 +519,13 @@ int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
   h->nv = nv;
   const int n = nz + nl;
   const int block = n <= 8 ? 32 : n <= 48 ? 64 : n <= 128 ? 128 : 256;
-  int rc = InitCommon(h, device, max_batch, (const void*)dense_generic_kernel,
-                      DenseWsDoubles(nz, nl, nv), block);
+  h->large = nz >= EnvInt("FBSTAB_DENSE_LARGE_MIN", 128) && !EnvInt("FBSTAB_FORCE_GENERIC", 0);
+  int rc = h->large
+               ? InitCommon(h, device, max_batch, (const void*)dense_large_kernel,
+                            DenseWsDoubles(nz, nl, nv), fbs::dl::kThreads,
+                            sizeof(double) * fbs::dl::kSmemDoubles)
+               : InitCommon(h, device, max_batch, (const void*)dense_generic_kernel,
+                            DenseWsDoubles(nz, nl, nv), block);
   if (rc == FBSTAB_OK && !EnvInt("FBSTAB_FORCE_GENERIC", 0))
     rc = fbs::DenseSmallInit(&h->small, nz, nl, nv, h->sm_count, h->counter);
   if (rc) {
@@ -514,6 +536,8 @@ int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
     return rc;
   }
   if (h->small.enabled) h->path = h->small.name;
+  if (h->large)
+    h->path = "dense-large-cta (512 thr/instance, DMMA A'GammaA + blocked Cholesky NB=64)";
   *handle = h;
   return FBSTAB_OK;
 }
@@ -593,7 +617,10 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
     if (rc) return Fail(FBSTAB_ERR_CUDA, "dense small-path launch failed");
   } else {
     const int grid = std::min(batch, h->grid_max);
-    dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+    if (h->large)
+      dense_large_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+    else
+      dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
   }
   CUDA_TRY(cudaGetLastError());
   h->last_launches = 1;
@@ -634,7 +661,10 @@ int fbstab_dense_batch_component(fbstab_dense_batch* h, int comp, int batch,
     if (rc) return Fail(FBSTAB_ERR_CUDA, "dense small-path launch failed");
   } else {
     const int grid = std::min(batch, h->grid_max);
-    dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+    if (h->large)
+      dense_large_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+    else
+      dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
   }
   CUDA_TRY(cudaGetLastError());
   h->last_launches = 1;

@@ -1,0 +1,409 @@
+// dense_large.cuh -- Problem policy for LARGE dense QPs (BASELINE config 5:
+// nz=512, nl=128, nv=1024): one 512-thread CTA per instance, the KKT reduction
+// and its factorisation on the FP64 tensor cores.
+//
+// Follows DenseCholeskySolver (reference dense_cholesky_solver.cc:32-127).
+// The reference factors K = [E G'; G -sigma I], E = H + sigma I + A' Gamma A,
+// with Eigen's diagonally pivoted LDL'; that pivot rule eliminates the E block
+// first (see dense_problem.cuh), so the same elimination is done here as
+//     E = L L'            blocked right-looking Cholesky (NB = 64)
+//     W' = G L^-T         falls out of the panel solves (the G rows are simply
+//                         further rows of every panel)
+//     S = sigma I + W'W   accumulated by the same trailing updates with the
+//                         sign flipped, then S = Ls Ls'
+// which is the oracle's `variant 2`.  What is a genuine dense contraction runs
+// as FP64 DMMA (mma.sync.m8n8k4.f64):
+//   * A' Gamma A : 128x128 tiles of E, K = nv deep (75% of the flops);
+//   * every trailing update of the blocked Cholesky (K = 64 deep).
+// Operand chunks (128 x 16) are staged global -> registers -> shared with the
+// next chunk's loads in flight during the current chunk's DMMAs.  Diagonal
+// blocks and panel solves work in shared memory; the triangular solves of
+// ::Solve are blocked the same way (one warp solves a diagonal block with
+// shuffles, all warps apply the block column).
+#pragma once
+
+#include "dense_problem.cuh"
+
+namespace fbs {
+namespace dl {
+
+constexpr int kThreads = 512;
+constexpr int TB = 128;  // tile edge of the DMMA products
+constexpr int KC = 16;   // depth of one staged chunk
+constexpr int KP = 20;   // padded depth stride in shared memory (conflict-free fragments)
+constexpr int NB = 64;   // Cholesky block
+constexpr int DP = NB + 1;
+constexpr int TR = 256;  // rows of one panel-solve tile
+// shared-memory carve (doubles)
+constexpr int kStage = 2 * (2 * TB * KP + KC);  // two buffers x (two operand chunks + Gamma)
+constexpr int kDiag = NB * DP + NB;             // diagonal block + its pivots
+constexpr int kPanel = TR * NB;
+constexpr int kSmemDoubles = (kDiag + kPanel) > kStage ? (kDiag + kPanel) : kStage;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// acc(128x128, this warp's 32x32 part) = sum_k opI(i,k) * [scale(k)] * opJ(j,k).
+// LoadI / LoadJ: (idx in [0,128), k in [0,depth)) -> element, 0 outside the
+// matrix.  The 16 warps form a 4x4 grid; warp (wm,wn) owns rows 32wm.., cols
+// 32wn.. as 4x4 m8n8 DMMA tiles.  `same`: opJ == opI (diagonal tile).
+template <bool SCALED, class LoadI, class LoadJ>
+__device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], double* sm, int depth,
+                                         LoadI li, LoadJ lj, const double* scale, bool same) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r8 = lane >> 2, c4 = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int sidx = 8 * warp + r8;  // staging: this thread's tile row/col index
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int nchunk = (depth + KC - 1) / KC;
+  double ri[4], rj[4], rs = 0.0;
+  auto fetch = [&](int ch) {
+    const int k0 = ch * KC;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int k = k0 + 4 * q + c4;
+      ri[q] = (k < depth) ? li(sidx, k) : 0.0;
+      if (!same) rj[q] = (k < depth) ? lj(sidx, k) : 0.0;
+    }
+    if (SCALED && tid < KC) rs = (k0 + tid < depth) ? scale[k0 + tid] : 0.0;
+  };
+  auto stash = [&](int buf) {
+    double* SI = sm + buf * (2 * TB * KP + KC);
+    double* SJ = SI + TB * KP;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      SI[sidx * KP + 4 * q + c4] = ri[q];
+      if (!same) SJ[sidx * KP + 4 * q + c4] = rj[q];
+    }
+    if (SCALED && tid < KC) SI[2 * TB * KP + tid] = rs;
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int ch = 0; ch < nchunk; ch++) {
+    if (ch + 1 < nchunk) fetch(ch + 1);  // global loads in flight during the DMMAs
+    const double* SI = sm + (ch & 1) * (2 * TB * KP + KC);
+    const double* SJ = same ? SI : SI + TB * KP;
+    const double* SG = SI + 2 * TB * KP;
+#pragma unroll
+    for (int kk = 0; kk < KC / 4; kk++) {
+      double af[4], bf[4];
+      const double g = SCALED ? SG[4 * kk + c4] : 1.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) af[a] = SI[(32 * wm + 8 * a + r8) * KP + 4 * kk + c4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const double v = SJ[(32 * wn + 8 * b + r8) * KP + 4 * kk + c4];
+        bf[b] = SCALED ? g * v : v;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    if (ch + 1 < nchunk) stash((ch + 1) & 1);
+    __syncthreads();
+  }
+}
+
+// Visits this thread's accumulator entries: f(tile_row, tile_col, value).
+template <class F>
+__device__ __forceinline__ void for_each_acc(const double (&acc)[4][4][2], F f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r8 = lane >> 2, c4 = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int r = 32 * wm + 8 * a + r8, c = 32 * wn + 8 * b + 2 * c4;
+      f(r, c, acc[a][b][0]);
+      f(r, c + 1, acc[a][b][1]);
+    }
+}
+
+}  // namespace dl
+
+struct DenseLargeProblem : DenseProblem {
+  double* sm;  // dl::kSmemDoubles of dynamic shared memory
+
+  // In-place lower Cholesky of the bs x bs diagonal block at (c0,c0) of K,
+  // right-looking in shared memory; the factor is left in D (stride DP) and
+  // written back.  false on a pivot <= 0 (Eigen LLT's failure rule).
+  __device__ __noinline__ bool factor_diag(int c0, int bs, double* D, double* dg) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < bs * bs; e += dl::kThreads) {
+      const int i = e % bs, j = e / bs;
+      D[i + j * dl::DP] = (i >= j) ? K[(c0 + i) + (size_t)(c0 + j) * n] : 0.0;
+    }
+    __syncthreads();
+    bool ok = true;
+    for (int j = 0; j < bs; j++) {
+      const double d = D[j + j * dl::DP];
+      if (!(d > 0.0)) ok = false;
+      const double sd = sqrt(d);
+      if (tid == 0) dg[j] = sd;
+      for (int i = j + 1 + tid; i < bs; i += dl::kThreads) D[i + j * dl::DP] /= sd;
+      __syncthreads();
+      const int m = bs - 1 - j;  // trailing (i,k), j < k <= i < bs
+      for (int e = tid; e < m * m; e += dl::kThreads) {
+        const int i = j + 1 + e % m, k = j + 1 + e / m;
+        if (i >= k) D[i + k * dl::DP] = fma(-D[i + j * dl::DP], D[k + j * dl::DP], D[i + k * dl::DP]);
+      }
+      __syncthreads();
+    }
+    for (int j = tid; j < bs; j += dl::kThreads) D[j + j * dl::DP] = dg[j];
+    __syncthreads();
+    for (int e = tid; e < bs * bs; e += dl::kThreads) {
+      const int i = e % bs, j = e / bs;
+      if (i >= j) K[(c0 + i) + (size_t)(c0 + j) * n] = D[i + j * dl::DP];
+    }
+    return ok;
+  }
+
+  // Rows [r0, n) of block column c0: X = B Lkk^-T, right-looking on a
+  // shared-memory tile of TR rows.
+  __device__ __noinline__ void panel_solve(int c0, int bs, const double* D, double* Tm) {
+    const int tid = threadIdx.x;
+    for (int r0 = c0 + bs; r0 < n; r0 += dl::TR) {
+      const int rows = min(dl::TR, n - r0);
+      for (int e = tid; e < rows * bs; e += dl::kThreads) {
+        const int r = e % rows, k = e / rows;
+        Tm[r + k * dl::TR] = K[(r0 + r) + (size_t)(c0 + k) * n];
+      }
+      __syncthreads();
+      for (int j = 0; j < bs; j++) {
+        const double dj = D[j + j * dl::DP];
+        for (int r = tid; r < rows; r += dl::kThreads) Tm[r + j * dl::TR] /= dj;
+        __syncthreads();
+        const int m = bs - 1 - j;
+        for (int e = tid; e < rows * m; e += dl::kThreads) {
+          const int r = e % rows, k = j + 1 + e / rows;
+          Tm[r + k * dl::TR] = fma(-Tm[r + j * dl::TR], D[k + j * dl::DP], Tm[r + k * dl::TR]);
+        }
+        __syncthreads();
+      }
+      for (int e = tid; e < rows * bs; e += dl::kThreads) {
+        const int r = e % rows, k = e / rows;
+        K[(r0 + r) + (size_t)(c0 + k) * n] = Tm[r + k * dl::TR];
+      }
+      __syncthreads();
+    }
+  }
+
+  // LinearSolver::Initialize, dense_cholesky_solver.cc:32-79
+  __device__ __noinline__ bool factor(const Team& t, const Vars& x, const Vars& xbar,
+                         double sigma, double alpha) {
+    const int tid = threadIdx.x;
+    double* Gam = r2;
+    for (int i = tid; i < nv; i += dl::kThreads) {
+      const double ys = x.y[i] + sigma * (x.v[i] - xbar.v[i]);
+      double ga, mu;
+      pfb_barrier(ys, x.v[i], alpha, sigma, &ga, &mu);
+      gamma[i] = ga;
+      mus[i] = mu;
+      Gam[i] = ga / mu;
+    }
+    __syncthreads();
+    // E = (H + sigma I) + A' (Gamma A), lower tiles -> K(0:nz, 0:nz)   (:52,62-63)
+    {
+      const double* Ap = A;
+      const int nvv = nv, nzz = nz;
+      for (int I = 0; I * dl::TB < nz; I++)
+        for (int J = 0; J <= I; J++) {
+          double acc[4][4][2];
+          auto li = [=](int idx, int k) {
+            const int c = I * dl::TB + idx;
+            return c < nzz ? Ap[k + (size_t)c * nvv] : 0.0;
+          };
+          auto lj = [=](int idx, int k) {
+            const int c = J * dl::TB + idx;
+            return c < nzz ? Ap[k + (size_t)c * nvv] : 0.0;
+          };
+          dl::mma_tile<true>(acc, sm, nv, li, lj, Gam, I == J);
+          dl::for_each_acc(acc, [&](int r, int c, double v) {
+            const int gr = I * dl::TB + r, gc = J * dl::TB + c;
+            if (gr < nz && gc <= gr)
+              K[gr + (size_t)gc * n] = (H[gr + (size_t)gc * nz] + (gr == gc ? sigma : 0.0)) + v;
+          });
+        }
+    }
+    // rows of G below E, and S initialised to sigma I   (:67-69 with the sign of
+    // the Schur complement folded into the updates)
+    for (int e = tid; e < nl * n; e += dl::kThreads) {
+      const int r = e % nl, c = e / nl;
+      K[nz + r + (size_t)c * n] = (c < nz) ? G[r + (size_t)c * nl] : ((c - nz == r) ? sigma : 0.0);
+    }
+    __syncthreads();
+    // blocked right-looking Cholesky over the E block columns, then the S ones
+    bool ok = true;
+    double* D = sm;
+    double* dg = sm + dl::NB * dl::DP;
+    double* Tm = sm + dl::kDiag;
+    for (int c0 = 0; c0 < n;) {
+      const bool inE = c0 < nz;
+      const int bs = min(dl::NB, (inE ? nz : n) - c0);
+      ok = factor_diag(c0, bs, D, dg) && ok;
+      panel_solve(c0, bs, D, Tm);
+      // trailing update with the panel X = K(c0+bs.., c0..c0+bs)
+      const int t0 = c0 + bs;
+      const double* Kp = K;
+      const int nn = n, nzz = nz;
+      for (int I = 0; t0 + I * dl::TB < n; I++)
+        for (int J = 0; J <= I; J++) {
+          double acc[4][4][2];
+          auto li = [=](int idx, int k) {
+            const int r = t0 + I * dl::TB + idx;
+            return r < nn ? Kp[r + (size_t)(c0 + k) * nn] : 0.0;
+          };
+          auto lj = [=](int idx, int k) {
+            const int r = t0 + J * dl::TB + idx;
+            return r < nn ? Kp[r + (size_t)(c0 + k) * nn] : 0.0;
+          };
+          dl::mma_tile<false>(acc, sm, bs, li, lj, nullptr, I == J);
+          dl::for_each_acc(acc, [&](int r, int c, double v) {
+            const int gr = t0 + I * dl::TB + r, gc = t0 + J * dl::TB + c;
+            if (gr < n && gc <= gr) {
+              const size_t at = gr + (size_t)gc * n;
+              // S = sigma I + W'W grows while E's columns are eliminated
+              K[at] = (inE && gc >= nzz) ? K[at] + v : K[at] - v;
+            }
+          });
+        }
+      __syncthreads();
+      c0 += bs;
+    }
+    return ok;
+  }
+
+  // One warp: solves the bs x bs lower-triangular system Lkk u = a (forward)
+  // or Lkk' u = a (backward) for the diagonal block at c0; a, u in shared memory.
+  // D: the block staged in shared memory (stride DP).
+  __device__ __forceinline__ void diag_trsv(const double* D, int bs, double* a,
+                                            bool transposed) {
+    const int lane = threadIdx.x & 31;
+    double v0 = (lane < bs) ? a[lane] : 0.0;
+    double v1 = (lane + 32 < bs) ? a[lane + 32] : 0.0;
+    if (!transposed) {
+      for (int j = 0; j < bs; j++) {
+        const double* col = D + j * dl::DP;
+        const double aj = __shfl_sync(0xffffffffu, j < 32 ? v0 : v1, j & 31);
+        const double uj = aj / col[j];
+        if (lane == (j & 31)) (j < 32 ? v0 : v1) = uj;
+        if (lane > j && lane < bs) v0 = fma(-col[lane], uj, v0);
+        if (lane + 32 > j && lane + 32 < bs) v1 = fma(-col[lane + 32], uj, v1);
+      }
+    } else {
+      for (int j = bs - 1; j >= 0; j--) {
+        // row j of Lkk' is L(j, i), i < j
+        const double aj = __shfl_sync(0xffffffffu, j < 32 ? v0 : v1, j & 31);
+        const double uj = aj / D[j + j * dl::DP];
+        if (lane == (j & 31)) (j < 32 ? v0 : v1) = uj;
+        if (lane < j) v0 = fma(-D[j + lane * dl::DP], uj, v0);
+        if (lane + 32 < j) v1 = fma(-D[j + (lane + 32) * dl::DP], uj, v1);
+      }
+    }
+    if (lane < bs) a[lane] = v0;
+    if (lane + 32 < bs) a[lane + 32] = v1;
+  }
+
+  // LinearSolver::Solve with r = -(rz,rl,rv), dense_cholesky_solver.cc:81-127
+  __device__ __noinline__ void solve(const Team& t, const double* rz, const double* rl,
+                        const double* rv, const Vars& dx) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = dl::kThreads / 32;
+    double* ub = sm;           // current block of the right-hand side (NB doubles)
+    double* Db = sm + dl::NB;  // its diagonal block of the factor (NB x DP)
+    auto stage_block = [&](int c0, int bs) {
+      if (tid < bs) ub[tid] = r1[c0 + tid];
+      for (int e = tid; e < bs * bs; e += dl::kThreads) {
+        const int i = e % bs, j = e / bs;
+        if (i >= j) Db[i + j * dl::DP] = K[(c0 + i) + (size_t)(c0 + j) * n];
+      }
+      __syncthreads();
+    };
+    for (int i = tid; i < nv; i += dl::kThreads) r2[i] = (-rv[i]) / mus[i];
+    for (int i = tid; i < nl; i += dl::kThreads) r1[nz + i] = rl[i];
+    __syncthreads();
+    for (int i = warp; i < nz; i += nw) {
+      const double* a = A + (size_t)i * nv;
+      double s = 0.0;
+      for (int k = lane; k < nv; k += 32) s = fma(a[k], r2[k], s);
+      s = warp_sum(s);
+      if (lane == 0) r1[i] = (-rz[i]) - s;
+    }
+    __syncthreads();
+    // forward: u = L^-1 a over the E block columns; the G rows ride along, so
+    // r1(nz:n) becomes c - W'u
+    auto forward = [&](int cbeg, int cend, int rend) {
+      for (int c0 = cbeg; c0 < cend; c0 += dl::NB) {
+        const int bs = min(dl::NB, cend - c0);
+        stage_block(c0, bs);
+        if (warp == 0) diag_trsv(Db, bs, ub, false);
+        __syncthreads();
+        if (tid < bs) r1[c0 + tid] = ub[tid];
+        for (int r = c0 + bs + tid; r < rend; r += dl::kThreads) {
+          double s = 0.0;
+          for (int k = 0; k < bs; k++) s = fma(K[r + (size_t)(c0 + k) * n], ub[k], s);
+          r1[r] -= s;
+        }
+        __syncthreads();
+      }
+    };
+    // backward: u <- L^-T u over block columns [cbeg, cend)
+    auto backward = [&](int cbeg, int cend) {
+      int last = cbeg + ((cend - cbeg - 1) / dl::NB) * dl::NB;
+      for (int c0 = last; c0 >= cbeg; c0 -= dl::NB) {
+        const int bs = min(dl::NB, cend - c0);
+        stage_block(c0, bs);
+        if (warp == 0) diag_trsv(Db, bs, ub, true);
+        __syncthreads();
+        if (tid < bs) r1[c0 + tid] = ub[tid];
+        // u(j) -= sum_i L(c0+i, j) u(c0+i) for the columns j left of the block
+        for (int j = cbeg + warp; j < c0; j += nw) {
+          const double* col = K + (size_t)j * n + c0;
+          double s = 0.0;
+          for (int i = lane; i < bs; i += 32) s = fma(col[i], ub[i], s);
+          s = warp_sum(s);
+          if (lane == 0) r1[j] -= s;
+        }
+        __syncthreads();
+      }
+    };
+    forward(0, nz, n);
+    // dl = S^-1 (W'u - c): the tail now holds c - W'u
+    for (int i = tid; i < nl; i += dl::kThreads) r1[nz + i] = -r1[nz + i];
+    __syncthreads();
+    forward(nz, n, n);
+    backward(nz, n);
+    // u <- u - W dl, W = (K(nz:n, 0:nz))'
+    for (int j = warp; j < nz; j += nw) {
+      const double* col = K + (size_t)j * n + nz;
+      double s = 0.0;
+      for (int i = lane; i < nl; i += 32) s = fma(col[i], r1[nz + i], s);
+      s = warp_sum(s);
+      if (lane == 0) r1[j] -= s;
+    }
+    __syncthreads();
+    backward(0, nz);
+    for (int i = tid; i < nz; i += dl::kThreads) dx.z[i] = r1[i];
+    for (int i = tid; i < nl; i += dl::kThreads) dx.l[i] = r1[nz + i];
+    __syncthreads();
+    // dv = (rv + gamma .* (A dz)) ./ mus ; dy = b - A dz
+    for (int i = tid; i < nv; i += dl::kThreads) {
+      double s = 0.0;
+      for (int j = 0; j < nz; j++) s = fma(A[i + (size_t)j * nv], dx.z[j], s);
+      dx.v[i] = (gamma[i] * s + (-rv[i])) / mus[i];
+      dx.y[i] = bvec[i] - s;
+    }
+    __syncthreads();
+  }
+};
+
+}  // namespace fbs

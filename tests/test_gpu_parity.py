@@ -422,6 +422,58 @@ def test_dense_config5_sample(fb, oracle):
     assert rel_err(z[:nz], oz) <= SOL_TOL
 
 
+@pytest.mark.parametrize("sizes,B", [((136, 24, 200), 6), ((200, 70, 130), 4),
+                                     ((128, 0, 64), 4), ((257, 65, 300), 3)])
+def test_dense_large_path_parity(fb, oracle, sizes, B):
+    """The DMMA path (dense_large.cuh) on ragged sizes -- tiles, Cholesky blocks
+    and panels all partially filled -- against the oracle's Cholesky + Schur
+    variant (same elimination order)."""
+    nz, nl, nv = sizes
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=12)
+    s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+    assert s.path.startswith("dense-large"), s.path
+    # Newton-step stage on random iterates
+    rng = np.random.default_rng(7)
+    z, l, v = rng.normal(size=B * nz), rng.normal(size=B * nl), rng.normal(size=B * nv)
+    zb, lb, vb = rng.normal(size=B * nz), rng.normal(size=B * nl), rng.normal(size=B * nv)
+    y = np.zeros(B * nv)
+    s.component(fb.capi.COMP_MARGIN, d, B, z=z, dy=y)
+    rz, rl, rv = rng.normal(size=B * nz), rng.normal(size=B * nl), rng.normal(size=B * nv)
+    dz, dl, dv, dy = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv), np.zeros(B * nv)
+    st = np.ones(B, dtype=np.int32)
+    sigma = 1e-4
+    s.component(fb.capi.COMP_NEWTON, d, B, z=z, l=l, v=v, y=y, zbar=zb, lbar=lb,
+                vbar=vb, rz=rz.copy(), rl=rl.copy(), rv=rv.copy(), dz=dz, dl=dl,
+                dv=dv, dy=dy, status=st, sigma=sigma)
+    assert (st == 0).all()
+    sz = s.field_sizes
+    for i in range(B):
+        sl = lambda a, n: a[i * n:(i + 1) * n]
+        p = oracle.Problem.dense(*[sl(d[k], sz[k]) for k in fb.problems.DENSE_FIELDS])
+        rc, (odz, odl, odv, ody), _, _ = p.linear_solve(
+            (sl(z, nz), sl(l, nl), sl(v, nv), sl(y, nv)), (sl(zb, nz), sl(lb, nl), sl(vb, nv)),
+            sigma, (sl(rz, nz), sl(rl, nl), sl(rv, nv)), variant=2)
+        assert rc == 0
+        for a, b_ in ((sl(dz, nz), odz), (sl(dl, nl), odl), (sl(dv, nv), odv),
+                      (sl(dy, nv), ody)):
+            assert rel_err(a, b_) <= 1e-9, (i, rel_err(a, b_))
+    # full solves
+    z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, oz, ol, ov, oy = oracle.dense_solve_batch(
+        nz, nl, nv, *[d[k] for k in fb.problems.DENSE_FIELDS], variant=2, nthreads=4)
+    assert (out["eflag"] == oo["eflag"]).all() and (out["status"] == 0).all()
+    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 1
+    same = _same_traj(out, oo)
+    # blocked DMMA elimination vs the oracle's unblocked one: same trajectory,
+    # iterates that differ by rounding amplified through the 1e-6 residual
+    # tolerance (3.3e-8 measured on the nl=0, nv<nz case); the BASELINE shapes
+    # are held to 1e-8 in test_dense_config5_sample
+    for i in range(B):
+        tol = 1e-7 if same[i] else 1e-5
+        assert rel_err(z[i * nz:(i + 1) * nz], oz[i * nz:(i + 1) * nz]) <= tol
+
+
 def test_device_pointers_and_stream(fb):
     """Device-resident buffers (torch CUDA tensors) are used in place and the
     call is asynchronous on the given stream; results equal the host path."""
