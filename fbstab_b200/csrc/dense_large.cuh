@@ -15,8 +15,8 @@
 // as FP64 DMMA (mma.sync.m8n8k4.f64):
 //   * A' Gamma A : 128x128 tiles of E, K = nv deep (75% of the flops);
 //   * every trailing update of the blocked Cholesky (K = 64 deep).
-// Operand chunks (128 x 16) are staged global -> registers -> shared with the
-// next chunk's loads in flight during the current chunk's DMMAs.  Diagonal
+// Operand chunks (128 x 16) are staged global -> shared by cp.async through a
+// three-deep ring, two chunks ahead of the DMMAs.  Diagonal
 // blocks and panel solves work in shared memory; the triangular solves of
 // ::Solve are blocked the same way (one warp solves a diagonal block with
 // shuffles, all warps apply the block column).
@@ -35,7 +35,9 @@ constexpr int NB = 64;   // Cholesky block
 constexpr int DP = NB + 1;
 constexpr int TR = 256;  // rows of one panel-solve tile
 // shared-memory carve (doubles)
-constexpr int kStage = 2 * (2 * TB * KP + KC);  // two buffers x (two operand chunks + Gamma)
+constexpr int kStages = 3;                      // cp.async ring depth
+constexpr int kStageDoubles = 2 * TB * KP + KC;  // two operand chunks + Gamma
+constexpr int kStage = kStages * kStageDoubles;
 constexpr int kDiag = NB * DP + NB;             // diagonal block + its pivots
 constexpr int kPanel = TR * NB;
 constexpr int kSmemDoubles = (kDiag + kPanel) > kStage ? (kDiag + kPanel) : kStage;
@@ -47,13 +49,29 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
       : "d"(a), "d"(b));
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS); `valid` false zero-fills.
+__device__ __forceinline__ void cp8(double* dst, const double* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // acc(128x128, this warp's 32x32 part) = sum_k opI(i,k) * [scale(k)] * opJ(j,k).
-// LoadI / LoadJ: (idx in [0,128), k in [0,depth)) -> element, 0 outside the
-// matrix.  The 16 warps form a 4x4 grid; warp (wm,wn) owns rows 32wm.., cols
-// 32wn.. as 4x4 m8n8 DMMA tiles.  `same`: opJ == opI (diagonal tile).
-template <bool SCALED, class LoadI, class LoadJ>
+// AddrI / AddrJ: (idx in [0,128), k in [0,depth)) -> global address of the
+// element, or nullptr outside the matrix (zero filled).  The 16 warps form a
+// 4x4 grid; warp (wm,wn) owns rows 32wm.., cols 32wn.. as 4x4 m8n8 DMMA tiles.
+// `same`: opJ == opI (diagonal tile).  Operand chunks travel global -> shared
+// as cp.async copies through a kStages-deep ring, two chunks ahead of the
+// DMMAs, with one barrier per chunk.
+template <bool SCALED, class AddrI, class AddrJ>
 __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], double* sm, int depth,
-                                         LoadI li, LoadJ lj, const double* scale, bool same) {
+                                         AddrI ai, AddrJ aj, const double* scale, bool same) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r8 = lane >> 2, c4 = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
@@ -63,33 +81,33 @@ __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], double* sm, int
 #pragma unroll
     for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
   const int nchunk = (depth + KC - 1) / KC;
-  double ri[4], rj[4], rs = 0.0;
-  auto fetch = [&](int ch) {
-    const int k0 = ch * KC;
+  auto issue = [&](int ch) {
+    if (ch < nchunk) {
+      const int k0 = ch * KC;
+      double* SI = sm + (ch % kStages) * kStageDoubles;
+      double* SJ = SI + TB * KP;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int k = k0 + 4 * q + c4;
-      ri[q] = (k < depth) ? li(sidx, k) : 0.0;
-      if (!same) rj[q] = (k < depth) ? lj(sidx, k) : 0.0;
+      for (int q = 0; q < 4; q++) {
+        const int k = k0 + 4 * q + c4;
+        const double* pi = (k < depth) ? ai(sidx, k) : nullptr;
+        cp8(SI + sidx * KP + 4 * q + c4, pi ? pi : scale, pi != nullptr);
+        if (!same) {
+          const double* pj = (k < depth) ? aj(sidx, k) : nullptr;
+          cp8(SJ + sidx * KP + 4 * q + c4, pj ? pj : scale, pj != nullptr);
+        }
+      }
+      if (SCALED && tid < KC)
+        cp8(SI + 2 * TB * KP + tid, scale + (k0 + tid < depth ? k0 + tid : 0), k0 + tid < depth);
     }
-    if (SCALED && tid < KC) rs = (k0 + tid < depth) ? scale[k0 + tid] : 0.0;
+    cp_commit();
   };
-  auto stash = [&](int buf) {
-    double* SI = sm + buf * (2 * TB * KP + KC);
-    double* SJ = SI + TB * KP;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      SI[sidx * KP + 4 * q + c4] = ri[q];
-      if (!same) SJ[sidx * KP + 4 * q + c4] = rj[q];
-    }
-    if (SCALED && tid < KC) SI[2 * TB * KP + tid] = rs;
-  };
-  fetch(0);
-  stash(0);
-  __syncthreads();
+  issue(0);
+  issue(1);
   for (int ch = 0; ch < nchunk; ch++) {
-    if (ch + 1 < nchunk) fetch(ch + 1);  // global loads in flight during the DMMAs
-    const double* SI = sm + (ch & 1) * (2 * TB * KP + KC);
+    cp_wait<1>();     // this thread's copies of chunk ch have landed
+    __syncthreads();  // everyone's have; everyone is done with chunk ch-1
+    issue(ch + 2);    // into the buffer chunk ch-1 used
+    const double* SI = sm + (ch % kStages) * kStageDoubles;
     const double* SJ = same ? SI : SI + TB * KP;
     const double* SG = SI + 2 * TB * KP;
 #pragma unroll
@@ -108,9 +126,9 @@ __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], double* sm, int
 #pragma unroll
         for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
-    if (ch + 1 < nchunk) stash((ch + 1) & 1);
-    __syncthreads();
   }
+  cp_wait<0>();
+  __syncthreads();  // the ring is free for the next tile (or the next phase)
 }
 
 // Visits this thread's accumulator entries: f(tile_row, tile_col, value).
@@ -152,10 +170,15 @@ struct DenseLargeProblem : DenseProblem {
       if (tid == 0) dg[j] = sd;
       for (int i = j + 1 + tid; i < bs; i += dl::kThreads) D[i + j * dl::DP] /= sd;
       __syncthreads();
-      const int m = bs - 1 - j;  // trailing (i,k), j < k <= i < bs
-      for (int e = tid; e < m * m; e += dl::kThreads) {
-        const int i = j + 1 + e % m, k = j + 1 + e / m;
-        if (i >= k) D[i + k * dl::DP] = fma(-D[i + j * dl::DP], D[k + j * dl::DP], D[i + k * dl::DP]);
+      // trailing (i,k), j < k <= i < bs: thread (tid & 63) owns row i, the
+      // eight thread groups stride over the columns
+      {
+        const int i = j + 1 + (tid & 63);
+        if (i < bs) {
+          const double lij = D[i + j * dl::DP];
+          for (int k = j + 1 + (tid >> 6); k <= i; k += dl::kThreads / 64)
+            D[i + k * dl::DP] = fma(-lij, D[k + j * dl::DP], D[i + k * dl::DP]);
+        }
       }
       __syncthreads();
     }
@@ -168,31 +191,37 @@ struct DenseLargeProblem : DenseProblem {
     return ok;
   }
 
-  // Rows [r0, n) of block column c0: X = B Lkk^-T, right-looking on a
-  // shared-memory tile of TR rows.
+  // Rows [r0, n) of block column c0: X = B Lkk^-T on shared-memory tiles of
+  // TR rows.  Two threads share a row (even / odd terms of the substitution's
+  // dot product, combined with one shuffle); no barrier inside a tile.
   __device__ __noinline__ void panel_solve(int c0, int bs, const double* D, double* Tm) {
     const int tid = threadIdx.x;
+    const int half = tid & 1, rl = tid >> 1;
     for (int r0 = c0 + bs; r0 < n; r0 += dl::TR) {
       const int rows = min(dl::TR, n - r0);
-      for (int e = tid; e < rows * bs; e += dl::kThreads) {
-        const int r = e % rows, k = e / rows;
-        Tm[r + k * dl::TR] = K[(r0 + r) + (size_t)(c0 + k) * n];
+      for (int k = tid / dl::TR; k < bs; k += dl::kThreads / dl::TR) {
+        const int r = tid % dl::TR;
+        if (r < rows) Tm[r + k * dl::TR] = K[(r0 + r) + (size_t)(c0 + k) * n];
       }
       __syncthreads();
-      for (int j = 0; j < bs; j++) {
-        const double dj = D[j + j * dl::DP];
-        for (int r = tid; r < rows; r += dl::kThreads) Tm[r + j * dl::TR] /= dj;
-        __syncthreads();
-        const int m = bs - 1 - j;
-        for (int e = tid; e < rows * m; e += dl::kThreads) {
-          const int r = e % rows, k = j + 1 + e / rows;
-          Tm[r + k * dl::TR] = fma(-Tm[r + j * dl::TR], D[k + j * dl::DP], Tm[r + k * dl::TR]);
+      const unsigned mask = __ballot_sync(0xffffffffu, rl < rows);
+      if (rl < rows) {
+        double* row = Tm + rl;
+        for (int j = 0; j < bs; j++) {
+          // x_j = (b_j - sum_{k<j} x_k L(j,k)) / L(j,j)
+          double s = 0.0;
+          for (int k = half; k < j; k += 2) s = fma(row[k * dl::TR], D[j + k * dl::DP], s);
+          s += __shfl_xor_sync(mask, s, 1);
+          const double xj = (row[j * dl::TR] - s) / D[j + j * dl::DP];
+          __syncwarp(mask);
+          if (half == 0) row[j * dl::TR] = xj;
+          __syncwarp(mask);
         }
-        __syncthreads();
       }
-      for (int e = tid; e < rows * bs; e += dl::kThreads) {
-        const int r = e % rows, k = e / rows;
-        K[(r0 + r) + (size_t)(c0 + k) * n] = Tm[r + k * dl::TR];
+      __syncthreads();
+      for (int k = tid / dl::TR; k < bs; k += dl::kThreads / dl::TR) {
+        const int r = tid % dl::TR;
+        if (r < rows) K[(r0 + r) + (size_t)(c0 + k) * n] = Tm[r + k * dl::TR];
       }
       __syncthreads();
     }
@@ -219,13 +248,13 @@ struct DenseLargeProblem : DenseProblem {
       for (int I = 0; I * dl::TB < nz; I++)
         for (int J = 0; J <= I; J++) {
           double acc[4][4][2];
-          auto li = [=](int idx, int k) {
+          auto li = [=](int idx, int k) -> const double* {
             const int c = I * dl::TB + idx;
-            return c < nzz ? Ap[k + (size_t)c * nvv] : 0.0;
+            return c < nzz ? Ap + k + (size_t)c * nvv : nullptr;
           };
-          auto lj = [=](int idx, int k) {
+          auto lj = [=](int idx, int k) -> const double* {
             const int c = J * dl::TB + idx;
-            return c < nzz ? Ap[k + (size_t)c * nvv] : 0.0;
+            return c < nzz ? Ap + k + (size_t)c * nvv : nullptr;
           };
           dl::mma_tile<true>(acc, sm, nv, li, lj, Gam, I == J);
           dl::for_each_acc(acc, [&](int r, int c, double v) {
@@ -259,15 +288,15 @@ struct DenseLargeProblem : DenseProblem {
       for (int I = 0; t0 + I * dl::TB < n; I++)
         for (int J = 0; J <= I; J++) {
           double acc[4][4][2];
-          auto li = [=](int idx, int k) {
+          auto li = [=](int idx, int k) -> const double* {
             const int r = t0 + I * dl::TB + idx;
-            return r < nn ? Kp[r + (size_t)(c0 + k) * nn] : 0.0;
+            return r < nn ? Kp + r + (size_t)(c0 + k) * nn : nullptr;
           };
-          auto lj = [=](int idx, int k) {
+          auto lj = [=](int idx, int k) -> const double* {
             const int r = t0 + J * dl::TB + idx;
-            return r < nn ? Kp[r + (size_t)(c0 + k) * nn] : 0.0;
+            return r < nn ? Kp + r + (size_t)(c0 + k) * nn : nullptr;
           };
-          dl::mma_tile<false>(acc, sm, bs, li, lj, nullptr, I == J);
+          dl::mma_tile<false>(acc, sm, bs, li, lj, Kp, I == J);
           dl::for_each_acc(acc, [&](int r, int c, double v) {
             const int gr = t0 + I * dl::TB + r, gc = t0 + J * dl::TB + c;
             if (gr < n && gc <= gr) {
