@@ -1,18 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- batched QP solves/sec on B200 (BASELINE.json metric).
 
-Workload (config.workload): BASELINE config 2 -- 65,536 independent random
-dense QPs with nz=32, nl=8, nv=64 per GPU, default FBstab options, cold start.
-A "step" is one complete batched solve of that shard.  With N GPUs every rank
-solves its own 65,536-instance shard of one N*65,536-instance batch (instances
-are independent: no data-path collective) and the packed results are gathered
-to rank 0 over NCCL inside the timed region -> "scaling": "weak".
+Default workload (config.workload): BASELINE config 2 -- 65,536 independent
+random dense QPs with nz=32, nl=8, nv=64 per GPU, default FBstab options, cold
+start.  `--config 3a|3b|4a|4b|5` selects the other BASELINE configs (servo
+motor / double integrator N=50, spacecraft / copolymerisation N=100, dense
+nz=512) with the same JSON line; they are reported in DESIGN.md, the driver's
+bench line is config 2.
+
+A "step" is one complete batched solve of this rank's shard.  With N GPUs every
+rank solves its own shard (instances are independent: no data-path collective)
+and the packed results are gathered to rank 0 over NCCL inside the timed region.
+Configs 2-4 keep the per-GPU batch fixed ("scaling": "weak"); config 5 shards
+its 1,024 instances across the GPUs as BASELINE.json words it ("strong").
 
   value   solves/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e     the same through the public C-ABI with HOST (pinned) buffers: H2D of
           the problem data and D2H of the results inside the timed region
-  roofline  FP64 (the binding roof for this path) against a
-          DFMA peak measured in this run, plus the HBM fraction
+  roofline  FP64 (the binding roof for this path) against the
+          DFMA / DMMA peak measured in this run, plus the HBM fraction
   cpu_baseline  the CPU oracle (restated reference, no Eigen in this image) on
           the host cores, on a bounded prefix of the same instances
 
@@ -31,31 +37,102 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NZ, NL, NV = 32, 8, 64
-BATCH = 65536
-CONFIG_ID = 2
-METRIC = "batched QP solves/sec (FBstabDense nz=32 nl=8 nv=64, 65,536 instances per GPU)"
 UNIT = "solves/s"
-WORKLOAD = ("batched FBstabDense 65,536 random dense QPs nz=32 nl=8 nv=64 per GPU "
-            "(BASELINE config 2), default options, cold start")
+
+# name -> (kind, spec, instances, generator config id, rho, scaling, cpu sample per core)
+CONFIGS = {
+    "2": ("dense", (32, 8, 64), 65536, 2, None, "weak", 2048),
+    "3a": ("mpc", ("servo_motor", 50), 16384, 3, 0.02, "weak", 96),
+    "3b": ("mpc", ("double_integrator", 50), 16384, 3, -0.1, "weak", 512),
+    "4a": ("mpc", ("spacecraft", 100), 4096, 4, 0.05, "weak", 2),
+    "4b": ("mpc", ("copolymerization", 100), 4096, 4, 0.05, "weak", 6),
+    "5": ("dense", (512, 128, 1024), 1024, 5, None, "strong", 1),
+}
+OCP_DIMS = {"servo_motor": (4, 1, 4), "double_integrator": (2, 1, 6),
+            "spacecraft": (6, 3, 12), "copolymerization": (18, 5, 10)}
 
 
-# ---- algorithmic work per solve ---------------------
-def work_flops(newton, prox, backtracks, check_feasibility=True):
-    nz, nl, nv = NZ, NL, NV
-    f_res = 2 * nz * nz + 4 * nl * nz + 2 * nv * nz
-    f_init = nv * nz * (nz + 1) + nv * nz + (nz + nl) ** 3 / 3.0
-    f_solve = 4 * nv * nz + 2 * (nz + nl) ** 2
-    w = newton * (f_init + f_solve + 2 * f_res) + backtracks * f_res
-    w = w + (2 * prox + 2) * f_res
-    if check_feasibility:
-        w = w + prox * f_res
-    return w
+class Workload:
+    """Sizes, generator and the algorithmic work model of one BASELINE config."""
 
+    def __init__(self, name):
+        self.name = name
+        (self.kind, spec, self.batch, self.cfg, self.rho, self.scaling,
+         self.cpu_per_core) = CONFIGS[name]
+        if self.kind == "dense":
+            self.nz, self.nl, self.nv = spec
+            self.label = (f"batched FBstabDense {self.batch:,} random dense QPs nz={self.nz} "
+                          f"nl={self.nl} nv={self.nv} (BASELINE config {name}), default "
+                          "options, cold start")
+            self.desc = {"nz": self.nz, "nl": self.nl, "nv": self.nv}
+        else:
+            self.ocp, self.N = spec
+            self.nx, self.nu, self.nc = OCP_DIMS[self.ocp]
+            K = self.N + 1
+            self.nz, self.nl, self.nv = K * (self.nx + self.nu), K * self.nx, K * self.nc
+            self.label = (f"batched FBstabMpc {self.ocp} OCP horizon N={self.N}, "
+                          f"{self.batch:,} instances (BASELINE config {name}; x0 = nominal + "
+                          + (f"{self.rho}*U(-1,1)" if self.rho > 0 else f"{-self.rho}*U(0,1)") +
+                          "), default options, cold start")
+            self.desc = {"ocp": self.ocp, "N": self.N, "nx": self.nx, "nu": self.nu,
+                         "nc": self.nc, "rho": self.rho}
+        self.metric = f"batched QP solves/sec ({self.label.split(' (BASELINE')[0]})"
 
-def bytes_per_solve():
-    data = NZ * NZ + NL * NZ + NV * NZ + NZ + NL + NV
-    return 8 * (data + (NZ + NL + NV) + (NZ + NL + 2 * NV)) + 48
+    # ---- problem data ------------------------------------------------------
+    def generate(self, fb, count, first, threads, alloc=None):
+        if self.kind == "dense":
+            return fb.problems.random_dense_qp(self.nz, self.nl, self.nv, count=count,
+                                               config=self.cfg, first=first,
+                                               nthreads=threads, alloc=alloc)
+        return fb.problems.ocp_batch(self.ocp, self.N, count=count, config=self.cfg,
+                                     rho=self.rho, first=first, alloc=alloc)[1]
+
+    def solver(self, fb, max_batch, device):
+        if self.kind == "dense":
+            return fb.FBstabDense(self.nz, self.nl, self.nv, max_batch=max_batch, device=device)
+        return fb.FBstabMpc(self.N, self.nx, self.nu, self.nc, max_batch=max_batch,
+                            device=device)
+
+    def cpu_solve(self, ob, fb, d, threads):
+        if self.kind == "dense":
+            return ob.dense_solve_batch(self.nz, self.nl, self.nv,
+                                        *[d[k] for k in fb.problems.DENSE_FIELDS],
+                                        nthreads=threads)
+        return ob.mpc_solve_batch(self.N, self.nx, self.nu, self.nc,
+                                  [d[k] for k in fb.problems.MPC_FIELDS], nthreads=threads)
+
+    # ---- algorithmic work per solve (SURVEY.md section 8(a)) ----------------
+    def flops(self, newton, prox, backtracks, check_feasibility=True):
+        if self.kind == "dense":
+            nz, nl, nv = self.nz, self.nl, self.nv
+            f_res = 2 * nz * nz + 4 * nl * nz + 2 * nv * nz
+            f_init = nv * nz * (nz + 1) + nv * nz + (nz + nl) ** 3 / 3.0
+            f_solve = 4 * nv * nz + 2 * (nz + nl) ** 2
+        else:
+            N, nx, nu, nc = self.N, self.nx, self.nu, self.nc
+            ns = nx + nu
+            f_res = (N + 1) * (2 * ns * ns + 2 * nc * ns) + 4 * N * nx * ns
+            f_init = (N + 1) * ((10 / 3.0) * nx ** 3 + 4 * nx * nx * nu + 2 * nx * nu * nu +
+                                nu ** 3 / 3.0 + nc * ns * ns + nc * ns)
+            f_solve = (N + 1) * (11 * nx * nx + 10 * nx * nu + 3 * nu * nu + 4 * nc * ns)
+        w = newton * (f_init + f_solve + 2 * f_res) + backtracks * f_res
+        w = w + (2 * prox + 2) * f_res
+        if check_feasibility:
+            w = w + prox * f_res
+        return w
+
+    def data_doubles(self):
+        if self.kind == "dense":
+            nz, nl, nv = self.nz, self.nl, self.nv
+            return nz * nz + nl * nz + nv * nz + nz + nl + nv
+        N, nx, nu, nc = self.N, self.nx, self.nu, self.nc
+        K = N + 1
+        return (K * (nx * nx + nu * nu + nu * nx + nx + nu + nc * nx + nc * nu + nc) +
+                N * (nx * nx + nx * nu + nx) + nx)
+
+    def bytes_per_solve(self):
+        nz, nl, nv = self.nz, self.nl, self.nv
+        return 8 * (self.data_doubles() + (nz + nl + nv) + (nz + nl + 2 * nv)) + 48
 
 
 class ClockSampler(threading.Thread):
@@ -81,7 +158,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in o.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.1)
 
     def summary(self):
         self.stop_flag.set()
@@ -104,44 +181,40 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_reference_run(count, threads, first=0):
+def cpu_reference_run(wl, count, threads, first=0):
     """Times the CPU oracle on `count` instances of the workload."""
     import fbstab_b200 as fb
     from oracle import binding as ob
     ob.build()
-    d = fb.problems.random_dense_qp(NZ, NL, NV, count=count, config=CONFIG_ID,
-                                    first=first, nthreads=threads)
-    args = [d[k] for k in fb.problems.DENSE_FIELDS]
+    d = wl.generate(fb, count, first, threads)
     t0 = time.perf_counter()
-    out, z, l, v, y = ob.dense_solve_batch(NZ, NL, NV, *args, nthreads=threads)
+    out, z, l, v, y = wl.cpu_solve(ob, fb, d, threads)
     dt = time.perf_counter() - t0
     return count / dt, dt, out, z
 
 
-def run_reference(args):
+def run_reference(args, wl):
     """--impl reference: the reference's CPU algorithm on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = host_threads()
-    # ~1.5 ms per solve per core: size each step for a few seconds of work
-    count = max(256, min(BATCH, 1024 * threads // 4))
+    count = max(threads, min(wl.batch, wl.cpu_per_core * threads))
     for _ in range(args.warmup):
-        cpu_reference_run(min(count, 256), threads)
+        cpu_reference_run(wl, max(threads, count // 16), threads)
     t_total = 0.0
     for s in range(args.steps):
-        _, dt, _, _ = cpu_reference_run(count, threads, first=s * count)
+        _, dt, _, _ = cpu_reference_run(wl, count, threads, first=s * count)
         t_total += dt
     value = args.steps * count / t_total
-    sample = (f"{count} instances per step (prefix of the {BATCH}-instance shard), "
+    sample = (f"{count} instances per step (prefix of the {wl.batch}-instance batch), "
               f"{threads} host threads, one solver per thread")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "impl": "reference", "metric": wl.metric, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nz": NZ, "nl": NL, "nv": NV,
-                   "instances_per_step": count},
+        "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict({"workload": wl.label, "instances_per_step": count}, **wl.desc),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample,
                          "note": "restated reference (oracle/), Eigen is not in this image"},
@@ -158,16 +231,19 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    wl = Workload(args.config)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl)
         return
 
     import torch
     import torch.distributed as dist
     import fbstab_b200 as fb
+    from fbstab_b200 import sharding
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -178,37 +254,39 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    total = args.batch or wl.batch
+    if wl.scaling == "weak":
+        B, first, global_batch = total, rank * total, world * total
+    else:
+        lo, hi = sharding.shard_range(total, world, rank)
+        B, first, global_batch = hi - lo, lo, total
+    cap = max(sharding.shard_sizes(global_batch, world))
     W = max(args.warmup, 3)
     K = args.steps
     threads = max(1, host_threads() // max(world, 1))
+    nz, nl, nv = wl.nz, wl.nl, wl.nv
 
     # ---- synthetic inputs: this rank's shard of the global batch, pinned host
     pin = lambda n: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
-    d_host = fb.problems.random_dense_qp(NZ, NL, NV, count=B, config=CONFIG_ID,
-                                         first=rank * B, nthreads=threads, alloc=pin)
+    d_host = wl.generate(fb, B, first, threads, alloc=pin)
     d_dev = {k: torch.from_numpy(a).to(dev) for k, a in d_host.items()}
-    solver = fb.FBstabDense(NZ, NL, NV, max_batch=B, device=local_rank)
+    solver = wl.solver(fb, B, local_rank)
     f64 = lambda n: torch.zeros(n, dtype=torch.float64, device=dev)
-    z, l, v, y = f64(B * NZ), f64(B * NL), f64(B * NV), f64(B * NV)
+    z, l, v, y = f64(B * nz), f64(B * nl), f64(B * nv), f64(B * nv)
     out = torch.zeros(B * fb.OUT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    rec = (NZ + NL + 2 * NV) * 8 + fb.OUT_DTYPE.itemsize
-    packed = torch.empty(B * rec, dtype=torch.uint8, device=dev)
-    gathered = ([torch.empty_like(packed) for _ in range(world)]
-                if (world > 1 and rank == 0) else None)
     stream = torch.cuda.current_stream()
 
-    def step_device():
+    def step_device(ev0=None, ev1=None):
         z.zero_(), l.zero_(), v.zero_()  # cold start
+        if ev0 is not None:
+            ev0.record(stream)
         solver.solve_batch(d_dev, z, l, v, y=y, out=out, stream=stream.cuda_stream)
+        if ev1 is not None:
+            ev1.record(stream)
         if world > 1:  # result gather to rank 0 (the only collective on the path)
-            off = 0
-            for t in (z, l, v, y):
-                nb = t.numel() * 8
-                packed[off:off + nb].copy_(t.view(torch.uint8))
-                off += nb
-            packed[off:].copy_(out)
-            dist.gather(packed, gathered, dst=0)
+            packed = sharding.pack(torch, z, l, v, y, out, B, cap, (nz, nl, nv))
+            bufs = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
+            dist.gather(packed, bufs, dst=0)
 
     def barrier():
         if world > 1:
@@ -226,18 +304,7 @@ def main():
     barrier()
     e0.record(stream)
     for s in range(K):
-        z.zero_(), l.zero_(), v.zero_()
-        ker0[s].record(stream)
-        solver.solve_batch(d_dev, z, l, v, y=y, out=out, stream=stream.cuda_stream)
-        ker1[s].record(stream)
-        if world > 1:
-            off = 0
-            for t in (z, l, v, y):
-                nb = t.numel() * 8
-                packed[off:off + nb].copy_(t.view(torch.uint8))
-                off += nb
-            packed[off:].copy_(out)
-            dist.gather(packed, gathered, dst=0)
+        step_device(ker0[s], ker1[s])
     e1.record(stream)
     barrier()
     clocks = sampler.summary()
@@ -247,14 +314,14 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_total = float(tt.item())
-    value = world * B * K / (ms_total * 1e-3)
+    value = global_batch * K / (ms_total * 1e-3)
     launches = K * solver.last_launches
 
     o = np.frombuffer(out.cpu().numpy().tobytes(), dtype=fb.OUT_DTYPE)
     flags = np.bincount(o["eflag"], minlength=6).tolist()
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region
-    zh, lh, vh, yh = pin(B * NZ), pin(B * NL), pin(B * NV), pin(B * NV)
+    zh, lh, vh, yh = pin(B * nz), pin(B * nl), pin(B * nv), pin(B * nv)
     oh = np.frombuffer(torch.empty(B * fb.OUT_DTYPE.itemsize, dtype=torch.uint8,
                                    pin_memory=True).numpy(), dtype=fb.OUT_DTYPE)
 
@@ -266,15 +333,16 @@ def main():
 
     step_host()
     barrier()
+    Ke = max(1, min(K, 3))
     t0 = time.perf_counter()
-    for _ in range(K):
+    for _ in range(Ke):
         step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / float(te.item())
+    e2e_value = global_batch * Ke / float(te.item())
     h2d = sum(a.nbytes for a in d_host.values()) + zh.nbytes + lh.nbytes + vh.nbytes
     d2h = zh.nbytes + lh.nbytes + vh.nbytes + yh.nbytes + oh.nbytes
     assert (oh["eflag"] == o["eflag"]).all(), "host and device paths disagree"
@@ -286,10 +354,10 @@ def main():
 
     # ---- roofline of the dominant kernel (the persistent solve kernel)
     dfma, dmma = fb.capi.fp64_peak(local_rank)
-    W_total = float(work_flops(o["newton_iters"].astype(np.float64),
-                               o["prox_iters"].astype(np.float64),
-                               o["ls_backtracks"].astype(np.float64)).sum())
-    B_total = float(bytes_per_solve()) * B
+    W_total = float(wl.flops(o["newton_iters"].astype(np.float64),
+                             o["prox_iters"].astype(np.float64),
+                             o["ls_backtracks"].astype(np.float64)).sum())
+    B_total = float(wl.bytes_per_solve()) * B
     ach_tf = W_total / (kernel_ms * 1e-3) / 1e12
     ach_gbs = B_total / (kernel_ms * 1e-3) / 1e9
     hbm_peak, hbm_src = 6650.0, "fallback"
@@ -298,14 +366,21 @@ def main():
             hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "measured"
     except Exception:
         pass
+    tensor_bound = args.config == "5"  # A'GammaA + Cholesky updates run as DMMA
+    peak = dmma if tensor_bound else dfma
+    # DRAM traffic of the config-2 kernel from the committed ncu capture
+    # (profiles/r1_dense_small_ncu_full.txt): 29.7 KB per instance
+    traffic = 29659.0 * B if args.config == "2" else None
     roofline = {
-        "bound": "fp64", "achieved": ach_tf, "peak": dfma, "unit": "TFLOP/s",
-        "frac": ach_tf / dfma, "traffic": None,
-        "peak_source": "DFMA loop measured in this run (fbstab_fp64_peak); DMMA "
-                       f"mma.sync peak {dmma:.1f} TFLOP/s",
+        "bound": "tensor" if tensor_bound else "fp64", "achieved": ach_tf, "peak": peak,
+        "unit": "TFLOP/s", "frac": ach_tf / peak, "traffic": traffic,
+        "peak_source": f"measured in this run (fbstab_fp64_peak): DFMA loop {dfma:.1f}, "
+                       f"FP64 mma.sync (DMMA) loop {dmma:.1f} TFLOP/s",
         "kernel": solver.path, "kernel_ms": kernel_ms,
         "algorithmic_flops_per_launch": W_total,
         "algorithmic_bytes_per_launch": B_total,
+        "work_model": "SURVEY.md 8(a) W_flops with this run's per-instance newton / prox / "
+                      "backtrack counters",
         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
     }
@@ -314,29 +389,35 @@ def main():
     cpu = None
     if not args.no_cpu:
         cores = host_threads()
-        count = max(256, min(B, 768 * cores // 2))
-        cv, cdt, co, cz = cpu_reference_run(count, cores, first=0)
-        match = bool((co["newton_iters"] == o["newton_iters"][:count]).all() and
-                     (co["prox_iters"] == o["prox_iters"][:count]).all() and
-                     (co["eflag"] == o["eflag"][:count]).all())
-        zg = z[:count * NZ].cpu().numpy()
-        err = float(np.abs(zg - cz).max() / max(1.0, np.abs(cz).max()))
+        count = max(1, min(B, wl.cpu_per_core * cores))
+        cv, cdt, co, cz = cpu_reference_run(wl, count, cores, first=first)
+        match = ((co["newton_iters"] == o["newton_iters"][:count]) &
+                 (co["prox_iters"] == o["prox_iters"][:count]) &
+                 (co["eflag"] == o["eflag"][:count]))
+        zg = z[:count * nz].cpu().numpy()
+        okf = (co["eflag"] == 0) & (o["eflag"][:count] == 0) & match
+        Z, CZ = zg.reshape(count, nz), cz.reshape(count, nz)
+        err = float(max([np.abs(Z[i] - CZ[i]).max() / max(1.0, np.abs(CZ[i]).max())
+                         for i in np.nonzero(okf)[0]] or [0.0]))
         cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {count} of the {B} instances of rank 0's shard, "
                          f"{cdt:.1f} s on {cores} host threads (one solver per thread)",
                "note": "restated reference (oracle/): Eigen is not in this image",
-               "trajectory_matches_gpu": match, "max_rel_solution_diff": err}
+               "same_flags": bool((co["eflag"] == o["eflag"][:count]).all()),
+               "same_trajectory_frac": float(match.mean()),
+               "max_rel_solution_diff_same_trajectory": err}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_total / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nz": NZ, "nl": NL, "nv": NV,
-                   "instances_per_gpu": B, "global_batch": world * B,
-                   "l2": "inputs (1.9 GB per GPU) exceed the 126 MB L2; no flush needed",
-                   "exit_flags": flags, "path": solver.path,
-                   "newton_iters_mean": float(o["newton_iters"].mean())},
+        "config": dict({"workload": wl.label, "instances_per_gpu": B,
+                        "global_batch": global_batch,
+                        "l2": f"inputs ({sum(a.nbytes for a in d_host.values()) / 1e6:.0f} MB "
+                              "per GPU) exceed the 126 MB L2; no flush needed",
+                        "exit_flags": flags, "path": solver.path,
+                        "newton_iters_mean": float(o["newton_iters"].mean())}, **wl.desc),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},

@@ -385,8 +385,10 @@ int fbstab_ocp_generate_batch(int kind, int N, int config, long first,
     const long inst = first + i;
     if (inst != 0 && rho != 0.0) {
       Rng rng((uint64_t)config, (uint64_t)inst);
+      // rho < 0: one-sided perturbation |rho| U(0,1), for OCPs whose nominal
+      // x0 sits on a constraint boundary (double integrator: x >= 0)
       for (size_t k = 0; k < nx; k++)
-        x0i[k] += rho * (2.0 * rng.uniform() - 1.0);
+        x0i[k] += rho > 0.0 ? rho * (2.0 * rng.uniform() - 1.0) : -rho * rng.uniform();
     }
   }
   return FBSTAB_OK;

@@ -239,7 +239,8 @@ int fbstab_ocp_generate(int kind, int N, double* Q, double* R, double* S,
                         double* q, double* r, double* A, double* B, double* c,
                         double* E, double* L, double* d, double* x0);
 /* `count` instances first..first+count-1 of benchmark config `config`:
- * identical stage data, x0 = nominal + rho*U(-1,1)^nx (instance 0 unperturbed). */
+ * identical stage data, x0 = nominal + rho*U(-1,1)^nx (instance 0 unperturbed);
+ * rho < 0 perturbs one-sidedly, x0 = nominal + |rho|*U(0,1)^nx. */
 int fbstab_ocp_generate_batch(int kind, int N, int config, long first, int count,
                               double rho, double* Q, double* R, double* S,
                               double* q, double* r, double* A, double* B,

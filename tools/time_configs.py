@@ -11,7 +11,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fbstab_b200 as fb  # noqa: E402
 
-RHO = {"servo_motor": 0.02, "double_integrator": 0.1, "spacecraft": 0.05,
+RHO = {"servo_motor": 0.02, "double_integrator": -0.1, "spacecraft": 0.05,
        "copolymerization": 0.05}
 CONFIGS = {
     "cfg2_dense32": ("dense", (32, 8, 64), 65536, 2),
