@@ -89,12 +89,23 @@ struct PendingCopy {
   const void* dev;
   size_t bytes;
 };
+struct RangeCopy {  // deferred mode: `stride` bytes per instance
+  void* dev;
+  void* host;
+  size_t stride;
+};
 
-// Resolves user pointers to device pointers, staging host memory.
+// Resolves user pointers to device pointers, staging host memory.  In deferred
+// mode (the batched solves) no copy is issued here: CopyIn / CopyOut move the
+// rows of an instance range, so that the H2D copy of chunk c+1 overlaps the
+// kernel of chunk c and the D2H copy of chunk c-1.
 struct Stager {
   cudaStream_t stream;
   bool any_host = false;
+  bool defer = false;
+  int batch = 1;
   std::vector<PendingCopy> d2h;
+  std::vector<RangeCopy> rin, rout;
   int In(DevBuf* buf, const void* user, size_t bytes, const void** out) {
     if (bytes == 0) {
       *out = nullptr;
@@ -108,7 +119,10 @@ struct Stager {
     any_host = true;
     int rc = buf->Ensure(bytes);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(buf->p, user, bytes, cudaMemcpyHostToDevice, stream));
+    if (defer)
+      rin.push_back({buf->p, const_cast<void*>(user), bytes / batch});
+    else
+      CUDA_TRY(cudaMemcpyAsync(buf->p, user, bytes, cudaMemcpyHostToDevice, stream));
     *out = buf->p;
     return FBSTAB_OK;
   }
@@ -126,10 +140,27 @@ struct Stager {
     any_host = true;
     int rc = buf->Ensure(bytes);
     if (rc) return rc;
-    if (copy_in)
-      CUDA_TRY(cudaMemcpyAsync(buf->p, user, bytes, cudaMemcpyHostToDevice, stream));
-    d2h.push_back({user, buf->p, bytes});
+    if (defer) {
+      if (copy_in) rin.push_back({buf->p, user, bytes / batch});
+      rout.push_back({buf->p, user, bytes / batch});
+    } else {
+      if (copy_in)
+        CUDA_TRY(cudaMemcpyAsync(buf->p, user, bytes, cudaMemcpyHostToDevice, stream));
+      d2h.push_back({user, buf->p, bytes});
+    }
     *out = buf->p;
+    return FBSTAB_OK;
+  }
+  int CopyIn(int lo, int n, cudaStream_t s) {
+    for (auto& c : rin)
+      CUDA_TRY(cudaMemcpyAsync((char*)c.dev + lo * c.stride, (char*)c.host + lo * c.stride,
+                               n * c.stride, cudaMemcpyHostToDevice, s));
+    return FBSTAB_OK;
+  }
+  int CopyOut(int lo, int n, cudaStream_t s) {
+    for (auto& c : rout)
+      CUDA_TRY(cudaMemcpyAsync((char*)c.host + lo * c.stride, (char*)c.dev + lo * c.stride,
+                               n * c.stride, cudaMemcpyDeviceToHost, s));
     return FBSTAB_OK;
   }
   int Finish() {
@@ -271,9 +302,19 @@ struct HandleBase {
   DevBuf comp[18];
   int last_launches = 0;
   const char* path = "generic";
+  // host-buffer pipeline: copy-in / copy-out streams and per-chunk events
+  static constexpr int kMaxChunks = 8;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
 
   void FreeAll() {
     cudaSetDevice(device);
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+    for (int i = 0; i < kMaxChunks; i++) {
+      if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+      if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+    }
     if (ws) cudaFree(ws);
     if (counter) cudaFree(counter);
     out_buf.Free();
@@ -301,6 +342,53 @@ int InitDevice(HandleBase* h, int device, int max_batch) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaMalloc(&h->counter, sizeof(int)));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < HandleBase::kMaxChunks; i++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+  }
+  return FBSTAB_OK;
+}
+
+// Runs `launch(lo, n)` over the batch.  Device-resident arguments: one launch on
+// the caller's stream, asynchronous.  Host buffers: the batch is cut into up to
+// kMaxChunks instance ranges of at least `min_chunk` instances (several waves
+// of the persistent grid each) and pipelined -- H2D of chunk c+1 on the
+// copy-in stream, kernel of chunk c on the caller's stream, D2H of chunk c-1
+// on the copy-out stream -- and the call returns when the results are in host
+// memory.
+template <class Launch>
+int RunPipelined(HandleBase* h, Stager* st, int batch, int min_chunk, Launch launch) {
+  cudaStream_t cs = st->stream;
+  if (!st->any_host) {
+    CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), cs));
+    int rc = launch(0, batch);
+    if (rc) return rc;
+    h->last_launches = 1;
+    return FBSTAB_OK;
+  }
+  int nchunk = std::max(1, std::min(HandleBase::kMaxChunks, batch / std::max(min_chunk, 1)));
+  nchunk = EnvInt("FBSTAB_PIPELINE_CHUNKS", nchunk);
+  nchunk = std::max(1, std::min(HandleBase::kMaxChunks, std::min(nchunk, batch)));
+  const int per = (batch + nchunk - 1) / nchunk;
+  int launches = 0;
+  for (int c = 0, lo = 0; lo < batch; c++, lo += per) {
+    const int n = std::min(per, batch - lo);
+    int rc = st->CopyIn(lo, n, h->s_in);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_in[c], h->s_in));
+    CUDA_TRY(cudaStreamWaitEvent(cs, h->ev_in[c], 0));
+    CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), cs));
+    if ((rc = launch(lo, n))) return rc;
+    launches++;
+    CUDA_TRY(cudaEventRecord(h->ev_k[c], cs));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+    if ((rc = st->CopyOut(lo, n, h->s_out))) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->s_out));
+  CUDA_TRY(cudaStreamSynchronize(cs));
+  h->last_launches = launches;
   return FBSTAB_OK;
 }
 
@@ -597,6 +685,8 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
   const auto t0 = std::chrono::steady_clock::now();
   Stager st;
   st.stream = (cudaStream_t)stream;
+  st.defer = true;
+  st.batch = batch;
   DenseArgs a;
   int rc = DenseStageData(h, &st, batch, H, f, G, hh, A, b, &a);
   if (rc) return rc;
@@ -609,22 +699,36 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
   if ((rc = st.InOut(&h->out_buf, out, B * sizeof(fbstab_out), false,
                      (void**)&a.c.out)))
     return rc;
-  CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
-  if (h->small.enabled) {
-    rc = fbs::DenseSmallLaunch(h->small, batch, a.H, a.f, a.G, a.h, a.A, a.b,
-                               a.c.z, a.c.l, a.c.v, a.c.y, a.c.out, h->opts, -1,
-                               nullptr, st.stream);
-    if (rc) return Fail(FBSTAB_ERR_CUDA, "dense small-path launch failed");
-  } else {
-    const int grid = std::min(batch, h->grid_max);
-    if (h->large)
-      dense_large_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
-    else
-      dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
-  }
-  CUDA_TRY(cudaGetLastError());
-  h->last_launches = 1;
-  if ((rc = st.Finish())) return rc;
+  auto launch = [&](int lo, int n) -> int {
+    DenseArgs c = a;
+    c.H += (size_t)lo * nz * nz;
+    c.f += (size_t)lo * nz;
+    c.G += (size_t)lo * nl * nz;
+    c.h += (size_t)lo * nl;
+    c.A += (size_t)lo * nv * nz;
+    c.b += (size_t)lo * nv;
+    c.c.z += (size_t)lo * nz;
+    c.c.l += (size_t)lo * nl;
+    c.c.v += (size_t)lo * nv;
+    c.c.y += (size_t)lo * nv;
+    c.c.out += lo;
+    c.c.batch = n;
+    if (h->small.enabled) {
+      if (fbs::DenseSmallLaunch(h->small, n, c.H, c.f, c.G, c.h, c.A, c.b, c.c.z, c.c.l,
+                                c.c.v, c.c.y, c.c.out, h->opts, -1, nullptr, st.stream))
+        return Fail(FBSTAB_ERR_CUDA, "dense small-path launch failed");
+    } else {
+      const int grid = std::min(n, h->grid_max);
+      if (h->large)
+        dense_large_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(c);
+      else
+        dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(c);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FBSTAB_OK;
+  };
+  const int capacity = h->small.enabled ? h->small.grid * fbs::DenseSmallWarpsPerCta() : h->grid_max;
+  if ((rc = RunPipelined(h, &st, batch, 8 * capacity, launch))) return rc;
   if (st.any_host && !IsDevicePtr(out)) {
     const double sec =
         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -763,6 +867,8 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
   const auto t0 = std::chrono::steady_clock::now();
   Stager st;
   st.stream = (cudaStream_t)stream;
+  st.defer = true;
+  st.batch = batch;
   fbs::MpcData a;
   const double* user[12] = {Q, R, S, q, r, A, B, c, E, L, d, x0};
   int rc = MpcStageData(h, &st, batch, user, &a);
@@ -776,13 +882,28 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
   if ((rc = st.InOut(&h->io[3], y, Bn * nv * D, false, (void**)&dy))) return rc;
   if ((rc = st.InOut(&h->out_buf, out, Bn * sizeof(fbstab_out), false, (void**)&dout)))
     return rc;
-  CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
-  if (fbs::MpcLaunch(h->plan, batch, a, dz, dl, dv, dy, dout, h->opts, -1, nullptr,
-                     h->counter, st.stream))
-    return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
-  CUDA_TRY(cudaGetLastError());
-  h->last_launches = 1;
-  if ((rc = st.Finish())) return rc;
+  auto launch = [&](int lo, int n) -> int {
+    const size_t N = h->N, nx = h->nx, nu = h->nu, nc = h->nc, K = N + 1, o = lo;
+    fbs::MpcData c = a;
+    c.Q += o * K * nx * nx;
+    c.R += o * K * nu * nu;
+    c.S += o * K * nu * nx;
+    c.q += o * K * nx;
+    c.r += o * K * nu;
+    c.A += o * N * nx * nx;
+    c.B += o * N * nx * nu;
+    c.c += o * N * nx;
+    c.E += o * K * nc * nx;
+    c.L += o * K * nc * nu;
+    c.d += o * K * nc;
+    c.x0 += o * nx;
+    if (fbs::MpcLaunch(h->plan, n, c, dz + o * nz, dl + o * nl, dv + o * nv, dy + o * nv,
+                       dout + lo, h->opts, -1, nullptr, h->counter, st.stream))
+      return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
+    CUDA_TRY(cudaGetLastError());
+    return FBSTAB_OK;
+  };
+  if ((rc = RunPipelined(h, &st, batch, 8 * h->plan.grid_max, launch))) return rc;
   if (st.any_host && !IsDevicePtr(out)) {
     const double sec =
         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

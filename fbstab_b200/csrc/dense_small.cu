@@ -909,6 +909,8 @@ dense_small_kernel(const __grid_constant__ Args a) {
 
 }  // namespace small
 
+int DenseSmallWarpsPerCta() { return small::kWarps; }
+
 int DenseSmallInit(DenseSmallPlan* p, int nz, int nl, int nv, int sm_count,
                    int* counter) {
   p->enabled = false;

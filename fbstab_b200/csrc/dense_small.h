@@ -16,6 +16,8 @@ struct DenseSmallPlan {
   size_t smem = 0;
 };
 
+// Instances in flight per CTA of the warp kernel.
+int DenseSmallWarpsPerCta();
 // Enables the plan when (nz,nl,nv) fits the warp kernel; returns 0.
 int DenseSmallInit(DenseSmallPlan* p, int nz, int nl, int nv, int sm_count,
                    int* counter);
