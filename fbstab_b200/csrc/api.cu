@@ -22,6 +22,7 @@
 #include "engine.cuh"
 #include "engine_args.cuh"
 #include "fbstab_b200.h"
+#include "mpc_lane.h"
 #include "mpc_riccati.h"
 
 namespace {
@@ -444,6 +445,11 @@ struct fbstab_dense_batch : HandleBase {
 struct fbstab_mpc_batch : HandleBase {
   int N = 0, nx = 0, nu = 0, nc = 0;
   fbs::MpcPlan plan;
+  // lane-per-instance path (small stages, large batches)
+  double* lane_ws = nullptr;
+  int lane_warps = 0;
+  int lane_min = 0;
+  char lane_name[160];
 };
 
 namespace {
@@ -807,6 +813,25 @@ int fbstab_mpc_batch_create(int N, int nx, int nu, int nc, int max_batch,
     return rc;
   }
   h->path = h->plan.name;
+  // Small stages: one LANE per instance once the batch fills the machine.
+  h->lane_min = EnvInt("FBSTAB_MPC_LANE_MIN", 256);
+  if (fbs::MpcLaneSupported(nx, nu, nc) && EnvInt("FBSTAB_MPC_LANE", 1) &&
+      max_batch >= h->lane_min) {
+    const int warps = std::min((max_batch + 31) / 32,
+                               h->sm_count * EnvInt("FBSTAB_MPC_LANE_WARPS_PER_SM", 8));
+    const size_t bytes = (size_t)warps * fbs::MpcLaneWsDoublesPerWarp(N, nx, nu, nc) * 8;
+    if (cudaMalloc(&h->lane_ws, bytes) == cudaSuccess) {
+      h->lane_warps = warps;
+      snprintf(h->lane_name, sizeof(h->lane_name),
+               "mpc-lane<nx,nu,nc> (lane per instance, %d warps, %.0f MB interleaved "
+               "workspace; batches < %d: %s)",
+               warps, bytes / 1e6, h->lane_min, "mpc-riccati-cta");
+      h->path = h->lane_name;
+    } else {
+      cudaGetLastError();
+      h->lane_ws = nullptr;
+    }
+  }
   *handle = h;
   return FBSTAB_OK;
 }
@@ -815,6 +840,7 @@ int fbstab_mpc_batch_destroy(fbstab_mpc_batch* h) {
   if (!h) return FBSTAB_OK;
   cudaSetDevice(h->device);
   fbs::MpcPlanFree(&h->plan);
+  if (h->lane_ws) cudaFree(h->lane_ws);
   h->FreeAll();
   delete h;
   return FBSTAB_OK;
@@ -897,13 +923,20 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
     c.L += o * K * nc * nu;
     c.d += o * K * nc;
     c.x0 += o * nx;
-    if (fbs::MpcLaunch(h->plan, n, c, dz + o * nz, dl + o * nl, dv + o * nv, dy + o * nv,
-                       dout + lo, h->opts, -1, nullptr, h->counter, st.stream))
+    const bool lane = h->lane_ws && n >= h->lane_min;
+    if (lane ? fbs::MpcLaneLaunch(h->N, h->nx, h->nu, h->nc, n, h->lane_warps, c, dz + o * nz,
+                                  dl + o * nl, dv + o * nv, dy + o * nv, dout + lo, h->opts,
+                                  h->lane_ws, h->counter, st.stream)
+             : fbs::MpcLaunch(h->plan, n, c, dz + o * nz, dl + o * nl, dv + o * nv,
+                              dy + o * nv, dout + lo, h->opts, -1, nullptr, h->counter,
+                              st.stream))
       return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
     CUDA_TRY(cudaGetLastError());
     return FBSTAB_OK;
   };
-  if ((rc = RunPipelined(h, &st, batch, 8 * h->plan.grid_max, launch))) return rc;
+  if ((rc = RunPipelined(h, &st, batch, h->lane_ws ? 8 * 32 * h->lane_warps : 8 * h->plan.grid_max,
+                         launch)))
+    return rc;
   if (st.any_host && !IsDevicePtr(out)) {
     const double sec =
         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

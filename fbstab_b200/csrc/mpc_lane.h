@@ -1,0 +1,22 @@
+// mpc_lane.h -- host interface of the lane-per-instance MPC path (mpc_lane.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "fbstab_b200.h"
+#include "mpc_riccati.h"
+
+namespace fbs {
+
+// True when (nx,nu,nc) has a compile-time instantiation of the lane kernel.
+bool MpcLaneSupported(int nx, int nu, int nc);
+// Lane-interleaved workspace of one warp (32 instances), in doubles.
+size_t MpcLaneWsDoublesPerWarp(int N, int nx, int nu, int nc);
+// Launches min(max_warps, ceil(batch/32)) single-warp CTAs; `ws` holds
+// max_warps * MpcLaneWsDoublesPerWarp doubles.  Returns 0 on success.
+int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps,
+                  const MpcData& data, double* z, double* l, double* v, double* y,
+                  fbstab_out* out, const fbstab_options& opts, double* ws, int* counter,
+                  cudaStream_t stream);
+
+}  // namespace fbs

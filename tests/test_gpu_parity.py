@@ -356,6 +356,41 @@ def test_mpc_batch_parity(fb, oracle, kind, N, B, rho):
         assert rel_err(Z[i], OZ[i]) <= tol, (i, rel_err(Z[i], OZ[i]), same[i])
 
 
+@pytest.mark.parametrize("kind,N,B,rho", [("servo_motor", 50, 512, 0.02),
+                                         ("double_integrator", 50, 512, -0.1),
+                                         ("double_integrator", 12, 320, 0.6),
+                                         ("servo_motor", 7, 257, 0.3)])
+def test_mpc_lane_path_parity(fb, oracle, kind, N, B, rho):
+    """The lane-per-instance kernel (mpc_lane.cu: small stages, batches >= 256)
+    against the oracle, including batches that mix converged and infeasible
+    instances and a batch size that leaves lanes of the last warp idle."""
+    dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=rho)
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    assert s.path.startswith("mpc-lane"), s.path
+    z, l, v = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, oz, ol, ov, oy = oracle.mpc_solve_batch(
+        *dims, [d[k] for k in fb.problems.MPC_FIELDS], nthreads=8)
+    assert (out["status"] == 0).all()
+    assert (out["eflag"] == oo["eflag"]).all(), (out["eflag"], oo["eflag"])
+    same = _same_traj(out, oo)
+    assert same.mean() >= 0.85, f"trajectory differs on {(~same).sum()} of {B}"
+    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 3
+    Z, OZ = z.reshape(B, -1), oz.reshape(B, -1)
+    Y, OY = y.reshape(B, -1), oy.reshape(B, -1)
+    for i in np.nonzero(out["eflag"] == 0)[0]:
+        tol = SOL_TOL if same[i] else 1e-4
+        assert rel_err(Z[i], OZ[i]) <= tol, (i, rel_err(Z[i], OZ[i]), same[i])
+        assert rel_err(Y[i], OY[i]) <= tol * 10
+    # a small batch of the same problem runs the CTA kernel: same answers
+    nb = 8
+    dsm = {k: a[:nb * (a.size // B)].copy() for k, a in d.items()}
+    z2, l2, v2 = np.zeros(nb * s.nz), np.zeros(nb * s.nl), np.zeros(nb * s.nv)
+    out2, _ = s.solve_batch(dsm, z2, l2, v2)
+    assert (out2["eflag"] == out["eflag"][:nb]).all()
+    assert np.abs(out2["newton_iters"] - out["newton_iters"][:nb]).max() <= 2
+
+
 def test_mpc_maxiter_matches_reference_behaviour(fb, oracle):
     """Spacecraft N=100 with default options runs into the Newton cap in the
     reference algorithm (SURVEY.md 8(d) open issue): the engine must report
