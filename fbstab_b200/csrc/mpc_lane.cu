@@ -121,19 +121,48 @@ struct Lane {
   // factor block of a stage: lower L | lower M | AM | SM | P | lower SG
   static constexpr int oL = 0, oM = TX, oAM = 2 * TX, oSM = oAM + NX * NX,
                        oP = oSM + NU * NX, oSG = oP + NX * NU, FS = oSG + TU;
+  // STAGE-MAJOR workspace: everything stage i needs is one contiguous block
+  //   [ xk: z l v y | xi: z l v y | dx: z l v y | ri: z l v | gamma mu | factor ]
+  // (element e of lane j at ws[e*32 + j]); a sweep touches consecutive blocks,
+  // so the next block is prefetched into L2 while the current one is computed.
+  static constexpr int V_Z = 0, V_L = NS, V_V = NS + NX, V_Y = NS + NX + NC,
+                       VSZ = NS + NX + 2 * NC;
+  static constexpr int O_XK = 0, O_XI = VSZ, O_DX = 2 * VSZ, O_RI = 3 * VSZ;
+  static constexpr int R_Z = 0, R_L = NS, R_V = NS + NX, RSZ = NS + NX + NC;
+  static constexpr int O_GM = O_RI + RSZ, O_FAC = O_GM + 2 * NC, O_DAT = O_FAC + FS;
+  // ... | the stage's problem data, transposed once from the instance-major wire
+  // format so that every later read is a coalesced, prefetchable access:
+  //   Q | R | S | q | r | A | B | c | E | L | d
+  static constexpr int D_Q = O_DAT, D_R = D_Q + NX * NX, D_S = D_R + NU * NU,
+                       D_q = D_S + NU * NX, D_r = D_q + NX, D_A = D_r + NU,
+                       D_B = D_A + NX * NX, D_c = D_B + NX * NU, D_E = D_c + NX,
+                       D_L = D_E + NC * NX, D_d = D_L + NC * NU, SB = D_d + NC;
 
   int N, nz, nl, nv;
   double* ws;  // this lane's column of the interleaved workspace
-  int o_xk, o_xi, o_dx, o_ri, o_gm, o_fac;
   const double *Q, *R, *S, *q, *r, *A, *B, *c, *E, *L, *d, *x0;
 
-  __device__ __forceinline__ double ld(int e) const { return ws[(size_t)e * 32]; }
-  __device__ __forceinline__ void st(int e, double v) const { ws[(size_t)e * 32] = v; }
-  // Vars block layout: z | l | v | y
-  __device__ __forceinline__ int zo(int base, int i) const { return base + i * NS; }
-  __device__ __forceinline__ int lo(int base, int i) const { return base + nz + i * NX; }
-  __device__ __forceinline__ int vo(int base, int i) const { return base + nz + nl + i * NC; }
-  __device__ __forceinline__ int yo(int base, int i) const { return base + nz + nl + nv + i * NC; }
+  // element `o` of stage i's block
+  __device__ __forceinline__ double ld(int i, int o) const {
+    return ws[((size_t)i * SB + o) * 32];
+  }
+  __device__ __forceinline__ void st(int i, int o, double v) const {
+    ws[((size_t)i * SB + o) * 32] = v;
+  }
+  // address of element `o` of stage i's block (stride 32 doubles between elements)
+  __device__ __forceinline__ const double* dat(int i, int o) const {
+    return ws + ((size_t)i * SB + o) * 32;
+  }
+  // L2 prefetch of elements [o0, o1) of stage i's block: the warp's 32 lanes
+  // cover the (o1-o0)*256 bytes line by line
+  __device__ __forceinline__ void prefetch(int i, int o0, int o1) const {
+    if (i < 0 || i > N) return;
+    const int lane = threadIdx.x & 31;
+    const char* base = (const char*)(ws - lane) + ((size_t)i * SB + o0) * 256;
+    const int lines = (o1 - o0) * 2;
+    for (int m = lane; m < lines; m += 32)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)m * 128));
+  }
 
   __device__ void bind(const LaneArgs& a, int inst) {
     const size_t i = (size_t)inst, K = N + 1;
@@ -151,44 +180,45 @@ struct Lane {
     x0 = a.data.x0 + i * NX;
   }
 
-  __device__ __forceinline__ void load_lower(int e, double (&M)[NX][NX]) const {
+  // packed lower triangles <-> register matrices (t = FS-sized register copy)
+  __device__ __forceinline__ static void unpack_x(const double* t, double (&M)[NX][NX]) {
     int k = 0;
 #pragma unroll
     for (int cc = 0; cc < NX; cc++)
 #pragma unroll
-      for (int rr = cc; rr < NX; rr++) M[rr][cc] = ld(e + k++);
+      for (int rr = cc; rr < NX; rr++) M[rr][cc] = t[k++];
   }
-  __device__ __forceinline__ void store_lower(int e, const double (&M)[NX][NX]) const {
+  __device__ __forceinline__ static void unpack_u(const double* t, double (&M)[NU][NU]) {
+    int k = 0;
+#pragma unroll
+    for (int cc = 0; cc < NU; cc++)
+#pragma unroll
+      for (int rr = cc; rr < NU; rr++) M[rr][cc] = t[k++];
+  }
+  __device__ __forceinline__ void store_lower(int i, int o, const double (&M)[NX][NX]) const {
     int k = 0;
 #pragma unroll
     for (int cc = 0; cc < NX; cc++)
 #pragma unroll
-      for (int rr = cc; rr < NX; rr++) st(e + k++, M[rr][cc]);
+      for (int rr = cc; rr < NX; rr++) st(i, o + k++, M[rr][cc]);
   }
-  __device__ __forceinline__ void load_lower_u(int e, double (&M)[NU][NU]) const {
+  __device__ __forceinline__ void store_lower_u(int i, int o, const double (&M)[NU][NU]) const {
     int k = 0;
 #pragma unroll
     for (int cc = 0; cc < NU; cc++)
 #pragma unroll
-      for (int rr = cc; rr < NU; rr++) M[rr][cc] = ld(e + k++);
-  }
-  __device__ __forceinline__ void store_lower_u(int e, const double (&M)[NU][NU]) const {
-    int k = 0;
-#pragma unroll
-    for (int cc = 0; cc < NU; cc++)
-#pragma unroll
-      for (int rr = cc; rr < NU; rr++) st(e + k++, M[rr][cc]);
+      for (int rr = cc; rr < NU; rr++) st(i, o + k++, M[rr][cc]);
   }
 
   // (E(i) x + L(i) u)[k], mpc_data.cc:66-105
   __device__ __forceinline__ double Az_entry(const double (&z)[NS], int i, int k) const {
-    const double* Em = E + (size_t)i * NC * NX;
-    const double* Lm = L + (size_t)i * NC * NU;
+    const double* Em = dat(i, D_E);
+    const double* Lm = dat(i, D_L);
     double s = 0.0, s2 = 0.0;
 #pragma unroll
-    for (int cc = 0; cc < NX; cc++) s = fma(__ldg(Em + k + cc * NC), z[cc], s);
+    for (int cc = 0; cc < NX; cc++) s = fma(Em[(k + cc * NC) * 32], z[cc], s);
 #pragma unroll
-    for (int cc = 0; cc < NU; cc++) s2 = fma(__ldg(Lm + k + cc * NC), z[NX + cc], s2);
+    for (int cc = 0; cc < NU; cc++) s2 = fma(Lm[(k + cc * NC) * 32], z[NX + cc], s2);
     return s + s2;
   }
 
@@ -196,18 +226,32 @@ struct Lane {
   __device__ double init(const double* z0, const double* l0, const double* v0) {
     double fn = 0.0;
     for (int i = 0; i <= N; i++) {
-      double z[NS];
+      // stage data: instance-major wire format -> this lane's workspace column
+      {
+        const double* src[11] = {Q + (size_t)i * NX * NX, R + (size_t)i * NU * NU,
+                                 S + (size_t)i * NU * NX, q + (size_t)i * NX,
+                                 r + (size_t)i * NU,      A + (size_t)i * NX * NX,
+                                 B + (size_t)i * NX * NU, c + (size_t)i * NX,
+                                 E + (size_t)i * NC * NX, L + (size_t)i * NC * NU,
+                                 d + (size_t)i * NC};
+        const int off[11] = {D_Q, D_R, D_S, D_q, D_r, D_A, D_B, D_c, D_E, D_L, D_d};
+        const int cnt[11] = {NX * NX, NU * NU, NU * NX, NX, NU, NX * NX, NX * NU, NX,
+                             NC * NX, NC * NU, NC};
 #pragma unroll
-      for (int k = 0; k < NS; k++) {
-        z[k] = z0[i * NS + k];
-        st(zo(o_xk, i) + k, z[k]);
-        st(zo(o_xi, i) + k, z[k]);
+        for (int a_ = 0; a_ < 11; a_++) {
+          const bool stage_only = (a_ == 5 || a_ == 6 || a_ == 7);  // A, B, c: N entries
+          if (!stage_only || i < N) {
+#pragma unroll
+            for (int k = 0; k < cnt[a_]; k++) st(i, off[a_] + k, __ldg(src[a_] + k));
+          }
+        }
       }
+      double z[NS], lv[NX], vv[NC], yv[NC];
+#pragma unroll
+      for (int k = 0; k < NS; k++) z[k] = z0[i * NS + k];
 #pragma unroll
       for (int k = 0; k < NX; k++) {
-        const double lv = l0[i * NX + k];
-        st(lo(o_xk, i) + k, lv);
-        st(lo(o_xi, i) + k, lv);
+        lv[k] = l0[i * NX + k];
         const double qv = __ldg(q + i * NX + k);
         fn = fma(qv, qv, fn);
         if (i < N) {
@@ -222,14 +266,23 @@ struct Lane {
       }
 #pragma unroll
       for (int k = 0; k < NC; k++) {
-        const double vv = v0[i * NC + k];
+        vv[k] = v0[i * NC + k];
         const double dv = __ldg(d + i * NC + k);
         fn = fma(dv, dv, fn);
-        const double yv = -dv - Az_entry(z, i, k);
-        st(vo(o_xk, i) + k, vv);
-        st(vo(o_xi, i) + k, vv);
-        st(yo(o_xk, i) + k, yv);
-        st(yo(o_xi, i) + k, yv);
+        yv[k] = -dv - Az_entry(z, i, k);
+      }
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int o = b ? O_XI : O_XK;
+#pragma unroll
+        for (int k = 0; k < NS; k++) st(i, o + V_Z + k, z[k]);
+#pragma unroll
+        for (int k = 0; k < NX; k++) st(i, o + V_L + k, lv[k]);
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+          st(i, o + V_V + k, vv[k]);
+          st(i, o + V_Y + k, yv[k]);
+        }
       }
     }
 #pragma unroll
@@ -238,88 +291,110 @@ struct Lane {
   }
 
   // Fused residual evaluation at x = base (+ t dx when trial): inner residual
-  // wrt xbar = xk (or wrt x itself when self_bar) -> ri, both norms.
+  // wrt xbar = xk (or wrt x itself when self_bar) -> ri, both norms.  Every
+  // load of a stage is issued before its first store (the compiler cannot
+  // move a load across a store to the same array, and each exposed load is a
+  // DRAM round trip).
   __device__ EvalOut evaluate(int base, bool trial, double t, bool self_bar, double sigma,
                               double alpha) {
     const double sg = self_bar ? 0.0 : sigma;
     double s[6] = {0, 0, 0, 0, 0, 0};
     double zp[NS], lc[NX], ln[NX];  // z(i-1), l(i), l(i+1)
-    auto get = [&](int off_base, int off_dx) {
-      double v = ld(off_base);
-      if (trial) v = fma(t, ld(off_dx), v);
-      return v;
-    };
 #pragma unroll
-    for (int k = 0; k < NX; k++) lc[k] = get(lo(base, 0) + k, lo(o_dx, 0) + k);
+    for (int k = 0; k < NX; k++) {
+      const double a0 = ld(0, base + V_L + k), b0 = ld(0, O_DX + V_L + k);
+      lc[k] = trial ? fma(t, b0, a0) : a0;
+      ln[k] = 0.0;
+    }
 #pragma unroll
     for (int k = 0; k < NS; k++) zp[k] = 0.0;
     for (int i = 0; i <= N; i++) {
+      prefetch(i + 1, 0, O_RI);
+      prefetch(i + 1, O_DAT, SB);
+      double xb[VSZ], xd[VSZ], zk[NS], lk[NX], vk[NC], la[NX], lb[NX];
+#pragma unroll
+      for (int k = 0; k < VSZ; k++) {
+        xb[k] = ld(i, base + k);
+        xd[k] = ld(i, O_DX + k);
+      }
+#pragma unroll
+      for (int k = 0; k < NS; k++) zk[k] = ld(i, O_XK + V_Z + k);
+#pragma unroll
+      for (int k = 0; k < NX; k++) lk[k] = ld(i, O_XK + V_L + k);
+#pragma unroll
+      for (int k = 0; k < NC; k++) vk[k] = ld(i, O_XK + V_V + k);
+      if (i < N) {
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+          la[k] = ld(i + 1, base + V_L + k);
+          lb[k] = ld(i + 1, O_DX + V_L + k);
+        }
+      }
       double z[NS], v[NC], y[NC];
 #pragma unroll
-      for (int k = 0; k < NS; k++) z[k] = get(zo(base, i) + k, zo(o_dx, i) + k);
+      for (int k = 0; k < NS; k++) z[k] = trial ? fma(t, xd[V_Z + k], xb[V_Z + k]) : xb[V_Z + k];
 #pragma unroll
       for (int k = 0; k < NC; k++) {
-        v[k] = get(vo(base, i) + k, vo(o_dx, i) + k);
-        double yv = ld(yo(base, i) + k);
-        if (trial) {  // y-aware axpy, full_variable.cc:55-65
-          yv = fma(t, ld(yo(o_dx, i) + k), yv);
-          yv = fma(-t, -__ldg(d + i * NC + k), yv);
-        }
-        y[k] = yv;
+        v[k] = trial ? fma(t, xd[V_V + k], xb[V_V + k]) : xb[V_V + k];
+        // y-aware axpy, full_variable.cc:55-65
+        const double y1 = fma(t, xd[V_Y + k], xb[V_Y + k]);
+        const double y2 = fma(-t, -dat(i, D_d)[k * 32], y1);
+        y[k] = trial ? y2 : xb[V_Y + k];
       }
       if (i < N) {
 #pragma unroll
-        for (int k = 0; k < NX; k++) ln[k] = get(lo(base, i + 1) + k, lo(o_dx, i + 1) + k);
+        for (int k = 0; k < NX; k++) ln[k] = trial ? fma(t, lb[k], la[k]) : la[k];
       }
-      const double* Qm = Q + (size_t)i * NX * NX;
-      const double* Rm = R + (size_t)i * NU * NU;
-      const double* Sm = S + (size_t)i * NU * NX;
-      const double* Em = E + (size_t)i * NC * NX;
-      const double* Lm = L + (size_t)i * NC * NU;
-      const double* Am = A + (size_t)i * NX * NX;
-      const double* Bm = B + (size_t)i * NX * NU;
+      const double* Qm = dat(i, D_Q);
+      const double* Rm = dat(i, D_R);
+      const double* Sm = dat(i, D_S);
+      const double* Em = dat(i, D_E);
+      const double* Lm = dat(i, D_L);
+      const double* Am = dat(i, D_A);
+      const double* Bm = dat(i, D_B);
+      double out[RSZ];
       // z block: tz = ((f + Hz) + G'l) + A'v
 #pragma unroll
       for (int rr = 0; rr < NS; rr++) {
         double s1 = 0.0, s2 = 0.0, tz;
         if (rr < NX) {
 #pragma unroll
-          for (int cc = 0; cc < NX; cc++) s1 = fma(__ldg(Qm + rr + cc * NX), z[cc], s1);
+          for (int cc = 0; cc < NX; cc++) s1 = fma(Qm[(rr + cc * NX) * 32], z[cc], s1);
 #pragma unroll
-          for (int cc = 0; cc < NU; cc++) s2 = fma(__ldg(Sm + cc + rr * NU), z[NX + cc], s2);
-          tz = __ldg(q + i * NX + rr) + (s1 + s2);
+          for (int cc = 0; cc < NU; cc++) s2 = fma(Sm[(cc + rr * NU) * 32], z[NX + cc], s2);
+          tz = dat(i, D_q)[rr * 32] + (s1 + s2);
           tz += -lc[rr];
           if (i < N) {
             double sa = 0.0;
 #pragma unroll
-            for (int cc = 0; cc < NX; cc++) sa = fma(__ldg(Am + cc + rr * NX), ln[cc], sa);
+            for (int cc = 0; cc < NX; cc++) sa = fma(Am[(cc + rr * NX) * 32], ln[cc], sa);
             tz += sa;
           }
           double sv = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; k++) sv = fma(__ldg(Em + k + rr * NC), v[k], sv);
+          for (int k = 0; k < NC; k++) sv = fma(Em[(k + rr * NC) * 32], v[k], sv);
           tz += sv;
         } else {
           const int ru = rr - NX;
 #pragma unroll
-          for (int cc = 0; cc < NX; cc++) s1 = fma(__ldg(Sm + ru + cc * NU), z[cc], s1);
+          for (int cc = 0; cc < NX; cc++) s1 = fma(Sm[(ru + cc * NU) * 32], z[cc], s1);
 #pragma unroll
-          for (int cc = 0; cc < NU; cc++) s2 = fma(__ldg(Rm + ru + cc * NU), z[NX + cc], s2);
-          tz = __ldg(r + i * NU + ru) + (s1 + s2);
+          for (int cc = 0; cc < NU; cc++) s2 = fma(Rm[(ru + cc * NU) * 32], z[NX + cc], s2);
+          tz = dat(i, D_r)[ru * 32] + (s1 + s2);
           if (i < N) {
             double sa = 0.0;
 #pragma unroll
-            for (int cc = 0; cc < NX; cc++) sa = fma(__ldg(Bm + cc + ru * NX), ln[cc], sa);
+            for (int cc = 0; cc < NX; cc++) sa = fma(Bm[(cc + ru * NX) * 32], ln[cc], sa);
             tz += sa;
           }
           double sv = 0.0;
 #pragma unroll
-          for (int k = 0; k < NC; k++) sv = fma(__ldg(Lm + k + ru * NC), v[k], sv);
+          for (int k = 0; k < NC; k++) sv = fma(Lm[(k + ru * NC) * 32], v[k], sv);
           tz += sv;
         }
         s[3] = fma(tz, tz, s[3]);
-        const double rr_ = tz + sg * (z[rr] - ld(zo(o_xk, i) + rr));
-        st(o_ri + i * NS + rr, rr_);
+        const double rr_ = tz + sg * (z[rr] - zk[rr]);
+        out[R_Z + rr] = rr_;
         s[0] = fma(rr_, rr_, s[0]);
       }
       // l block: tl = h - Gz
@@ -329,30 +404,32 @@ struct Lane {
         if (i == 0) {
           tl = -__ldg(x0 + rr) + z[rr];
         } else {
-          const double* Ap = A + (size_t)(i - 1) * NX * NX;
-          const double* Bp = B + (size_t)(i - 1) * NX * NU;
+          const double* Ap = dat(i - 1, D_A);
+          const double* Bp = dat(i - 1, D_B);
           double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-          for (int cc = 0; cc < NX; cc++) s1 = fma(__ldg(Ap + rr + cc * NX), zp[cc], s1);
+          for (int cc = 0; cc < NX; cc++) s1 = fma(Ap[(rr + cc * NX) * 32], zp[cc], s1);
 #pragma unroll
-          for (int cc = 0; cc < NU; cc++) s2 = fma(__ldg(Bp + rr + cc * NX), zp[NX + cc], s2);
-          tl = (-__ldg(c + (size_t)(i - 1) * NX + rr) - (s1 + s2)) + z[rr];
+          for (int cc = 0; cc < NU; cc++) s2 = fma(Bp[(rr + cc * NX) * 32], zp[NX + cc], s2);
+          tl = (-dat(i - 1, D_c)[rr * 32] - (s1 + s2)) + z[rr];
         }
         s[4] = fma(tl, tl, s[4]);
-        const double rl = tl + sg * (lc[rr] - ld(lo(o_xk, i) + rr));
-        st(o_ri + nz + i * NX + rr, rl);
+        const double rl = tl + sg * (lc[rr] - lk[rr]);
+        out[R_L + rr] = rl;
         s[1] = fma(rl, rl, s[1]);
       }
       // v block
 #pragma unroll
       for (int k = 0; k < NC; k++) {
-        const double ys = y[k] + sg * (v[k] - ld(vo(o_xk, i) + k));
+        const double ys = y[k] + sg * (v[k] - vk[k]);
         const double rv = pfb(ys, v[k], alpha);
-        st(o_ri + nz + nl + i * NC + k, rv);
+        out[R_V + k] = rv;
         s[2] = fma(rv, rv, s[2]);
         const double nn = pnr(y[k], v[k], alpha);
         s[5] = fma(nn, nn, s[5]);
       }
+#pragma unroll
+      for (int k = 0; k < RSZ; k++) st(i, O_RI + k, out[k]);
 #pragma unroll
       for (int k = 0; k < NS; k++) zp[k] = z[k];
 #pragma unroll
@@ -369,19 +446,23 @@ struct Lane {
   // xi <- xi + t dx (same fused multiply-adds as the trial evaluation)
   __device__ void commit(double t) {
     for (int i = 0; i <= N; i++) {
+      prefetch(i + 1, O_XI, O_RI);
+      prefetch(i + 1, D_d, SB);
+      double xb[VSZ], xd[VSZ];
 #pragma unroll
-      for (int k = 0; k < NS; k++)
-        st(zo(o_xi, i) + k, fma(t, ld(zo(o_dx, i) + k), ld(zo(o_xi, i) + k)));
+      for (int k = 0; k < VSZ; k++) {
+        xb[k] = ld(i, O_XI + k);
+        xd[k] = ld(i, O_DX + k);
+      }
 #pragma unroll
-      for (int k = 0; k < NX; k++)
-        st(lo(o_xi, i) + k, fma(t, ld(lo(o_dx, i) + k), ld(lo(o_xi, i) + k)));
+      for (int k = 0; k < V_Y; k++) xb[k] = fma(t, xd[k], xb[k]);
 #pragma unroll
       for (int k = 0; k < NC; k++) {
-        st(vo(o_xi, i) + k, fma(t, ld(vo(o_dx, i) + k), ld(vo(o_xi, i) + k)));
-        double yv = fma(t, ld(yo(o_dx, i) + k), ld(yo(o_xi, i) + k));
-        yv = fma(-t, -__ldg(d + i * NC + k), yv);
-        st(yo(o_xi, i) + k, yv);
+        const double y1 = fma(t, xd[V_Y + k], xb[V_Y + k]);
+        xb[V_Y + k] = fma(-t, -dat(i, D_d)[k * 32], y1);
       }
+#pragma unroll
+      for (int k = 0; k < VSZ; k++) st(i, O_XI + k, xb[k]);
     }
   }
 
@@ -395,31 +476,38 @@ struct Lane {
 #pragma unroll
       for (int b_ = 0; b_ < NX; b_++) Lc[a_][b_] = (a_ == b_) ? rs : 0.0;
     for (int i = 0; i <= N; i++) {
-      const int fb = o_fac + i * FS;
-      store_lower(fb + oL, Lc);
+      prefetch(i + 1, O_XK + V_V, O_DX);
+      prefetch(i + 1, O_DAT, SB);
+      double yv[NC], vv[NC], vk[NC];
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        yv[k] = ld(i, O_XI + V_Y + k);
+        vv[k] = ld(i, O_XI + V_V + k);
+        vk[k] = ld(i, O_XK + V_V + k);
+      }
+      store_lower(i, O_FAC + oL, Lc);
       double Gam[NC];
 #pragma unroll
       for (int k = 0; k < NC; k++) {
-        const double yv = ld(yo(o_xi, i) + k), vv = ld(vo(o_xi, i) + k);
-        const double ys = yv + sigma * (vv - ld(vo(o_xk, i) + k));
+        const double ys = yv[k] + sigma * (vv[k] - vk[k]);
         double ga, mu;
-        pfb_barrier(ys, vv, alpha, sigma, &ga, &mu);
-        st(o_gm + i * NC + k, ga);
-        st(o_gm + nv + i * NC + k, mu);
+        pfb_barrier(ys, vv[k], alpha, sigma, &ga, &mu);
+        st(i, O_GM + k, ga);
+        st(i, O_GM + NC + k, mu);
         Gam[k] = ga / mu;
       }
-      const double* Qm = Q + (size_t)i * NX * NX;
-      const double* Rm = R + (size_t)i * NU * NU;
-      const double* Sm = S + (size_t)i * NU * NX;
-      const double* Em = E + (size_t)i * NC * NX;
-      const double* Lm = L + (size_t)i * NC * NU;
+      const double* Qm = dat(i, D_Q);
+      const double* Rm = dat(i, D_R);
+      const double* Sm = dat(i, D_S);
+      const double* Em = dat(i, D_E);
+      const double* Lm = dat(i, D_L);
       double Ee[NC][NX], Le[NC][NU];
 #pragma unroll
       for (int k = 0; k < NC; k++) {
 #pragma unroll
-        for (int cc = 0; cc < NX; cc++) Ee[k][cc] = __ldg(Em + k + cc * NC);
+        for (int cc = 0; cc < NX; cc++) Ee[k][cc] = Em[(k + cc * NC) * 32];
 #pragma unroll
-        for (int cc = 0; cc < NU; cc++) Le[k][cc] = __ldg(Lm + k + cc * NC);
+        for (int cc = 0; cc < NU; cc++) Le[k][cc] = Lm[(k + cc * NC) * 32];
       }
       // Linv = inv(L L'), column by column (:142-144)
       double Mm[NX][NX];
@@ -453,11 +541,11 @@ struct Lane {
           double sv = 0.0;
 #pragma unroll
           for (int k = 0; k < NC; k++) sv = fma(Ee[k][rr], Gam[k] * Ee[k][cc], sv);
-          const double qt = (__ldg(Qm + rr + cc * NX) + (rr == cc ? sigma : 0.0)) + sv;
+          const double qt = (Qm[(rr + cc * NX) * 32] + (rr == cc ? sigma : 0.0)) + sv;
           Mm[rr][cc] = qt + Mm[rr][cc];
         }
       ok = chol<NX>(Mm) && ok;
-      store_lower(fb + oM, Mm);
+      store_lower(i, O_FAC + oM, Mm);
       // R~, S~
       double Rt[NU][NU], St[NU][NX];
 #pragma unroll
@@ -467,7 +555,7 @@ struct Lane {
           double sv = 0.0;
 #pragma unroll
           for (int k = 0; k < NC; k++) sv = fma(Le[k][rr], Gam[k] * Le[k][cc], sv);
-          Rt[rr][cc] = (__ldg(Rm + rr + cc * NU) + (rr == cc ? sigma : 0.0)) + sv;
+          Rt[rr][cc] = (Rm[(rr + cc * NU) * 32] + (rr == cc ? sigma : 0.0)) + sv;
         }
 #pragma unroll
       for (int cc = 0; cc < NX; cc++)
@@ -476,30 +564,30 @@ struct Lane {
           double sv = 0.0;
 #pragma unroll
           for (int k = 0; k < NC; k++) sv = fma(Le[k][rr], Gam[k] * Ee[k][cc], sv);
-          St[rr][cc] = __ldg(Sm + rr + cc * NU) + sv;
+          St[rr][cc] = Sm[(rr + cc * NU) * 32] + sv;
         }
       // AM = A M^-T, SM = S~ M^-T (:149-161)
       double AM[NX][NX], SM[NU][NX];
       if (i < N) {
-        const double* Am = A + (size_t)i * NX * NX;
+        const double* Am = dat(i, D_A);
 #pragma unroll
         for (int rr = 0; rr < NX; rr++) {
           double src[NX];
 #pragma unroll
-          for (int cc = 0; cc < NX; cc++) src[cc] = __ldg(Am + rr + cc * NX);
+          for (int cc = 0; cc < NX; cc++) src[cc] = Am[(rr + cc * NX) * 32];
           row_trsm_lt<NX>(Mm, src, AM[rr]);
         }
 #pragma unroll
         for (int rr = 0; rr < NX; rr++)
 #pragma unroll
-          for (int cc = 0; cc < NX; cc++) st(fb + oAM + rr + cc * NX, AM[rr][cc]);
+          for (int cc = 0; cc < NX; cc++) st(i, O_FAC + oAM + rr + cc * NX, AM[rr][cc]);
       }
 #pragma unroll
       for (int rr = 0; rr < NU; rr++) row_trsm_lt<NX>(Mm, St[rr], SM[rr]);
 #pragma unroll
       for (int rr = 0; rr < NU; rr++)
 #pragma unroll
-        for (int cc = 0; cc < NX; cc++) st(fb + oSM + rr + cc * NU, SM[rr][cc]);
+        for (int cc = 0; cc < NX; cc++) st(i, O_FAC + oSM + rr + cc * NU, SM[rr][cc]);
       // SG = chol(R~ - SM SM') (:163-166)
       double SG[NU][NU];
 #pragma unroll
@@ -515,12 +603,12 @@ struct Lane {
           SG[rr][cc] = sv;
         }
       ok = chol<NU>(SG) && ok;
-      store_lower_u(fb + oSG, SG);
+      store_lower_u(i, O_FAC + oSG, SG);
       if (i == N) break;
       // P = (AM SM' - B) SG^-T (:170-175)
       double P[NX][NU];
       {
-        const double* Bm = B + (size_t)i * NX * NU;
+        const double* Bm = dat(i, D_B);
 #pragma unroll
         for (int rr = 0; rr < NX; rr++) {
           double src[NU];
@@ -529,11 +617,11 @@ struct Lane {
             double sv = 0.0;
 #pragma unroll
             for (int k = 0; k < NX; k++) sv = fma(AM[rr][k], SM[j][k], sv);
-            src[j] = sv - __ldg(Bm + rr + j * NX);
+            src[j] = sv - Bm[(rr + j * NX) * 32];
           }
           row_trsm_lt<NU>(SG, src, P[rr]);
 #pragma unroll
-          for (int j = 0; j < NU; j++) st(fb + oP + rr + j * NX, P[rr][j]);
+          for (int j = 0; j < NU; j++) st(i, O_FAC + oP + rr + j * NX, P[rr][j]);
         }
       }
       // L(i+1) = chol(sigma I + P P' + AM AM') (:179-183)
@@ -557,51 +645,80 @@ struct Lane {
     return ok;
   }
 
+  // dv = (rv + gamma .* A dz) ./ mus ; dy = b - A dz for one stage (:331-341);
+  // rv, ga, mu were loaded before the stage's first store
+  __device__ __forceinline__ void finish_stage(int i, const double (&dz)[NS],
+                                               const double (&rv)[NC], const double (&ga)[NC],
+                                               const double (&mu)[NC]) {
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+      const double sv = Az_entry(dz, i, k);
+      st(i, O_DX + V_V + k, ((-rv[k]) + ga[k] * sv) / mu[k]);
+      st(i, O_DX + V_Y + k, (-sv) + (-dat(i, D_d)[k * 32]));
+    }
+  }
+
   // RiccatiLinearSolver::Solve on r = -(ri), riccati_linear_solver.cc:212-344.
   // Storage reuse as in mpc_riccati.cuh: theta(i) -> dx.l(i), M^-1 h -> dx.z x(i),
   // SG^-1(.) -> dx.z u(i) until the backward sweep writes the step there.
   __device__ void solve() {
     double th[NX];  // theta(i)
 #pragma unroll
-    for (int k = 0; k < NX; k++) th[k] = ld(o_ri + nz + k);  // r2(0) = rl(0)
+    for (int k = 0; k < NX; k++) th[k] = ld(0, O_RI + R_L + k);  // r2(0) = rl(0)
     double lp[NX];  // dl(i+1) in the backward sweep
     for (int i = 0; i <= N; i++) {
-      const int fb = o_fac + i * FS;
-      // r3 = rv ./ mus, r1 = r.z - A' r3 for this stage (:222-225)
-      double tv[NC], r1[NS];
+      prefetch(i + 1, O_RI, SB);
+      double rr_[RSZ], mu[NC], ga[NC], fa[FS], rln[NX];
 #pragma unroll
-      for (int k = 0; k < NC; k++)
-        tv[k] = (-ld(o_ri + nz + nl + i * NC + k)) / ld(o_gm + nv + i * NC + k);
+      for (int k = 0; k < RSZ; k++) rr_[k] = ld(i, O_RI + k);
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        ga[k] = ld(i, O_GM + k);
+        mu[k] = ld(i, O_GM + NC + k);
+      }
+#pragma unroll
+      for (int k = 0; k < FS; k++) fa[k] = ld(i, O_FAC + k);
+      if (i < N) {
+#pragma unroll
+        for (int k = 0; k < NX; k++) rln[k] = ld(i + 1, O_RI + R_L + k);
+      }
+      // r3 = rv ./ mus, r1 = r.z - A' r3 for this stage (:222-225)
+      double tv[NC], r1[NS], rvv[NC];
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        rvv[k] = rr_[R_V + k];
+        tv[k] = (-rvv[k]) / mu[k];
+      }
       {
-        const double* Em = E + (size_t)i * NC * NX;
-        const double* Lm = L + (size_t)i * NC * NU;
+        const double* Em = dat(i, D_E);
+        const double* Lm = dat(i, D_L);
 #pragma unroll
         for (int rr = 0; rr < NS; rr++) {
           double sv = 0.0;
           if (rr < NX) {
 #pragma unroll
-            for (int k = 0; k < NC; k++) sv = fma(__ldg(Em + k + rr * NC), tv[k], sv);
+            for (int k = 0; k < NC; k++) sv = fma(Em[(k + rr * NC) * 32], tv[k], sv);
           } else {
 #pragma unroll
-            for (int k = 0; k < NC; k++) sv = fma(__ldg(Lm + k + (rr - NX) * NC), tv[k], sv);
+            for (int k = 0; k < NC; k++) sv = fma(Lm[(k + (rr - NX) * NC) * 32], tv[k], sv);
           }
-          r1[rr] = (-ld(o_ri + i * NS + rr)) - sv;
+          r1[rr] = (-rr_[R_Z + rr]) - sv;
         }
       }
       double Lc[NX][NX], Mm[NX][NX], SG[NU][NU], SM[NU][NX];
-      load_lower(fb + oL, Lc);
-      load_lower(fb + oM, Mm);
-      load_lower_u(fb + oSG, SG);
+      unpack_x(fa + oL, Lc);
+      unpack_x(fa + oM, Mm);
+      unpack_u(fa + oSG, SG);
 #pragma unroll
       for (int rr = 0; rr < NU; rr++)
 #pragma unroll
-        for (int cc = 0; cc < NX; cc++) SM[rr][cc] = ld(fb + oSM + rr + cc * NU);
+        for (int cc = 0; cc < NX; cc++) SM[rr][cc] = fa[oSM + rr + cc * NU];
       // h(i) = (L L')^-1 theta(i) - r1x(i)
-      double sa[NX], sb[NX], sc[NX], tx[NX];
+      double sa[NX], sb[NX], sc[NX], tx[NX], thi[NX];
 #pragma unroll
       for (int k = 0; k < NX; k++) {
         sa[k] = th[k];
-        st(lo(o_dx, i) + k, th[k]);
+        thi[k] = th[k];
       }
       trsv_l<NX>(Lc, sa, sb);
       trsv_lt<NX>(Lc, sb, sc);
@@ -618,20 +735,23 @@ struct Lane {
       }
       if (i < N) {
         trsv_l<NU>(SG, ub, tu);  // tu = SG^-1 (SM tx + ru)
-#pragma unroll
-        for (int k = 0; k < NX; k++) st(zo(o_dx, i) + k, tx[k]);
-#pragma unroll
-        for (int k = 0; k < NU; k++) st(zo(o_dx, i) + NX + k, tu[k]);
         // theta(i+1) = (P tu + AM tx) + r2(i+1)
 #pragma unroll
         for (int k = 0; k < NX; k++) {
           double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-          for (int cc = 0; cc < NU; cc++) s1 = fma(ld(fb + oP + k + cc * NX), tu[cc], s1);
+          for (int cc = 0; cc < NU; cc++) s1 = fma(fa[oP + k + cc * NX], tu[cc], s1);
 #pragma unroll
-          for (int cc = 0; cc < NX; cc++) s2 = fma(ld(fb + oAM + k + cc * NX), tx[cc], s2);
-          th[k] = (s1 + s2) + ld(o_ri + nz + (i + 1) * NX + k);
+          for (int cc = 0; cc < NX; cc++) s2 = fma(fa[oAM + k + cc * NX], tx[cc], s2);
+          th[k] = (s1 + s2) + rln[k];
         }
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+          st(i, O_DX + V_L + k, thi[k]);
+          st(i, O_DX + V_Z + k, tx[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < NU; k++) st(i, O_DX + V_Z + NX + k, tu[k]);
       } else {
         // terminal stage :267-285
         double uc[NU], uN[NU], xN[NX];
@@ -648,56 +768,68 @@ struct Lane {
 #pragma unroll
         for (int k = 0; k < NX; k++) {
           xN[k] = -sb[k];
-          sa[k] = xN[k] + th[k];
+          sa[k] = xN[k] + thi[k];
         }
         trsv_l<NX>(Lc, sa, sb);
         trsv_lt<NX>(Lc, sb, sc);
+        double zN[NS];
 #pragma unroll
         for (int k = 0; k < NX; k++) {
           lp[k] = -sc[k];
-          st(lo(o_dx, i) + k, lp[k]);
-          st(zo(o_dx, i) + k, xN[k]);
+          zN[k] = xN[k];
         }
 #pragma unroll
-        for (int k = 0; k < NU; k++) st(zo(o_dx, i) + NX + k, uN[k]);
-        double zN[NS];
-#pragma unroll
-        for (int k = 0; k < NX; k++) zN[k] = xN[k];
-#pragma unroll
         for (int k = 0; k < NU; k++) zN[NX + k] = uN[k];
-        finish_stage(i, zN);
+#pragma unroll
+        for (int k = 0; k < NX; k++) st(i, O_DX + V_L + k, lp[k]);
+#pragma unroll
+        for (int k = 0; k < NS; k++) st(i, O_DX + V_Z + k, zN[k]);
+        finish_stage(i, zN, rvv, ga, mu);
       }
     }
     // backward recursion :297-327
     for (int i = N - 1; i >= 0; i--) {
-      const int fb = o_fac + i * FS;
+      prefetch(i - 1, O_DX, SB);
+      double fa[FS], dxz[NS], thi[NX], rvv[NC], ga[NC], mu[NC];
+#pragma unroll
+      for (int k = 0; k < FS; k++) fa[k] = ld(i, O_FAC + k);
+#pragma unroll
+      for (int k = 0; k < NS; k++) dxz[k] = ld(i, O_DX + V_Z + k);
+#pragma unroll
+      for (int k = 0; k < NX; k++) thi[k] = ld(i, O_DX + V_L + k);
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        rvv[k] = ld(i, O_RI + R_V + k);
+        ga[k] = ld(i, O_GM + k);
+        mu[k] = ld(i, O_GM + NC + k);
+      }
       double Lc[NX][NX], Mm[NX][NX], SG[NU][NU];
-      load_lower(fb + oL, Lc);
-      load_lower(fb + oM, Mm);
-      load_lower_u(fb + oSG, SG);
+      unpack_x(fa + oL, Lc);
+      unpack_x(fa + oM, Mm);
+      unpack_u(fa + oSG, SG);
       double ua[NU], ui[NU], sa[NX], sb[NX], sc[NX], xi_[NX];
 #pragma unroll
       for (int k = 0; k < NU; k++) {
         double sv = 0.0;
 #pragma unroll
-        for (int rr = 0; rr < NX; rr++) sv = fma(ld(fb + oP + rr + k * NX), lp[rr], sv);
-        ua[k] = ld(zo(o_dx, i) + NX + k) + sv;
+        for (int rr = 0; rr < NX; rr++) sv = fma(fa[oP + rr + k * NX], lp[rr], sv);
+        ua[k] = dxz[NX + k] + sv;
       }
       trsv_lt<NU>(SG, ua, ui);
 #pragma unroll
       for (int k = 0; k < NX; k++) {
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-        for (int rr = 0; rr < NU; rr++) s1 = fma(ld(fb + oSM + rr + k * NU), ui[rr], s1);
+        for (int rr = 0; rr < NU; rr++) s1 = fma(fa[oSM + rr + k * NU], ui[rr], s1);
 #pragma unroll
-        for (int rr = 0; rr < NX; rr++) s2 = fma(ld(fb + oAM + rr + k * NX), lp[rr], s2);
-        sa[k] = (ld(zo(o_dx, i) + k) + s1) + s2;
+        for (int rr = 0; rr < NX; rr++) s2 = fma(fa[oAM + rr + k * NX], lp[rr], s2);
+        sa[k] = (dxz[k] + s1) + s2;
       }
       trsv_lt<NX>(Mm, sa, sb);
 #pragma unroll
       for (int k = 0; k < NX; k++) {
         xi_[k] = -sb[k];
-        sa[k] = ld(lo(o_dx, i) + k) + xi_[k];
+        sa[k] = thi[k] + xi_[k];
       }
       trsv_l<NX>(Lc, sa, sb);
       trsv_lt<NX>(Lc, sb, sc);
@@ -705,35 +837,28 @@ struct Lane {
 #pragma unroll
       for (int k = 0; k < NX; k++) {
         lp[k] = -sc[k];
-        st(lo(o_dx, i) + k, lp[k]);
-        st(zo(o_dx, i) + k, xi_[k]);
         zi[k] = xi_[k];
       }
 #pragma unroll
-      for (int k = 0; k < NU; k++) {
-        st(zo(o_dx, i) + NX + k, ui[k]);
-        zi[NX + k] = ui[k];
-      }
-      finish_stage(i, zi);
-    }
-  }
-  // dv = (rv + gamma .* A dz) ./ mus ; dy = b - A dz for one stage (:331-341)
-  __device__ __forceinline__ void finish_stage(int i, const double (&dz)[NS]) {
+      for (int k = 0; k < NU; k++) zi[NX + k] = ui[k];
 #pragma unroll
-    for (int k = 0; k < NC; k++) {
-      const double sv = Az_entry(dz, i, k);
-      const double rv = ld(o_ri + nz + nl + i * NC + k);
-      const double ga = ld(o_gm + i * NC + k), mu = ld(o_gm + nv + i * NC + k);
-      st(vo(o_dx, i) + k, ((-rv) + ga * sv) / mu);
-      st(yo(o_dx, i) + k, (-sv) + (-__ldg(d + i * NC + k)));
+      for (int k = 0; k < NX; k++) st(i, O_DX + V_L + k, lp[k]);
+#pragma unroll
+      for (int k = 0; k < NS; k++) st(i, O_DX + V_Z + k, zi[k]);
+      finish_stage(i, zi, rvv, ga, mu);
     }
   }
 
   // ProjectDuals on xi
   __device__ void project() {
-    for (int i = 0; i <= N; i++)
+    for (int i = 0; i <= N; i++) {
+      prefetch(i + 1, O_XI + V_V, O_XI + V_Y);
+      double v[NC];
 #pragma unroll
-      for (int k = 0; k < NC; k++) st(vo(o_xi, i) + k, fmax(ld(vo(o_xi, i) + k), 0.0));
+      for (int k = 0; k < NC; k++) v[k] = ld(i, O_XI + V_V + k);
+#pragma unroll
+      for (int k = 0; k < NC; k++) st(i, O_XI + V_V + k, fmax(v[k], 0.0));
+    }
   }
 
   // dx = xi - xk (y-aware), its norm, and FullFeasibility::CheckFeasibility on
@@ -747,46 +872,64 @@ struct Lane {
     for (int k = 0; k < NS; k++) zp[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < NX; k++) {
-      lc[k] = ld(lo(o_xi, 0) + k) + (-1.0) * ld(lo(o_xk, 0) + k);
+      lc[k] = ld(0, O_XI + V_L + k) + (-1.0) * ld(0, O_XK + V_L + k);
       ln[k] = 0.0;
     }
     for (int i = 0; i <= N; i++) {
-      double z[NS], v[NC];
+      prefetch(i + 1, 0, O_DX);
+      if (check) prefetch(i + 1, O_DAT, SB);
+      double xa[VSZ], xb[VSZ], la[NX], lb[NX];
 #pragma unroll
-      for (int k = 0; k < NS; k++) {
-        z[k] = ld(zo(o_xi, i) + k) + (-1.0) * ld(zo(o_xk, i) + k);
-        st(zo(o_dx, i) + k, z[k]);
-        s[0] = fma(z[k], z[k], s[0]);
-      }
-#pragma unroll
-      for (int k = 0; k < NX; k++) {
-        st(lo(o_dx, i) + k, lc[k]);
-        s[1] = fma(lc[k], lc[k], s[1]);
+      for (int k = 0; k < VSZ; k++) {
+        xa[k] = ld(i, O_XI + k);
+        xb[k] = ld(i, O_XK + k);
       }
       if (i < N) {
 #pragma unroll
-        for (int k = 0; k < NX; k++)
-          ln[k] = ld(lo(o_xi, i + 1) + k) + (-1.0) * ld(lo(o_xk, i + 1) + k);
+        for (int k = 0; k < NX; k++) {
+          la[k] = ld(i + 1, O_XI + V_L + k);
+          lb[k] = ld(i + 1, O_XK + V_L + k);
+        }
+      }
+      double z[NS], v[NC], dyv[NC];
+#pragma unroll
+      for (int k = 0; k < NS; k++) {
+        z[k] = xa[V_Z + k] + (-1.0) * xb[V_Z + k];
+        s[0] = fma(z[k], z[k], s[0]);
+      }
+#pragma unroll
+      for (int k = 0; k < NX; k++) s[1] = fma(lc[k], lc[k], s[1]);
+      if (i < N) {
+#pragma unroll
+        for (int k = 0; k < NX; k++) ln[k] = la[k] + (-1.0) * lb[k];
       }
 #pragma unroll
       for (int k = 0; k < NC; k++) {
-        v[k] = ld(vo(o_xi, i) + k) + (-1.0) * ld(vo(o_xk, i) + k);
-        st(vo(o_dx, i) + k, v[k]);
+        v[k] = xa[V_V + k] + (-1.0) * xb[V_V + k];
         s[2] = fma(v[k], v[k], s[2]);
-        const double yv = ld(yo(o_xi, i) + k) + (-1.0) * ld(yo(o_xk, i) + k);
-        st(yo(o_dx, i) + k, yv + (-__ldg(d + i * NC + k)));
+        const double yv = xa[V_Y + k] + (-1.0) * xb[V_Y + k];
+        dyv[k] = yv + (-dat(i, D_d)[k * 32]);
+      }
+#pragma unroll
+      for (int k = 0; k < NS; k++) st(i, O_DX + V_Z + k, z[k]);
+#pragma unroll
+      for (int k = 0; k < NX; k++) st(i, O_DX + V_L + k, lc[k]);
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        st(i, O_DX + V_V + k, v[k]);
+        st(i, O_DX + V_Y + k, dyv[k]);
       }
       if (check) {
-        const double* Qm = Q + (size_t)i * NX * NX;
-        const double* Rm = R + (size_t)i * NU * NU;
-        const double* Sm = S + (size_t)i * NU * NX;
-        const double* Em = E + (size_t)i * NC * NX;
-        const double* Lm = L + (size_t)i * NC * NU;
+        const double* Qm = dat(i, D_Q);
+        const double* Rm = dat(i, D_R);
+        const double* Sm = dat(i, D_S);
+        const double* Em = dat(i, D_E);
+        const double* Lm = dat(i, D_L);
 #pragma unroll
         for (int k = 0; k < NC; k++) {
           mx0 = fmax(mx0, Az_entry(z, i, k));
           mp1 = fmax(mp1, fabs(v[k]));
-          sm1 += (-__ldg(d + i * NC + k)) * v[k];
+          sm1 += (-dat(i, D_d)[k * 32]) * v[k];
         }
 #pragma unroll
         for (int rr = 0; rr < NX; rr++) {
@@ -795,15 +938,15 @@ struct Lane {
             gz = -z[rr];
             hh = -__ldg(x0 + rr);
           } else {
-            const double* Ap = A + (size_t)(i - 1) * NX * NX;
-            const double* Bp = B + (size_t)(i - 1) * NX * NU;
+            const double* Ap = dat(i - 1, D_A);
+            const double* Bp = dat(i - 1, D_B);
             double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-            for (int cc = 0; cc < NX; cc++) s1 = fma(__ldg(Ap + rr + cc * NX), zp[cc], s1);
+            for (int cc = 0; cc < NX; cc++) s1 = fma(Ap[(rr + cc * NX) * 32], zp[cc], s1);
 #pragma unroll
-            for (int cc = 0; cc < NU; cc++) s2 = fma(__ldg(Bp + rr + cc * NX), zp[NX + cc], s2);
+            for (int cc = 0; cc < NU; cc++) s2 = fma(Bp[(rr + cc * NX) * 32], zp[NX + cc], s2);
             gz = (s1 + s2) - z[rr];
-            hh = -__ldg(c + (size_t)(i - 1) * NX + rr);
+            hh = -dat(i - 1, D_c)[rr * 32];
           }
           mx1 = fmax(mx1, fabs(gz));
           mp2 = fmax(mp2, fabs(lc[rr]));
@@ -814,37 +957,37 @@ struct Lane {
           double s1 = 0.0, s2 = 0.0, p, fe;
           if (rr < NX) {
 #pragma unroll
-            for (int cc = 0; cc < NX; cc++) s1 = fma(__ldg(Qm + rr + cc * NX), z[cc], s1);
+            for (int cc = 0; cc < NX; cc++) s1 = fma(Qm[(rr + cc * NX) * 32], z[cc], s1);
 #pragma unroll
-            for (int cc = 0; cc < NU; cc++) s2 = fma(__ldg(Sm + cc + rr * NU), z[NX + cc], s2);
-            fe = __ldg(q + i * NX + rr);
+            for (int cc = 0; cc < NU; cc++) s2 = fma(Sm[(cc + rr * NU) * 32], z[NX + cc], s2);
+            fe = dat(i, D_q)[rr * 32];
             double sv = 0.0;
 #pragma unroll
-            for (int k = 0; k < NC; k++) sv = fma(__ldg(Em + k + rr * NC), v[k], sv);
+            for (int k = 0; k < NC; k++) sv = fma(Em[(k + rr * NC) * 32], v[k], sv);
             p = sv + (-lc[rr]);
             if (i < N) {
-              const double* Am = A + (size_t)i * NX * NX;
+              const double* Am = dat(i, D_A);
               double sa = 0.0;
 #pragma unroll
-              for (int cc = 0; cc < NX; cc++) sa = fma(__ldg(Am + cc + rr * NX), ln[cc], sa);
+              for (int cc = 0; cc < NX; cc++) sa = fma(Am[(cc + rr * NX) * 32], ln[cc], sa);
               p += sa;
             }
           } else {
             const int ru = rr - NX;
 #pragma unroll
-            for (int cc = 0; cc < NX; cc++) s1 = fma(__ldg(Sm + ru + cc * NU), z[cc], s1);
+            for (int cc = 0; cc < NX; cc++) s1 = fma(Sm[(ru + cc * NU) * 32], z[cc], s1);
 #pragma unroll
-            for (int cc = 0; cc < NU; cc++) s2 = fma(__ldg(Rm + ru + cc * NU), z[NX + cc], s2);
-            fe = __ldg(r + i * NU + ru);
+            for (int cc = 0; cc < NU; cc++) s2 = fma(Rm[(ru + cc * NU) * 32], z[NX + cc], s2);
+            fe = dat(i, D_r)[ru * 32];
             double sv = 0.0;
 #pragma unroll
-            for (int k = 0; k < NC; k++) sv = fma(__ldg(Lm + k + ru * NC), v[k], sv);
+            for (int k = 0; k < NC; k++) sv = fma(Lm[(k + ru * NC) * 32], v[k], sv);
             p = sv;
             if (i < N) {
-              const double* Bm = B + (size_t)i * NX * NU;
+              const double* Bm = dat(i, D_B);
               double sa = 0.0;
 #pragma unroll
-              for (int cc = 0; cc < NX; cc++) sa = fma(__ldg(Bm + cc + ru * NX), ln[cc], sa);
+              for (int cc = 0; cc < NX; cc++) sa = fma(Bm[(cc + ru * NX) * 32], ln[cc], sa);
               p += sa;
             }
           }
@@ -872,17 +1015,33 @@ struct Lane {
     return sqrt(a * a + b * b + c2 * c2);
   }
 
-  __device__ void copy_vars(int from, int to) {
-    const int n = nz + nl + 2 * nv;
-    for (int e = 0; e < n; e++) st(to + e, ld(from + e));
+  // xk <- xi
+  __device__ void copy_xi_to_xk() {
+    for (int i = 0; i <= N; i++) {
+      prefetch(i + 1, O_XI, O_DX);
+      double x[VSZ];
+#pragma unroll
+      for (int k = 0; k < VSZ; k++) x[k] = ld(i, O_XI + k);
+#pragma unroll
+      for (int k = 0; k < VSZ; k++) st(i, O_XK + k, x[k]);
+    }
   }
 
+  // result block `from` (O_XK / O_XI / O_DX) -> the caller's instance-major arrays
   __device__ void write_result(int from, double* z, double* l, double* v, double* y) {
-    for (int e = 0; e < nz; e++) z[e] = ld(from + e);
-    for (int e = 0; e < nl; e++) l[e] = ld(from + nz + e);
-    for (int e = 0; e < nv; e++) {
-      v[e] = ld(from + nz + nl + e);
-      y[e] = ld(from + nz + nl + nv + e);
+    for (int i = 0; i <= N; i++) {
+      double x[VSZ];
+#pragma unroll
+      for (int k = 0; k < VSZ; k++) x[k] = ld(i, from + k);
+#pragma unroll
+      for (int k = 0; k < NS; k++) z[i * NS + k] = x[V_Z + k];
+#pragma unroll
+      for (int k = 0; k < NX; k++) l[i * NX + k] = x[V_L + k];
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        v[i * NC + k] = x[V_V + k];
+        y[i * NC + k] = x[V_Y + k];
+      }
     }
   }
 };
@@ -898,14 +1057,7 @@ __global__ void __launch_bounds__(32, 8) mpc_lane_kernel(const __grid_constant__
   p.nz = (a.N + 1) * LN::NS;
   p.nl = (a.N + 1) * NX;
   p.nv = (a.N + 1) * NC;
-  const int VS = p.nz + p.nl + 2 * p.nv;
   p.ws = a.ws + (size_t)blockIdx.x * a.ws_stride + lane;
-  p.o_xk = 0;
-  p.o_xi = VS;
-  p.o_dx = 2 * VS;
-  p.o_ri = 3 * VS;
-  p.o_gm = p.o_ri + p.nz + p.nl + p.nv;
-  p.o_fac = p.o_gm + 2 * p.nv;
 
   // per-lane solver state (fbstab_algorithm-impl.h:113-304 as a phase machine)
   bool active = false, exhausted = false;
@@ -947,7 +1099,7 @@ __global__ void __launch_bounds__(32, 8) mpc_lane_kernel(const __grid_constant__
     e.Ei = e.Eo = 0.0;
     if (active && need_eval) {
       const bool self_bar = (phase == PH_TOP) || (phase == PH_FINAL);
-      const int base = (phase == PH_FINAL && !pick_xi) ? p.o_xk : p.o_xi;
+      const int base = (phase == PH_FINAL && !pick_xi) ? LN::O_XK : LN::O_XI;
       e = p.evaluate(base, phase == PH_TRIAL, tstep, self_bar, sigma, alpha);
       evals++;
     }
@@ -1075,7 +1227,7 @@ __global__ void __launch_bounds__(32, 8) mpc_lane_kernel(const __grid_constant__
           which = 2;
           finish = true;
         } else {
-          p.copy_vars(p.o_xi, p.o_xk);
+          p.copy_xi_to_xk();
           prox++;
           k++;
           if (k >= o.max_prox_iters) {
@@ -1091,7 +1243,7 @@ __global__ void __launch_bounds__(32, 8) mpc_lane_kernel(const __grid_constant__
     }
     // ---- WriteVariable + PrepareOutput, impl:349-383 ---------------------------
     if (finish) {
-      const int from = which == 0 ? p.o_xk : which == 1 ? p.o_xi : p.o_dx;
+      const int from = which == 0 ? LN::O_XK : which == 1 ? LN::O_XI : LN::O_DX;
       p.write_result(from, a.z + (size_t)inst * p.nz, a.l + (size_t)inst * p.nl,
                      a.v + (size_t)inst * p.nv, a.y + (size_t)inst * p.nv);
       fbstab_out* out = a.out + inst;
@@ -1132,7 +1284,9 @@ size_t MpcLaneWsDoublesPerWarp(int N, int nx, int nu, int nc) {
   const size_t nz = K * (nx + nu), nl = K * nx, nv = K * nc;
   const size_t fs = (size_t)nx * (nx + 1) + (size_t)nx * nx + 2 * (size_t)nx * nu +
                     (size_t)nu * (nu + 1) / 2;
-  return 32 * (3 * (nz + nl + 2 * nv) + (nz + nl + nv) + 2 * nv + K * fs);
+  const size_t dat = 2 * (size_t)nx * nx + (size_t)nu * nu + 2 * (size_t)nu * nx + 2 * nx + nu +
+                     (size_t)nc * nx + (size_t)nc * nu + nc;
+  return 32 * (3 * (nz + nl + 2 * nv) + (nz + nl + nv) + 2 * nv + K * (fs + dat));
 }
 
 int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps, const MpcData& data,
