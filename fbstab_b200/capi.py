@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfbstab_b200.so")
+LIB_PATH = os.environ.get("FBSTAB_B200_LIB") or os.path.join(_HERE, "libfbstab_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOGPU, ERR_ALLOC = 0, 1, 2, 3, 4
 EXIT_FLAGS = {0: "SUCCESS", 1: "DIVERGENCE", 2: "MAXITERATIONS",

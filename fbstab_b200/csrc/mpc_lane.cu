@@ -37,6 +37,15 @@
 #include "engine.cuh"
 #include "mpc_lane.h"
 
+#ifdef PREFETCH_L1
+#define PREFETCH_OP "prefetch.global.L1"
+#else
+#define PREFETCH_OP "prefetch.global.L2"
+#endif
+#ifndef PREFETCH_DIST
+#define PREFETCH_DIST 1
+#endif
+
 namespace fbs {
 namespace {
 
@@ -55,8 +64,14 @@ struct LaneArgs {
 
 enum { PH_TOP = 0, PH_TRIAL = 1, PH_REEVAL = 2, PH_FINAL = 3 };
 
-// ---- register-resident small dense algebra (operation order of the team
-// versions in mpc_riccati.cuh) ------------------------------------------------
+// ---- register-resident small dense algebra ----------------------------------
+// Same recursions as the team versions in mpc_riccati.cuh, with one change that
+// matters for the latency of a lone instance: the Cholesky factors keep the
+// RECIPROCAL of their diagonal in the diagonal slot, so that the ~40 dependent
+// divisions per stage of the triangular solves become multiplications (an FP64
+// division is a ~100-cycle dependent chain; a straggler instance runs its
+// stages strictly one after the other).  Results differ from the dividing
+// kernels by rounding only.
 template <int M>
 __device__ __forceinline__ bool chol(double (&A)[M][M]) {
   bool ok = true;
@@ -67,24 +82,24 @@ __device__ __forceinline__ bool chol(double (&A)[M][M]) {
     for (int j = 0; j < k; j++) s = fma(A[k][j], A[k][j], s);
     double x = A[k][k] - s;
     if (!(x > 0.0)) ok = false;
-    x = sqrt(x);
+    const double rx = 1.0 / sqrt(x);
 #pragma unroll
     for (int i = k + 1; i < M; i++) {
       double a = 0.0;
 #pragma unroll
       for (int j = 0; j < k; j++) a = fma(A[i][j], A[k][j], a);
-      A[i][k] = (A[i][k] - a) / x;
+      A[i][k] = (A[i][k] - a) * rx;
     }
-    A[k][k] = x;
+    A[k][k] = rx;  // reciprocal diagonal
   }
   return ok;
 }
-// y = L^-1 x (x destroyed)
+// y = L^-1 x (x destroyed); L carries reciprocal diagonals
 template <int M>
 __device__ __forceinline__ void trsv_l(const double (&L)[M][M], double (&x)[M], double (&y)[M]) {
 #pragma unroll
   for (int j = 0; j < M; j++) {
-    const double xj = x[j] / L[j][j];
+    const double xj = x[j] * L[j][j];
     y[j] = xj;
 #pragma unroll
     for (int i = j + 1; i < M; i++) x[i] = fma(-L[i][j], xj, x[i]);
@@ -95,7 +110,7 @@ template <int M>
 __device__ __forceinline__ void trsv_lt(const double (&L)[M][M], double (&x)[M], double (&y)[M]) {
 #pragma unroll
   for (int i = M - 1; i >= 0; i--) {
-    const double xi = x[i] / L[i][i];
+    const double xi = x[i] * L[i][i];
     y[i] = xi;
 #pragma unroll
     for (int r = 0; r < i; r++) x[r] = fma(-L[i][r], xi, x[r]);
@@ -110,7 +125,7 @@ __device__ __forceinline__ void row_trsm_lt(const double (&L)[M][M], const doubl
     double s = src[j];
 #pragma unroll
     for (int k = 0; k < j; k++) s = fma(-X[k], L[j][k], s);
-    X[j] = s / L[j][j];
+    X[j] = s * L[j][j];
   }
 }
 
@@ -161,7 +176,7 @@ struct Lane {
     const char* base = (const char*)(ws - lane) + ((size_t)i * SB + o0) * 256;
     const int lines = (o1 - o0) * 2;
     for (int m = lane; m < lines; m += 32)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)m * 128));
+      asm volatile(PREFETCH_OP " [%0];" ::"l"(base + (size_t)m * 128));
   }
 
   __device__ void bind(const LaneArgs& a, int inst) {
@@ -309,8 +324,8 @@ struct Lane {
 #pragma unroll
     for (int k = 0; k < NS; k++) zp[k] = 0.0;
     for (int i = 0; i <= N; i++) {
-      prefetch(i + 1, 0, O_RI);
-      prefetch(i + 1, O_DAT, SB);
+      prefetch(i + PREFETCH_DIST, 0, O_RI);
+      prefetch(i + PREFETCH_DIST, O_DAT, SB);
       double xb[VSZ], xd[VSZ], zk[NS], lk[NX], vk[NC], la[NX], lb[NX];
 #pragma unroll
       for (int k = 0; k < VSZ; k++) {
@@ -446,8 +461,8 @@ struct Lane {
   // xi <- xi + t dx (same fused multiply-adds as the trial evaluation)
   __device__ void commit(double t) {
     for (int i = 0; i <= N; i++) {
-      prefetch(i + 1, O_XI, O_RI);
-      prefetch(i + 1, D_d, SB);
+      prefetch(i + PREFETCH_DIST, O_XI, O_RI);
+      prefetch(i + PREFETCH_DIST, D_d, SB);
       double xb[VSZ], xd[VSZ];
 #pragma unroll
       for (int k = 0; k < VSZ; k++) {
@@ -466,24 +481,49 @@ struct Lane {
     }
   }
 
-  // RiccatiLinearSolver::Initialize, riccati_linear_solver.cc:77-210
-  __device__ bool factor(double sigma, double alpha) {
+  // RiccatiLinearSolver::Initialize, riccati_linear_solver.cc:77-210.
+  // with_commit: the accepted step xi <- xi + t dx is applied in the same sweep
+  // (saves one pass over the horizon in the common accept-then-Newton round).
+  __device__ bool factor(double sigma, double alpha, bool with_commit, double t) {
     bool ok = true;
     double Lc[NX][NX];
-    const double rs = sqrt(sigma);
+    const double rs = 1.0 / sqrt(sigma);  // reciprocal diagonal of L(0) = sqrt(sigma) I
 #pragma unroll
     for (int a_ = 0; a_ < NX; a_++)
 #pragma unroll
       for (int b_ = 0; b_ < NX; b_++) Lc[a_][b_] = (a_ == b_) ? rs : 0.0;
     for (int i = 0; i <= N; i++) {
-      prefetch(i + 1, O_XK + V_V, O_DX);
-      prefetch(i + 1, O_DAT, SB);
+      prefetch(i + PREFETCH_DIST, O_XK + V_V, O_RI);
+      prefetch(i + PREFETCH_DIST, O_DAT, SB);
       double yv[NC], vv[NC], vk[NC];
 #pragma unroll
       for (int k = 0; k < NC; k++) {
         yv[k] = ld(i, O_XI + V_Y + k);
         vv[k] = ld(i, O_XI + V_V + k);
         vk[k] = ld(i, O_XK + V_V + k);
+      }
+      if (with_commit) {
+        double xz[V_V], dz[V_V], dv[NC], dy[NC], dd[NC];
+#pragma unroll
+        for (int k = 0; k < V_V; k++) {
+          xz[k] = ld(i, O_XI + k);
+          dz[k] = ld(i, O_DX + k);
+        }
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+          dv[k] = ld(i, O_DX + V_V + k);
+          dy[k] = ld(i, O_DX + V_Y + k);
+          dd[k] = dat(i, D_d)[k * 32];
+        }
+#pragma unroll
+        for (int k = 0; k < V_V; k++) st(i, O_XI + k, fma(t, dz[k], xz[k]));
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+          vv[k] = fma(t, dv[k], vv[k]);
+          yv[k] = fma(-t, -dd[k], fma(t, dy[k], yv[k]));
+          st(i, O_XI + V_V + k, vv[k]);
+          st(i, O_XI + V_Y + k, yv[k]);
+        }
       }
       store_lower(i, O_FAC + oL, Lc);
       double Gam[NC];
@@ -518,7 +558,7 @@ struct Lane {
         for (int k = 0; k < NX; k++) w[k] = (k == cc) ? 1.0 : 0.0;
 #pragma unroll
         for (int j = 0; j < NX; j++) {
-          w[j] /= Lc[j][j];
+          w[j] *= Lc[j][j];
           const double wj = w[j];
 #pragma unroll
           for (int k = j + 1; k < NX; k++) w[k] = fma(-Lc[k][j], wj, w[k]);
@@ -528,7 +568,7 @@ struct Lane {
           double sv = w[k];
 #pragma unroll
           for (int j = k + 1; j < NX; j++) sv = fma(-Lc[j][k], w[j], sv);
-          w[k] = sv / Lc[k][k];
+          w[k] = sv * Lc[k][k];
         }
 #pragma unroll
         for (int rr = cc; rr < NX; rr++) Mm[rr][cc] = w[rr];
@@ -667,7 +707,7 @@ struct Lane {
     for (int k = 0; k < NX; k++) th[k] = ld(0, O_RI + R_L + k);  // r2(0) = rl(0)
     double lp[NX];  // dl(i+1) in the backward sweep
     for (int i = 0; i <= N; i++) {
-      prefetch(i + 1, O_RI, SB);
+      prefetch(i + PREFETCH_DIST, O_RI, SB);
       double rr_[RSZ], mu[NC], ga[NC], fa[FS], rln[NX];
 #pragma unroll
       for (int k = 0; k < RSZ; k++) rr_[k] = ld(i, O_RI + k);
@@ -789,7 +829,7 @@ struct Lane {
     }
     // backward recursion :297-327
     for (int i = N - 1; i >= 0; i--) {
-      prefetch(i - 1, O_DX, SB);
+      prefetch(i - PREFETCH_DIST, O_DX, SB);
       double fa[FS], dxz[NS], thi[NX], rvv[NC], ga[NC], mu[NC];
 #pragma unroll
       for (int k = 0; k < FS; k++) fa[k] = ld(i, O_FAC + k);
@@ -852,7 +892,7 @@ struct Lane {
   // ProjectDuals on xi
   __device__ void project() {
     for (int i = 0; i <= N; i++) {
-      prefetch(i + 1, O_XI + V_V, O_XI + V_Y);
+      prefetch(i + PREFETCH_DIST, O_XI + V_V, O_XI + V_Y);
       double v[NC];
 #pragma unroll
       for (int k = 0; k < NC; k++) v[k] = ld(i, O_XI + V_V + k);
@@ -876,8 +916,8 @@ struct Lane {
       ln[k] = 0.0;
     }
     for (int i = 0; i <= N; i++) {
-      prefetch(i + 1, 0, O_DX);
-      if (check) prefetch(i + 1, O_DAT, SB);
+      prefetch(i + PREFETCH_DIST, 0, O_DX);
+      if (check) prefetch(i + PREFETCH_DIST, O_DAT, SB);
       double xa[VSZ], xb[VSZ], la[NX], lb[NX];
 #pragma unroll
       for (int k = 0; k < VSZ; k++) {
@@ -1018,7 +1058,7 @@ struct Lane {
   // xk <- xi
   __device__ void copy_xi_to_xk() {
     for (int i = 0; i <= N; i++) {
-      prefetch(i + 1, O_XI, O_DX);
+      prefetch(i + PREFETCH_DIST, O_XI, O_DX);
       double x[VSZ];
 #pragma unroll
       for (int k = 0; k < VSZ; k++) x[k] = ld(i, O_XI + k);
@@ -1185,10 +1225,11 @@ __global__ void __launch_bounds__(32, 8) mpc_lane_kernel(const __grid_constant__
       }
     }
     // ---- commit the accepted (or forced) step: xi <- xi + t dx ---------------
-    if (do_commit) p.commit(tstep);
+    // (lanes that go on to a Newton step commit inside the factor sweep)
+    if (do_commit && !do_newton) p.commit(tstep);
     // ---- Newton step ------------------------------------------------------------
     if (do_newton) {
-      if (!p.factor(sigma, alpha)) {  // impl:263-267
+      if (!p.factor(sigma, alpha, do_commit, tstep)) {  // impl:263-267
         status = FBSTAB_STATUS_FACTOR_FAILED;
         finish = true;
         which = 0;
