@@ -242,6 +242,9 @@ __device__ void PersistentLoop(const Args& a, int nz, int nl, int nv) {
   fbs::Team t{red};
   const CommonArgs& c = a.c;
   double* ws0 = c.ws + (size_t)blockIdx.x * c.ws_stride;
+#ifdef FBSTAB_PHASE_TIMERS
+  if (threadIdx.x == 0) fbs::g_phase_last[blockIdx.x] = clock64();
+#endif
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(c.counter, 1);
     __syncthreads();
@@ -635,6 +638,18 @@ int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
   *handle = h;
   return FBSTAB_OK;
 }
+
+#ifdef FBSTAB_PHASE_TIMERS
+// development builds only: read (and optionally clear) the phase cycle counters
+extern "C" int fbstab_debug_phase_cycles(unsigned long long* out32, int reset) {
+  if (out32) cudaMemcpyFromSymbol(out32, fbs::g_phase_cycles, 32 * sizeof(unsigned long long));
+  if (reset) {
+    unsigned long long z[32] = {};
+    cudaMemcpyToSymbol(fbs::g_phase_cycles, z, sizeof(z));
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+#endif
 
 int fbstab_dense_batch_destroy(fbstab_dense_batch* h) {
   if (!h) return FBSTAB_OK;

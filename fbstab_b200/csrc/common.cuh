@@ -33,6 +33,26 @@ struct Team {
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 
+// Optional per-phase cycle accounting (development builds only:
+// -DFBSTAB_PHASE_TIMERS, tools/phase_timers.py).  lap(i) charges the cycles
+// since the previous lap of this CTA to phase i.
+#ifdef FBSTAB_PHASE_TIMERS
+// (static: one copy per translation unit; only api.cu reads it back)
+static __device__ unsigned long long g_phase_cycles[32];
+static __device__ long long g_phase_last[1024];
+__device__ __forceinline__ void phase_lap(int idx) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long now = clock64();
+    atomicAdd(&g_phase_cycles[idx], (unsigned long long)(now - g_phase_last[blockIdx.x]));
+    g_phase_last[blockIdx.x] = now;
+  }
+}
+#define FBS_LAP(idx) ::fbs::phase_lap(idx)
+#else
+#define FBS_LAP(idx) ((void)0)
+#endif
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);

@@ -62,24 +62,28 @@ __device__ __forceinline__ void cp_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// acc(128x128, this warp's 32x32 part) = sum_k opI(i,k) * [scale(k)] * opJ(j,k).
+// acc(128x128, this warp's 32x32 part) += sum_k opI(i,k) * w * opJ(j,k), where
+// the weight w is 1 (MODE 0), scale[k] (MODE 1: Gamma of A' Gamma A) or
+// csgn[b] = +-1 per 8-column group of the tile (MODE 2: the trailing update
+// subtracts inside E and W, adds inside S).  The caller PRELOADS acc with the
+// tile's current value (H + sigma I, or the trailing K): those 32 global loads
+// per thread are all in flight while the first operand chunks arrive, instead
+// of 32 dependent load -> store round trips after the product.
 // AddrI / AddrJ: (idx in [0,128), k in [0,depth)) -> global address of the
 // element, or nullptr outside the matrix (zero filled).  The 16 warps form a
 // 4x4 grid; warp (wm,wn) owns rows 32wm.., cols 32wn.. as 4x4 m8n8 DMMA tiles.
 // `same`: opJ == opI (diagonal tile).  Operand chunks travel global -> shared
 // as cp.async copies through a kStages-deep ring, two chunks ahead of the
 // DMMAs, with one barrier per chunk.
-template <bool SCALED, class AddrI, class AddrJ>
+template <int MODE, class AddrI, class AddrJ>
 __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], double* sm, int depth,
-                                         AddrI ai, AddrJ aj, const double* scale, bool same) {
+                                         AddrI ai, AddrJ aj, const double* scale, bool same,
+                                         const double (&csgn)[4]) {
+  constexpr bool SCALED = (MODE == 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r8 = lane >> 2, c4 = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
   const int sidx = 8 * warp + r8;  // staging: this thread's tile row/col index
-#pragma unroll
-  for (int a = 0; a < 4; a++)
-#pragma unroll
-    for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
   const int nchunk = (depth + KC - 1) / KC;
   auto issue = [&](int ch) {
     if (ch < nchunk) {
@@ -119,7 +123,7 @@ __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], double* sm, int
 #pragma unroll
       for (int b = 0; b < 4; b++) {
         const double v = SJ[(32 * wn + 8 * b + r8) * KP + 4 * kk + c4];
-        bf[b] = SCALED ? g * v : v;
+        bf[b] = SCALED ? g * v : (MODE == 2 ? csgn[b] * v : v);
       }
 #pragma unroll
       for (int a = 0; a < 4; a++)
@@ -147,6 +151,22 @@ __device__ __forceinline__ void for_each_acc(const double (&acc)[4][4][2], F f) 
     }
 }
 
+// Preloads this thread's accumulator entries: acc = f(tile_row, tile_col).
+template <class F>
+__device__ __forceinline__ void init_acc(double (&acc)[4][4][2], F f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r8 = lane >> 2, c4 = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int r = 32 * wm + 8 * a + r8, c = 32 * wn + 8 * b + 2 * c4;
+      acc[a][b][0] = f(r, c);
+      acc[a][b][1] = f(r, c + 1);
+    }
+}
+
 }  // namespace dl
 
 struct DenseLargeProblem : DenseProblem {
@@ -157,10 +177,12 @@ struct DenseLargeProblem : DenseProblem {
   // written back.  false on a pivot <= 0 (Eigen LLT's failure rule).
   __device__ __noinline__ bool factor_diag(int c0, int bs, double* D, double* dg) {
     const int tid = threadIdx.x;
-    for (int e = tid; e < bs * bs; e += dl::kThreads) {
+    for (int e = tid; e < bs * bs; e += dl::kThreads) {  // all copies in flight at once
       const int i = e % bs, j = e / bs;
-      D[i + j * dl::DP] = (i >= j) ? K[(c0 + i) + (size_t)(c0 + j) * n] : 0.0;
+      dl::cp8(D + i + j * dl::DP, K + (c0 + i) + (size_t)(c0 + j) * n, i >= j);
     }
+    dl::cp_commit();
+    dl::cp_wait<0>();
     __syncthreads();
     bool ok = true;
     for (int j = 0; j < bs; j++) {
@@ -194,7 +216,56 @@ struct DenseLargeProblem : DenseProblem {
   // Rows [r0, n) of block column c0: X = B Lkk^-T on shared-memory tiles of
   // TR rows.  Two threads share a row (even / odd terms of the substitution's
   // dot product, combined with one shuffle); no barrier inside a tile.
+  // bs == NB fast path: the tile arrives by cp.async (every copy in flight at
+  // once), a thread keeps its half of the row (the x_k with k = half mod 2) in
+  // registers through the fully unrolled substitution and stores the result
+  // straight to global memory.  Same operation order as the general path.
+  __device__ __noinline__ void panel_solve_full(int c0, const double* D, double* Tm) {
+    constexpr int BS = dl::NB;
+    const int tid = threadIdx.x;
+    const int half = tid & 1, rl = tid >> 1;
+    for (int r0 = c0 + BS; r0 < n; r0 += dl::TR) {
+      const int rows = min(dl::TR, n - r0);
+      {
+        const int r = tid % dl::TR;
+        for (int k = tid / dl::TR; k < BS; k += dl::kThreads / dl::TR)
+          dl::cp8(Tm + r + k * dl::TR, K + (r0 + min(r, rows - 1)) + (size_t)(c0 + k) * n,
+                  r < rows);
+        dl::cp_commit();
+        dl::cp_wait<0>();
+      }
+      __syncthreads();
+      double x[BS / 2];
+#pragma unroll
+      for (int m = 0; m < BS / 2; m++) x[m] = Tm[rl + (2 * m + half) * dl::TR];
+#pragma unroll
+      for (int j = 0; j < BS; j++) {
+        // x_j = (b_j - sum_{k<j} x_k L(j,k)) / L(j,j)
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < (j + 1) / 2; m++) {
+          const int k = 2 * m + half;
+          const double ljk = (2 * m + 1 < j || k < j) ? D[j + k * dl::DP] : 0.0;
+          s = fma(x[m], ljk, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        const double xj = (x[j >> 1] - s) / D[j + j * dl::DP];
+        if (half == (j & 1)) x[j >> 1] = xj;
+      }
+      if (rl < rows) {
+#pragma unroll
+        for (int m = 0; m < BS / 2; m++)
+          K[(r0 + rl) + (size_t)(c0 + 2 * m + half) * n] = x[m];
+      }
+      __syncthreads();
+    }
+  }
+
   __device__ __noinline__ void panel_solve(int c0, int bs, const double* D, double* Tm) {
+    if (bs == dl::NB) {
+      panel_solve_full(c0, D, Tm);
+      return;
+    }
     const int tid = threadIdx.x;
     const int half = tid & 1, rl = tid >> 1;
     for (int r0 = c0 + bs; r0 < n; r0 += dl::TR) {
@@ -232,6 +303,7 @@ struct DenseLargeProblem : DenseProblem {
                          double sigma, double alpha) {
     const int tid = threadIdx.x;
     double* Gam = r2;
+    FBS_LAP(15);
     for (int i = tid; i < nv; i += dl::kThreads) {
       const double ys = x.y[i] + sigma * (x.v[i] - xbar.v[i]);
       double ga, mu;
@@ -256,14 +328,22 @@ struct DenseLargeProblem : DenseProblem {
             const int c = J * dl::TB + idx;
             return c < nzz ? Ap + k + (size_t)c * nvv : nullptr;
           };
-          dl::mma_tile<true>(acc, sm, nv, li, lj, Gam, I == J);
+          const double* Hp = H;
+          dl::init_acc(acc, [&](int r, int c) -> double {
+            const int gr = I * dl::TB + r, gc = J * dl::TB + c;
+            return (gr < nzz && gc <= gr)
+                       ? __ldg(Hp + gr + (size_t)gc * nzz) + (gr == gc ? sigma : 0.0)
+                       : 0.0;
+          });
+          const double one[4] = {1.0, 1.0, 1.0, 1.0};
+          dl::mma_tile<1>(acc, sm, nv, li, lj, Gam, I == J, one);
           dl::for_each_acc(acc, [&](int r, int c, double v) {
             const int gr = I * dl::TB + r, gc = J * dl::TB + c;
-            if (gr < nz && gc <= gr)
-              K[gr + (size_t)gc * n] = (H[gr + (size_t)gc * nz] + (gr == gc ? sigma : 0.0)) + v;
+            if (gr < nz && gc <= gr) K[gr + (size_t)gc * n] = v;
           });
         }
     }
+    FBS_LAP(1);
     // rows of G below E, and S initialised to sigma I   (:67-69 with the sign of
     // the Schur complement folded into the updates)
     for (int e = tid; e < nl * n; e += dl::kThreads) {
@@ -271,6 +351,7 @@ struct DenseLargeProblem : DenseProblem {
       K[nz + r + (size_t)c * n] = (c < nz) ? G[r + (size_t)c * nl] : ((c - nz == r) ? sigma : 0.0);
     }
     __syncthreads();
+    FBS_LAP(2);
     // blocked right-looking Cholesky over the E block columns, then the S ones
     bool ok = true;
     double* D = sm;
@@ -280,7 +361,9 @@ struct DenseLargeProblem : DenseProblem {
       const bool inE = c0 < nz;
       const int bs = min(dl::NB, (inE ? nz : n) - c0);
       ok = factor_diag(c0, bs, D, dg) && ok;
+      FBS_LAP(3);
       panel_solve(c0, bs, D, Tm);
+      FBS_LAP(4);
       // trailing update with the panel X = K(c0+bs.., c0..c0+bs)
       const int t0 = c0 + bs;
       const double* Kp = K;
@@ -296,17 +379,29 @@ struct DenseLargeProblem : DenseProblem {
             const int r = t0 + J * dl::TB + idx;
             return r < nn ? Kp + r + (size_t)(c0 + k) * nn : nullptr;
           };
-          dl::mma_tile<false>(acc, sm, bs, li, lj, Kp, I == J);
+          dl::init_acc(acc, [&](int r, int c) -> double {
+            const int gr = t0 + I * dl::TB + r, gc = t0 + J * dl::TB + c;
+            return (gr < nn && gc <= gr) ? Kp[gr + (size_t)gc * nn] : 0.0;
+          });
+          // S = sigma I + W'W grows while E's columns are eliminated; everything
+          // else shrinks: the sign rides on the B operand's column
+          double csgn[4];
+          {
+            const int lane = tid & 31, wn = (tid >> 5) & 3;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+              const int gc = t0 + J * dl::TB + 32 * wn + 8 * b + (lane >> 2);
+              csgn[b] = (inE && gc >= nzz) ? 1.0 : -1.0;
+            }
+          }
+          dl::mma_tile<2>(acc, sm, bs, li, lj, Kp, I == J, csgn);
           dl::for_each_acc(acc, [&](int r, int c, double v) {
             const int gr = t0 + I * dl::TB + r, gc = t0 + J * dl::TB + c;
-            if (gr < n && gc <= gr) {
-              const size_t at = gr + (size_t)gc * n;
-              // S = sigma I + W'W grows while E's columns are eliminated
-              K[at] = (inE && gc >= nzz) ? K[at] + v : K[at] - v;
-            }
+            if (gr < n && gc <= gr) K[gr + (size_t)gc * n] = v;
           });
         }
       __syncthreads();
+      FBS_LAP(5);
       c0 += bs;
     }
     return ok;
@@ -353,10 +448,13 @@ struct DenseLargeProblem : DenseProblem {
       if (tid < bs) ub[tid] = r1[c0 + tid];
       for (int e = tid; e < bs * bs; e += dl::kThreads) {
         const int i = e % bs, j = e / bs;
-        if (i >= j) Db[i + j * dl::DP] = K[(c0 + i) + (size_t)(c0 + j) * n];
+        if (i >= j) dl::cp8(Db + i + j * dl::DP, K + (c0 + i) + (size_t)(c0 + j) * n, true);
       }
+      dl::cp_commit();
+      dl::cp_wait<0>();
       __syncthreads();
     };
+    FBS_LAP(15);
     for (int i = tid; i < nv; i += dl::kThreads) r2[i] = (-rv[i]) / mus[i];
     for (int i = tid; i < nl; i += dl::kThreads) r1[nz + i] = rl[i];
     __syncthreads();
@@ -405,7 +503,9 @@ struct DenseLargeProblem : DenseProblem {
         __syncthreads();
       }
     };
+    FBS_LAP(6);
     forward(0, nz, n);
+    FBS_LAP(7);
     // dl = S^-1 (W'u - c): the tail now holds c - W'u
     for (int i = tid; i < nl; i += dl::kThreads) r1[nz + i] = -r1[nz + i];
     __syncthreads();
@@ -420,7 +520,9 @@ struct DenseLargeProblem : DenseProblem {
       if (lane == 0) r1[j] -= s;
     }
     __syncthreads();
+    FBS_LAP(8);
     backward(0, nz);
+    FBS_LAP(9);
     for (int i = tid; i < nz; i += dl::kThreads) dx.z[i] = r1[i];
     for (int i = tid; i < nl; i += dl::kThreads) dx.l[i] = r1[nz + i];
     __syncthreads();
@@ -432,6 +534,7 @@ struct DenseLargeProblem : DenseProblem {
       dx.y[i] = bvec[i] - s;
     }
     __syncthreads();
+    FBS_LAP(10);
   }
 };
 

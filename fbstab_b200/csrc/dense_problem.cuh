@@ -54,6 +54,7 @@ struct DenseProblem {
 
   // tz = ((f + Hz) + G'l) + A'v ; tl = h - Gz   (full_residual.cc:52-63)
   __device__ void kkt(const Team& t, const Vars& x, double* oz, double* ol) const {
+    FBS_LAP(15);
     for (int i = t.rank(); i < n; i += t.size()) {
       if (i < nz) {
         double s = 0.0;
@@ -67,6 +68,7 @@ struct DenseProblem {
       }
     }
     t.sync();
+    FBS_LAP(11);
     for (int i = t.warp(); i < nz; i += t.nwarps()) {
       double s1 = 0.0, s2 = 0.0;
       const double* g = G + (size_t)i * nl;
@@ -78,6 +80,7 @@ struct DenseProblem {
       if (t.lane() == 0) oz[i] = (oz[i] + s1) + s2;
     }
     t.sync();
+    FBS_LAP(12);
   }
 
   // LinearSolver::Initialize, dense_cholesky_solver.cc:32-79
