@@ -273,7 +273,7 @@ dense_generic_kernel(const __grid_constant__ DenseArgs a) {
   PersistentLoop<DenseArgs, fbs::DenseProblem, SetupDense>(a, a.nz, a.nl, a.nv);
 }
 
-// Large dense QPs (BASELINE config 5): 512 threads per instance, DMMA SYRK and
+// Large dense QPs (BASELINE config 5): 256 threads per instance, DMMA SYRK and
 // blocked Cholesky (dense_large.cuh); the dynamic shared memory is its scratch.
 __device__ inline void SetupDenseLarge(const DenseArgs& a, int inst, double*& ws,
                                        fbs::DenseLargeProblem* p) {
@@ -281,7 +281,7 @@ __device__ inline void SetupDenseLarge(const DenseArgs& a, int inst, double*& ws
   SetupDense(a, inst, ws, p);
   p->sm = dyn_smem;
 }
-__global__ void __launch_bounds__(fbs::dl::kThreads, 1)
+__global__ void __launch_bounds__(fbs::dl::kThreads, 2)
 dense_large_kernel(const __grid_constant__ DenseArgs a) {
   PersistentLoop<DenseArgs, fbs::DenseLargeProblem, SetupDenseLarge>(a, a.nz, a.nl, a.nv);
 }
@@ -634,7 +634,7 @@ int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
   }
   if (h->small.enabled) h->path = h->small.name;
   if (h->large)
-    h->path = "dense-large-cta (512 thr/instance, DMMA A'GammaA + blocked Cholesky NB=64)";
+    h->path = "dense-large-cta (256 thr/instance, 2 CTA/SM, DMMA A'GammaA + blocked Cholesky NB=64)";
   *handle = h;
   return FBSTAB_OK;
 }

@@ -1,5 +1,6 @@
 // dense_large.cuh -- Problem policy for LARGE dense QPs (BASELINE config 5:
-// nz=512, nl=128, nv=1024): one 512-thread CTA per instance, the KKT reduction
+// nz=512, nl=128, nv=1024): one 256-thread CTA per instance, two CTAs per SM
+// (one instance's latency-bound phases overlap the other's DMMA phases), the KKT reduction
 // and its factorisation on the FP64 tensor cores.
 //
 // Follows DenseCholeskySolver (reference dense_cholesky_solver.cc:32-127).
@@ -27,16 +28,17 @@
 namespace fbs {
 namespace dl {
 
-constexpr int kThreads = 512;
-constexpr int TB = 128;  // tile edge of the DMMA products
+constexpr int kThreads = 256;  // two CTAs (= two instances) per SM
+constexpr int TB = 128;   // tile rows of the DMMA products
+constexpr int TBN = 64;   // tile columns
 constexpr int KC = 16;   // depth of one staged chunk
 constexpr int KP = 20;   // padded depth stride in shared memory (conflict-free fragments)
 constexpr int NB = 64;   // Cholesky block
 constexpr int DP = NB + 1;
-constexpr int TR = 256;  // rows of one panel-solve tile
+constexpr int TR = 128;  // rows of one panel-solve tile
 // shared-memory carve (doubles)
 constexpr int kStages = 3;                      // cp.async ring depth
-constexpr int kStageDoubles = 2 * TB * KP + KC;  // two operand chunks + Gamma
+constexpr int kStageDoubles = (TB + TBN) * KP + KC;  // two operand chunks + Gamma
 constexpr int kStage = kStages * kStageDoubles;
 constexpr int kDiag = NB * DP + NB;             // diagonal block + its pivots
 constexpr int kPanel = TR * NB;
@@ -70,20 +72,26 @@ __device__ __forceinline__ void cp_wait() {
 // per thread are all in flight while the first operand chunks arrive, instead
 // of 32 dependent load -> store round trips after the product.
 // AddrI / AddrJ: (idx in [0,128), k in [0,depth)) -> global address of the
-// element, or nullptr outside the matrix (zero filled).  The 16 warps form a
-// 4x4 grid; warp (wm,wn) owns rows 32wm.., cols 32wn.. as 4x4 m8n8 DMMA tiles.
-// `same`: opJ == opI (diagonal tile).  Operand chunks travel global -> shared
+// element, or nullptr outside the matrix (zero filled).  A tile is 128 x 64;
+// the 8 warps form a 4x2 grid, warp (wm,wn) owns rows 32wm.., cols 32wn.. as
+// 4x4 m8n8 DMMA tiles.  `j_alias` >= 0: the J operand rows are rows
+// j_alias.. of the I operand (tiles on the diagonal), nothing extra is staged.
+// `active` false: this warp's 32x32 part lies strictly above the diagonal; it
+// only helps staging.  (Measured and rejected, tools/probes/dmma_probe.cu and
+// profiles/r1_dense_large_phases.txt: 16-byte cp.async with a row-pair thread
+// mapping, a k-major trailing layout, TMA bulk row copies, register staging.)
+// Operand chunks travel global -> shared
 // as cp.async copies through a kStages-deep ring, two chunks ahead of the
 // DMMAs, with one barrier per chunk.
 template <int MODE, class AddrI, class AddrJ>
 __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], double* sm, int depth,
-                                         AddrI ai, AddrJ aj, const double* scale, bool same,
-                                         const double (&csgn)[4]) {
+                                         AddrI ai, AddrJ aj, const double* scale, int j_alias,
+                                         bool active, const double (&csgn)[4]) {
   constexpr bool SCALED = (MODE == 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r8 = lane >> 2, c4 = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;
-  const int sidx = 8 * warp + r8;  // staging: this thread's tile row/col index
+  const int wm = warp >> 1, wn = warp & 1;
+  const int sidx = 8 * warp + r8;  // staging: this thread's tile row/col index (0..63)
   const int nchunk = (depth + KC - 1) / KC;
   auto issue = [&](int ch) {
     if (ch < nchunk) {
@@ -93,15 +101,20 @@ __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], double* sm, int
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int k = k0 + 4 * q + c4;
-        const double* pi = (k < depth) ? ai(sidx, k) : nullptr;
-        cp8(SI + sidx * KP + 4 * q + c4, pi ? pi : scale, pi != nullptr);
-        if (!same) {
+#pragma unroll
+        for (int hh = 0; hh < TB / 64; hh++) {
+          const int idx = 64 * hh + sidx;
+          const double* pi = (k < depth) ? ai(idx, k) : nullptr;
+          cp8(SI + idx * KP + 4 * q + c4, pi ? pi : scale, pi != nullptr);
+        }
+        if (j_alias < 0) {
           const double* pj = (k < depth) ? aj(sidx, k) : nullptr;
           cp8(SJ + sidx * KP + 4 * q + c4, pj ? pj : scale, pj != nullptr);
         }
       }
       if (SCALED && tid < KC)
-        cp8(SI + 2 * TB * KP + tid, scale + (k0 + tid < depth ? k0 + tid : 0), k0 + tid < depth);
+        cp8(SI + (TB + TBN) * KP + tid, scale + (k0 + tid < depth ? k0 + tid : 0),
+            k0 + tid < depth);
     }
     cp_commit();
   };
@@ -111,9 +124,10 @@ __device__ __forceinline__ void mma_tile(double (&acc)[4][4][2], double* sm, int
     cp_wait<1>();     // this thread's copies of chunk ch have landed
     __syncthreads();  // everyone's have; everyone is done with chunk ch-1
     issue(ch + 2);    // into the buffer chunk ch-1 used
+    if (!active) continue;  // sub-tile strictly above the diagonal: nothing to compute
     const double* SI = sm + (ch % kStages) * kStageDoubles;
-    const double* SJ = same ? SI : SI + TB * KP;
-    const double* SG = SI + 2 * TB * KP;
+    const double* SJ = (j_alias >= 0) ? SI + j_alias * KP : SI + TB * KP;
+    const double* SG = SI + (TB + TBN) * KP;
 #pragma unroll
     for (int kk = 0; kk < KC / 4; kk++) {
       double af[4], bf[4];
@@ -140,7 +154,7 @@ template <class F>
 __device__ __forceinline__ void for_each_acc(const double (&acc)[4][4][2], F f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r8 = lane >> 2, c4 = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp >> 1, wn = warp & 1;
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -156,7 +170,7 @@ template <class F>
 __device__ __forceinline__ void init_acc(double (&acc)[4][4][2], F f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r8 = lane >> 2, c4 = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp >> 1, wn = warp & 1;
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -318,27 +332,30 @@ struct DenseLargeProblem : DenseProblem {
       const double* Ap = A;
       const int nvv = nv, nzz = nz;
       for (int I = 0; I * dl::TB < nz; I++)
-        for (int J = 0; J <= I; J++) {
+        for (int J = 0; J * dl::TBN < nz && J * dl::TBN < (I + 1) * dl::TB; J++) {
           double acc[4][4][2];
           auto li = [=](int idx, int k) -> const double* {
             const int c = I * dl::TB + idx;
             return c < nzz ? Ap + k + (size_t)c * nvv : nullptr;
           };
           auto lj = [=](int idx, int k) -> const double* {
-            const int c = J * dl::TB + idx;
+            const int c = J * dl::TBN + idx;
             return c < nzz ? Ap + k + (size_t)c * nvv : nullptr;
           };
           const double* Hp = H;
           dl::init_acc(acc, [&](int r, int c) -> double {
-            const int gr = I * dl::TB + r, gc = J * dl::TB + c;
+            const int gr = I * dl::TB + r, gc = J * dl::TBN + c;
             return (gr < nzz && gc <= gr)
                        ? __ldg(Hp + gr + (size_t)gc * nzz) + (gr == gc ? sigma : 0.0)
                        : 0.0;
           });
           const double one[4] = {1.0, 1.0, 1.0, 1.0};
-          dl::mma_tile<1>(acc, sm, nv, li, lj, Gam, I == J, one);
+          const int off = J * dl::TBN - I * dl::TB;  // >= 0: a tile on the diagonal
+          const int wm = (tid >> 5) >> 1, wn = (tid >> 5) & 1;
+          const bool active = off + 32 * wn <= 32 * wm + 31;
+          dl::mma_tile<1>(acc, sm, nv, li, lj, Gam, off >= 0 ? off : -1, active, one);
           dl::for_each_acc(acc, [&](int r, int c, double v) {
-            const int gr = I * dl::TB + r, gc = J * dl::TB + c;
+            const int gr = I * dl::TB + r, gc = J * dl::TBN + c;
             if (gr < nz && gc <= gr) K[gr + (size_t)gc * n] = v;
           });
         }
@@ -369,34 +386,37 @@ struct DenseLargeProblem : DenseProblem {
       const double* Kp = K;
       const int nn = n, nzz = nz;
       for (int I = 0; t0 + I * dl::TB < n; I++)
-        for (int J = 0; J <= I; J++) {
+        for (int J = 0; t0 + J * dl::TBN < n && J * dl::TBN < (I + 1) * dl::TB; J++) {
           double acc[4][4][2];
           auto li = [=](int idx, int k) -> const double* {
             const int r = t0 + I * dl::TB + idx;
             return r < nn ? Kp + r + (size_t)(c0 + k) * nn : nullptr;
           };
           auto lj = [=](int idx, int k) -> const double* {
-            const int r = t0 + J * dl::TB + idx;
+            const int r = t0 + J * dl::TBN + idx;
             return r < nn ? Kp + r + (size_t)(c0 + k) * nn : nullptr;
           };
           dl::init_acc(acc, [&](int r, int c) -> double {
-            const int gr = t0 + I * dl::TB + r, gc = t0 + J * dl::TB + c;
+            const int gr = t0 + I * dl::TB + r, gc = t0 + J * dl::TBN + c;
             return (gr < nn && gc <= gr) ? Kp[gr + (size_t)gc * nn] : 0.0;
           });
           // S = sigma I + W'W grows while E's columns are eliminated; everything
           // else shrinks: the sign rides on the B operand's column
           double csgn[4];
+          const int wm = (tid >> 5) >> 1, wn = (tid >> 5) & 1;
           {
-            const int lane = tid & 31, wn = (tid >> 5) & 3;
+            const int lane = tid & 31;
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-              const int gc = t0 + J * dl::TB + 32 * wn + 8 * b + (lane >> 2);
+              const int gc = t0 + J * dl::TBN + 32 * wn + 8 * b + (lane >> 2);
               csgn[b] = (inE && gc >= nzz) ? 1.0 : -1.0;
             }
           }
-          dl::mma_tile<2>(acc, sm, bs, li, lj, Kp, I == J, csgn);
+          const int off = J * dl::TBN - I * dl::TB;
+          const bool active = off + 32 * wn <= 32 * wm + 31;
+          dl::mma_tile<2>(acc, sm, bs, li, lj, Kp, off >= 0 ? off : -1, active, csgn);
           dl::for_each_acc(acc, [&](int r, int c, double v) {
-            const int gr = t0 + I * dl::TB + r, gc = t0 + J * dl::TB + c;
+            const int gr = t0 + I * dl::TB + r, gc = t0 + J * dl::TBN + c;
             if (gr < n && gc <= gr) K[gr + (size_t)gc * n] = v;
           });
         }

@@ -11,14 +11,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
-lib = os.path.join(ROOT, "build", "libfbstab_b200_phases.so")
+tbn = "64"
+if "--tbn" in sys.argv:
+    i = sys.argv.index("--tbn")
+    tbn = sys.argv[i + 1]
+    del sys.argv[i:i + 2]
+lib = os.path.join(ROOT, "build", f"libfbstab_b200_phases{tbn}.so")
 if "--build" in sys.argv or not os.path.exists(lib):
     objs = []
     procs = []
     for src in g.CUDA_SOURCES + g.HOST_SOURCES:
-        obj = os.path.join(ROOT, "build", "ph_" + src + ".o")
+        obj = os.path.join(ROOT, "build", f"ph{tbn}_" + src + ".o")
         objs.append(obj)
-        procs.append(subprocess.Popen(["nvcc"] + g.NVCC_FLAGS + ["-DFBSTAB_PHASE_TIMERS", "-c",
+        procs.append(subprocess.Popen(["nvcc"] + g.NVCC_FLAGS + ["-DFBSTAB_PHASE_TIMERS", "-DFBS_DL_TBN=" + tbn, "-c",
                                       os.path.join(g.CSRC, src), "-o", obj]))
     assert all(p.wait() == 0 for p in procs)
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared",
