@@ -6,6 +6,7 @@
 // their CTA for the next instance -- no host round trips, no per-iteration
 // launches, natural load balance over the 9..28-iteration spread.
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -185,6 +186,19 @@ struct DenseArgs {
   CommonArgs c;
 };
 
+// dense_large_kernel: the same block plus the batch-wide TMA tensor map of A
+struct DenseLargeArgs {
+  int nz, nl, nv;
+  const double *H, *f, *G, *h, *A, *b;
+  CommonArgs c;
+  int use_tma;  // 0: cp.async operand staging
+  int inst0;    // index of this launch's first instance in the tensor map
+  double* xt;   // row-major panel copies, xt_rows x NB doubles per CTA (or nullptr)
+  int xt_rows;
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmX;
+};
+
 __host__ __device__ inline size_t VecDoubles(int nz, int nl, int nv) {
   return 4 * (size_t)(nz + nl + 2 * nv) + (size_t)(nz + nl + nv);
 }
@@ -209,8 +223,9 @@ __device__ inline void CarveBuffers(double*& p, int nz, int nl, int nv,
   w->ri.v = Carve(p, nv);
 }
 
-__device__ inline void SetupDense(const DenseArgs& a, int inst, double*& ws,
-                                  fbs::DenseProblem* p) {
+template <class Args>
+__device__ inline void SetupDenseT(const Args& a, int inst, double*& ws,
+                                   fbs::DenseProblem* p) {
   p->nz = a.nz;
   p->nl = a.nl;
   p->nv = a.nv;
@@ -228,6 +243,10 @@ __device__ inline void SetupDense(const DenseArgs& a, int inst, double*& ws,
   p->mus = Carve(ws, a.nv);
   p->tmp = Carve(ws, p->n);
   p->tz = Carve(ws, a.nz);
+}
+__device__ inline void SetupDense(const DenseArgs& a, int inst, double*& ws,
+                                  fbs::DenseProblem* p) {
+  SetupDenseT(a, inst, ws, p);
 }
 size_t DenseWsDoubles(int nz, int nl, int nv) {
   const size_t n = nz + nl;
@@ -275,15 +294,91 @@ dense_generic_kernel(const __grid_constant__ DenseArgs a) {
 
 // Large dense QPs (BASELINE config 5): 256 threads per instance, DMMA SYRK and
 // blocked Cholesky (dense_large.cuh); the dynamic shared memory is its scratch.
-__device__ inline void SetupDenseLarge(const DenseArgs& a, int inst, double*& ws,
+// Dynamic shared memory of dense_large_kernel: [SmemHeader | pad to 1024 B | scratch]
+constexpr size_t kDenseLargeSmem = sizeof(double) * fbs::dl::kSmemDoubles + 2048;
+__device__ inline double* DenseLargeScratch(double* dyn) {
+  const size_t a = ((size_t)(dyn + 8) + 1023) & ~(size_t)1023;
+  return (double*)a;
+}
+__device__ inline void SetupDenseLarge(const DenseLargeArgs& a, int inst, double*& ws,
                                        fbs::DenseLargeProblem* p) {
   extern __shared__ double dyn_smem[];
-  SetupDense(a, inst, ws, p);
-  p->sm = dyn_smem;
+  SetupDenseT(a, inst, ws, p);
+  p->hdr = (fbs::dl::SmemHeader*)dyn_smem;
+  p->sm = DenseLargeScratch(dyn_smem);
+  p->tmA = a.use_tma ? (const void*)&a.tmA : nullptr;
+  p->tma_row0 = (a.inst0 + inst) * a.nz;
+  if (a.use_tma && a.xt) {
+    p->tmX = (const void*)&a.tmX;
+    p->xt = a.xt + (size_t)blockIdx.x * a.xt_rows * fbs::dl::NB;
+    p->xt_row0 = blockIdx.x * a.xt_rows;
+  }
 }
 __global__ void __launch_bounds__(fbs::dl::kThreads, 2)
-dense_large_kernel(const __grid_constant__ DenseArgs a) {
-  PersistentLoop<DenseArgs, fbs::DenseLargeProblem, SetupDenseLarge>(a, a.nz, a.nl, a.nv);
+dense_large_kernel(const __grid_constant__ DenseLargeArgs a) {
+  extern __shared__ double dyn_smem[];
+  if (threadIdx.x == 0) {
+    fbs::dl::SmemHeader* hdr = (fbs::dl::SmemHeader*)dyn_smem;
+    for (int s = 0; s < fbs::dl::kStages; s++)
+      fbs::tma::mbar_init(fbs::tma::smem_addr(&hdr->full[s]), 1);
+    hdr->seq = 0;
+    fbs::tma::fence_mbar_init();
+  }
+  __syncthreads();
+  PersistentLoop<DenseLargeArgs, fbs::DenseLargeProblem, SetupDenseLarge>(a, a.nz, a.nl, a.nv);
+}
+
+DenseLargeArgs ToLarge(const DenseArgs& a) {
+  DenseLargeArgs r;
+  memset(&r, 0, sizeof(r));
+  r.nz = a.nz;
+  r.nl = a.nl;
+  r.nv = a.nv;
+  r.H = a.H;
+  r.f = a.f;
+  r.G = a.G;
+  r.h = a.h;
+  r.A = a.A;
+  r.b = a.b;
+  r.c = a.c;
+  return r;
+}
+
+// Batch-wide tensor map of A (column-major nv x nz per instance, instance-major):
+// dim0 = k (nv, contiguous), dim1 = batch * nz columns; box 16 x 64, 128B swizzle.
+// Returns false when the shape / alignment rules of the TMA engine are not met
+// or the driver entry point is unavailable: the kernel then stages with cp.async.
+bool EncodeTensorMapRows(CUtensorMap* tm, const double* base, int inner, long long rows);
+bool EncodeTensorMapA(CUtensorMap* tm, const double* A, int nv, int nz, int batch) {
+  return EncodeTensorMapRows(tm, A, nv, (long long)batch * nz);
+}
+// 2-D map of `rows` rows of `inner` contiguous doubles each.
+bool EncodeTensorMapRows(CUtensorMap* tm, const double* A, int nv, long long rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                               const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
+            cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return (EncodeFn) nullptr;
+    }
+    return (EncodeFn)p;
+  }();
+  if (!fn || (nv & 1) || nv < fbs::dl::KC || ((size_t)A & 15) || rows > 0x7fffffffLL)
+    return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)nv, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)nv * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)fbs::dl::KC, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A, gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---- handles ----------------------------------------------------------------
@@ -307,7 +402,7 @@ struct HandleBase {
   int last_launches = 0;
   const char* path = "generic";
   // host-buffer pipeline: copy-in / copy-out streams and per-chunk events
-  static constexpr int kMaxChunks = 8;
+  static constexpr int kMaxChunks = 32;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
 
@@ -444,6 +539,11 @@ int SetOptions(HandleBase* h, const fbstab_options* o) {
 struct fbstab_dense_batch : HandleBase {
   fbs::DenseSmallPlan small;
   bool large = false;
+  // large path: row-major panel copies for the TMA-staged trailing updates
+  double* xt = nullptr;
+  int xt_rows = 0;
+  bool xt_map = false;
+  CUtensorMap tmX;
 };
 struct fbstab_mpc_batch : HandleBase {
   int N = 0, nx = 0, nu = 0, nc = 0;
@@ -619,8 +719,7 @@ int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
   h->large = nz >= EnvInt("FBSTAB_DENSE_LARGE_MIN", 128) && !EnvInt("FBSTAB_FORCE_GENERIC", 0);
   int rc = h->large
                ? InitCommon(h, device, max_batch, (const void*)dense_large_kernel,
-                            DenseWsDoubles(nz, nl, nv), fbs::dl::kThreads,
-                            sizeof(double) * fbs::dl::kSmemDoubles)
+                            DenseWsDoubles(nz, nl, nv), fbs::dl::kThreads, kDenseLargeSmem)
                : InitCommon(h, device, max_batch, (const void*)dense_generic_kernel,
                             DenseWsDoubles(nz, nl, nv), block);
   if (rc == FBSTAB_OK && !EnvInt("FBSTAB_FORCE_GENERIC", 0))
@@ -633,6 +732,19 @@ int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
     return rc;
   }
   if (h->small.enabled) h->path = h->small.name;
+  if (h->large && !h->small.enabled && EnvInt("FBSTAB_DENSE_LARGE_TMA", 1)) {
+    // one panel copy (rows of K x NB) per resident CTA, rows padded to the tile height
+    h->xt_rows = (n + fbs::dl::TB - 1) / fbs::dl::TB * fbs::dl::TB;
+    const size_t bytes = (size_t)h->grid_max * h->xt_rows * fbs::dl::NB * sizeof(double);
+    if (cudaMalloc(&h->xt, bytes) == cudaSuccess) {
+      cudaMemset(h->xt, 0, bytes);
+      h->xt_map = EncodeTensorMapRows(&h->tmX, h->xt, fbs::dl::NB,
+                                      (long long)h->grid_max * h->xt_rows);
+    } else {
+      cudaGetLastError();
+      h->xt = nullptr;
+    }
+  }
   if (h->large)
     h->path = "dense-large-cta (256 thr/instance, 2 CTA/SM, DMMA A'GammaA + blocked Cholesky NB=64)";
   *handle = h;
@@ -653,6 +765,10 @@ extern "C" int fbstab_debug_phase_cycles(unsigned long long* out32, int reset) {
 
 int fbstab_dense_batch_destroy(fbstab_dense_batch* h) {
   if (!h) return FBSTAB_OK;
+  if (h->xt) {
+    cudaSetDevice(h->device);
+    cudaFree(h->xt);
+  }
   h->FreeAll();
   delete h;
   return FBSTAB_OK;
@@ -720,6 +836,10 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
   if ((rc = st.InOut(&h->out_buf, out, B * sizeof(fbstab_out), false,
                      (void**)&a.c.out)))
     return rc;
+  // TMA operand staging of the large path: one tensor map over A of the whole batch
+  CUtensorMap tmA;
+  const bool use_tma = h->large && !h->small.enabled && EnvInt("FBSTAB_DENSE_LARGE_TMA", 1) &&
+                       EncodeTensorMapA(&tmA, a.A, h->nv, h->nz, batch);
   auto launch = [&](int lo, int n) -> int {
     DenseArgs c = a;
     c.H += (size_t)lo * nz * nz;
@@ -740,16 +860,28 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
         return Fail(FBSTAB_ERR_CUDA, "dense small-path launch failed");
     } else {
       const int grid = std::min(n, h->grid_max);
-      if (h->large)
-        dense_large_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(c);
-      else
+      if (h->large) {
+        DenseLargeArgs cl = ToLarge(c);
+        cl.A = a.A;  // instances are addressed from the start of the batch (inst0)
+        cl.A += (size_t)lo * nv * nz;
+        cl.use_tma = use_tma ? 1 : 0;
+        cl.inst0 = lo;
+        if (use_tma) cl.tmA = tmA;
+        if (use_tma && h->xt_map) {
+          cl.xt = h->xt;
+          cl.xt_rows = h->xt_rows;
+          cl.tmX = h->tmX;
+        }
+        dense_large_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(cl);
+      } else {
         dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(c);
+      }
     }
     CUDA_TRY(cudaGetLastError());
     return FBSTAB_OK;
   };
   const int capacity = h->small.enabled ? h->small.grid * fbs::DenseSmallWarpsPerCta() : h->grid_max;
-  if ((rc = RunPipelined(h, &st, batch, 8 * capacity, launch))) return rc;
+  if ((rc = RunPipelined(h, &st, batch, 4 * capacity, launch))) return rc;
   if (st.any_host && !IsDevicePtr(out)) {
     const double sec =
         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -787,7 +919,7 @@ int fbstab_dense_batch_component(fbstab_dense_batch* h, int comp, int batch,
   } else {
     const int grid = std::min(batch, h->grid_max);
     if (h->large)
-      dense_large_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
+      dense_large_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(ToLarge(a));
     else
       dense_generic_kernel<<<grid, h->block, h->dyn_smem, st.stream>>>(a);
   }

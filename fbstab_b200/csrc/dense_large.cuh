@@ -23,7 +23,10 @@
 // shuffles, all warps apply the block column).
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is looked up at run time)
+
 #include "dense_problem.cuh"
+#include "tma.cuh"
 
 namespace fbs {
 namespace dl {
@@ -62,6 +65,101 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- TMA operand staging for A' Gamma A ---------------------------------------
+// One 2-D tensor map covers A of the whole batch (dim0 = k, contiguous, nv long;
+// dim1 = the batch * nz columns of A); a box is 16 k x 64 columns = 64 rows of
+// 128 bytes, 128-byte swizzled, so that the DMMA fragment reads are the
+// 2-wavefront minimum without padding.  One thread issues 2-3 boxes per chunk;
+// the other 255 issue no copy instruction at all (every LDGSTS of the cp.async
+// path costs the FP64 pipe ~35 cycles, tools/probes/dmma_probe.cu: 21.6 ->
+// 17.9 cycles per DMMA with boxes).
+constexpr int kTmaBoxBytes = 64 * 128;
+constexpr int kTmaStageBytes = (TB + TBN) / 64 * kTmaBoxBytes;
+static_assert(kStages * kTmaStageBytes <= kSmemDoubles * 8, "TMA ring must fit the scratch");
+struct SmemHeader {  // first bytes of the dynamic shared memory
+  unsigned long long full[kStages];  // mbarriers: chunk landed
+  unsigned seq;                      // chunks issued so far (slot / parity bookkeeping)
+};
+__device__ __forceinline__ void tma_box(unsigned dst, const void* tmap, int c0, int c1,
+                                        unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ double lds64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+
+// Tile product with TMA-staged operands, both k-contiguous in global memory:
+//   MODE 1: acc += sum_k A(k, rowI + i) Gam(k) A(k, rowJ + j)       (A' Gamma A)
+//   MODE 2: acc += csgn(j) sum_k Xt(rowI + i, k) Xt(rowJ + j, k)    (trailing update; Xt is
+//           the row-major copy of the current panel that the panel solve leaves behind)
+// rowI / rowJ: dim-1 coordinates of the tile's first I / J operand row in the
+// tensor map.  seq: running chunk number (uniform over the CTA).
+template <int MODE>
+__device__ __forceinline__ void tile_tma(double (&acc)[4][4][2], unsigned ring,
+                                         unsigned bar0, const void* tmap, int rowI,
+                                         int rowJ, int j_alias, bool active,
+                                         const double* Gam, const double (&csgn)[4],
+                                         int depth, unsigned& seq) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r8 = lane >> 2, c4 = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int nchunk = (depth + KC - 1) / KC;
+  auto issue = [&](int ch, unsigned sq) {
+    const unsigned slot = sq % kStages;
+    const unsigned bar = bar0 + 8 * slot;
+    const unsigned dst = ring + slot * kTmaStageBytes;
+    tma::mbar_arrive_expect_tx(bar, (j_alias < 0 ? (TB + TBN) : TB) * 128);
+#pragma unroll
+    for (int bx = 0; bx < TB / 64; bx++)
+      tma_box(dst + bx * kTmaBoxBytes, tmap, ch * KC, rowI + 64 * bx, bar);
+    if (j_alias < 0) tma_box(dst + (TB / 64) * kTmaBoxBytes, tmap, ch * KC, rowJ, bar);
+  };
+  if (tid == 0) {
+    issue(0, seq);
+    if (nchunk > 1) issue(1, seq + 1);
+  }
+  for (int ch = 0; ch < nchunk; ch++) {
+    const unsigned sq = seq + ch, slot = sq % kStages;
+    double gk[KC / 4];
+    if (MODE == 1) {
+#pragma unroll
+      for (int kk = 0; kk < KC / 4; kk++) {
+        const int k = ch * KC + 4 * kk + c4;
+        gk[kk] = (k < depth) ? __ldg(Gam + k) : 0.0;
+      }
+    }
+    tma::mbar_wait(bar0 + 8 * slot, (sq / kStages) & 1);  // chunk ch has landed
+    __syncthreads();                                       // everyone is done with chunk ch-1
+    if (tid == 0 && ch + 2 < nchunk) issue(ch + 2, sq + 2);  // into the slot chunk ch-1 used
+    if (!active) continue;
+    const unsigned SI = ring + slot * kTmaStageBytes;
+    const unsigned SJ = (j_alias >= 0) ? SI + j_alias * 128 : SI + (TB / 64) * kTmaBoxBytes;
+#pragma unroll
+    for (int kk = 0; kk < KC / 4; kk++) {
+      // element (row, k) of a box sits at row*128 + (((k/2) ^ (row%8)) * 16) + (k%2)*8
+      const unsigned koff = ((unsigned)((2 * kk + (c4 >> 1)) ^ r8) << 4) | ((unsigned)(c4 & 1) << 3);
+      double af[4], bf[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) af[a] = lds64(SI + (32 * wm + 8 * a + r8) * 128 + koff);
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        bf[b] = (MODE == 1 ? gk[kk] : csgn[b]) * lds64(SJ + (32 * wn + 8 * b + r8) * 128 + koff);
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+  }
+  seq += nchunk;
+  __syncthreads();  // the slots are free for the next tile
 }
 
 // acc(128x128, this warp's 32x32 part) += sum_k opI(i,k) * w * opJ(j,k), where
@@ -184,7 +282,13 @@ __device__ __forceinline__ void init_acc(double (&acc)[4][4][2], F f) {
 }  // namespace dl
 
 struct DenseLargeProblem : DenseProblem {
-  double* sm;  // dl::kSmemDoubles of dynamic shared memory
+  double* sm;  // dl::kSmemDoubles of dynamic shared memory (1024-byte aligned)
+  dl::SmemHeader* hdr = nullptr;  // mbarriers + chunk counter of the TMA ring
+  const void* tmA = nullptr;      // batch-wide tensor map of A, or nullptr (cp.async staging)
+  int tma_row0 = 0;               // dim-1 coordinate of this instance's first column of A
+  const void* tmX = nullptr;      // tensor map of the row-major panel copies, or nullptr
+  double* xt = nullptr;           // this CTA's panel copy Xt[r * NB + k], r = row of K
+  int xt_row0 = 0;                // dim-1 coordinate of this CTA's row 0 in tmX
 
   // In-place lower Cholesky of the bs x bs diagonal block at (c0,c0) of K,
   // right-looking in shared memory; the factor is left in D (stride DP) and
@@ -234,7 +338,8 @@ struct DenseLargeProblem : DenseProblem {
   // once), a thread keeps its half of the row (the x_k with k = half mod 2) in
   // registers through the fully unrolled substitution and stores the result
   // straight to global memory.  Same operation order as the general path.
-  __device__ __noinline__ void panel_solve_full(int c0, const double* D, double* Tm) {
+  __device__ __noinline__ void panel_solve_full(int c0, const double* D, double* Tm,
+                                                double* xt_out) {
     constexpr int BS = dl::NB;
     const int tid = threadIdx.x;
     const int half = tid & 1, rl = tid >> 1;
@@ -270,14 +375,19 @@ struct DenseLargeProblem : DenseProblem {
 #pragma unroll
         for (int m = 0; m < BS / 2; m++)
           K[(r0 + rl) + (size_t)(c0 + 2 * m + half) * n] = x[m];
+        if (xt_out) {  // row-major copy for the TMA-staged trailing update
+#pragma unroll
+          for (int m = 0; m < BS / 2; m++) xt_out[(size_t)(r0 + rl) * BS + 2 * m + half] = x[m];
+        }
       }
       __syncthreads();
     }
   }
 
-  __device__ __noinline__ void panel_solve(int c0, int bs, const double* D, double* Tm) {
+  __device__ __noinline__ void panel_solve(int c0, int bs, const double* D, double* Tm,
+                                           double* xt_out) {
     if (bs == dl::NB) {
-      panel_solve_full(c0, D, Tm);
+      panel_solve_full(c0, D, Tm, xt_out);
       return;
     }
     const int tid = threadIdx.x;
@@ -331,6 +441,14 @@ struct DenseLargeProblem : DenseProblem {
     {
       const double* Ap = A;
       const int nvv = nv, nzz = nz;
+      unsigned seq = 0;
+      if (tmA) {
+        // the scratch was last touched through the generic proxy (panel tiles,
+        // cp.async rings); order those accesses before the TMA engine's writes
+        tma::fence_proxy_async();
+        __syncthreads();
+        seq = hdr->seq;
+      }
       for (int I = 0; I * dl::TB < nz; I++)
         for (int J = 0; J * dl::TBN < nz && J * dl::TBN < (I + 1) * dl::TB; J++) {
           double acc[4][4][2];
@@ -353,12 +471,21 @@ struct DenseLargeProblem : DenseProblem {
           const int off = J * dl::TBN - I * dl::TB;  // >= 0: a tile on the diagonal
           const int wm = (tid >> 5) >> 1, wn = (tid >> 5) & 1;
           const bool active = off + 32 * wn <= 32 * wm + 31;
-          dl::mma_tile<1>(acc, sm, nv, li, lj, Gam, off >= 0 ? off : -1, active, one);
+          if (tmA)
+            dl::tile_tma<1>(acc, tma::smem_addr(sm), tma::smem_addr(hdr->full), tmA,
+                            tma_row0 + I * dl::TB, tma_row0 + J * dl::TBN,
+                            off >= 0 ? off : -1, active, Gam, one, nv, seq);
+          else
+            dl::mma_tile<1>(acc, sm, nv, li, lj, Gam, off >= 0 ? off : -1, active, one);
           dl::for_each_acc(acc, [&](int r, int c, double v) {
             const int gr = I * dl::TB + r, gc = J * dl::TBN + c;
             if (gr < nz && gc <= gr) K[gr + (size_t)gc * n] = v;
           });
         }
+      if (tmA) {
+        __syncthreads();
+        if (tid == 0) hdr->seq = seq;
+      }
     }
     FBS_LAP(1);
     // rows of G below E, and S initialised to sigma I   (:67-69 with the sign of
@@ -379,8 +506,17 @@ struct DenseLargeProblem : DenseProblem {
       const int bs = min(dl::NB, (inE ? nz : n) - c0);
       ok = factor_diag(c0, bs, D, dg) && ok;
       FBS_LAP(3);
-      panel_solve(c0, bs, D, Tm);
+      const bool tmaX = tmX != nullptr && bs == dl::NB;
+      panel_solve(c0, bs, D, Tm, tmaX ? xt : nullptr);
       FBS_LAP(4);
+      unsigned seq = 0;
+      if (tmaX) {
+        // Xt was written with ordinary stores and the scratch through the generic
+        // proxy: order both before the TMA engine's accesses
+        tma::fence_proxy_async_all();
+        __syncthreads();
+        seq = hdr->seq;
+      }
       // trailing update with the panel X = K(c0+bs.., c0..c0+bs)
       const int t0 = c0 + bs;
       const double* Kp = K;
@@ -414,13 +550,19 @@ struct DenseLargeProblem : DenseProblem {
           }
           const int off = J * dl::TBN - I * dl::TB;
           const bool active = off + 32 * wn <= 32 * wm + 31;
-          dl::mma_tile<2>(acc, sm, bs, li, lj, Kp, off >= 0 ? off : -1, active, csgn);
+          if (tmaX)
+            dl::tile_tma<2>(acc, tma::smem_addr(sm), tma::smem_addr(hdr->full), tmX,
+                            xt_row0 + t0 + I * dl::TB, xt_row0 + t0 + J * dl::TBN,
+                            off >= 0 ? off : -1, active, nullptr, csgn, bs, seq);
+          else
+            dl::mma_tile<2>(acc, sm, bs, li, lj, Kp, off >= 0 ? off : -1, active, csgn);
           dl::for_each_acc(acc, [&](int r, int c, double v) {
             const int gr = t0 + I * dl::TB + r, gc = t0 + J * dl::TBN + c;
             if (gr < n && gc <= gr) K[gr + (size_t)gc * n] = v;
           });
         }
       __syncthreads();
+      if (tmaX && tid == 0) hdr->seq = seq;
       FBS_LAP(5);
       c0 += bs;
     }

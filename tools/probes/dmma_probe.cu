@@ -3,6 +3,7 @@
 // (16 independent accumulators, 4+4 fragments per k-step)?
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/dmma_probe tools/probes/dmma_probe.cu
 #include <cstdio>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -39,7 +40,8 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 // traffic of a chunk (8 x 8-byte copies per thread from an L2-resident buffer
 // into a second shared region, wait_group 1); 5: as 4 with generic (non-LDS) loads
 template <int MODE>
-__global__ void probe(double* out, int iters, double a0, double b0, const double* gsrc) {
+__global__ void probe(double* out, int iters, double a0, double b0, const double* gsrc,
+                      const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r8 = lane >> 2, c4 = lane & 3;
@@ -55,16 +57,18 @@ __global__ void probe(double* out, int iters, double a0, double b0, const double
   for (int a = 0; a < 4; a++) { af[a] = a0 + a; bf[a] = b0 + a; }
   const int wm = (warp >> 1) & 3, wn = warp & 1;
   double* ring = sm + 4096;
+  // 1024-byte aligned ring for the swizzled TMA boxes
+  double* tring = (double*)((((size_t)(sm + 4096)) + 1023) & ~(size_t)1023);
   const double* smr = sm;
   if (MODE == 5) {  // defeat the address-space inference: generic loads
     asm volatile("" : "+l"(smr));
   }
   __shared__ unsigned long long bars[3];
   const int nwarps = blockDim.x >> 5;
-  if (MODE == 7) {
+  if (MODE == 7 || MODE == 9) {
     if (threadIdx.x == 0) {
       for (int b = 0; b < 3; b++)
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[b])), "r"(nwarps));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[b])), "r"(MODE == 9 ? 1 : nwarps));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -73,8 +77,25 @@ __global__ void probe(double* out, int iters, double a0, double b0, const double
     if (MODE >= 4 && MODE != 7) {
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     }
+    if (MODE == 9 && it >= 2) mbar_wait((unsigned)__cvta_generic_to_shared(&bars[(it - 2) % 3]), ((it - 2) / 3) & 1);
     if (MODE == 7 && it >= 2) mbar_wait((unsigned)__cvta_generic_to_shared(&bars[(it - 2) % 3]), ((it - 2) / 3) & 1);
     if (MODE >= 3) __syncthreads();
+    if (MODE == 9) {
+      // three 64-row x 16-k boxes (128 B rows, 128B swizzle) per chunk, one thread
+      if (threadIdx.x == 0) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[it % 3]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(3 * 64 * 128) : "memory");
+        double* dst = tring + (it % 3) * 3072;
+#pragma unroll
+        for (int bx = 0; bx < 3; bx++) {
+          const int c0 = 16 * (it & 63), c1 = 64 * bx + 256 * (it & 3);
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+              ::"r"((unsigned)__cvta_generic_to_shared(dst + bx * 1024)), "l"(&tmap), "r"(c0), "r"(c1), "r"(bar)
+              : "memory");
+        }
+      }
+    }
     if (MODE == 7) {
       // 256 rows of 128 B per chunk, spread over the warps' lane 0..7
       double* dst = ring + (it % 3) * 5136;
@@ -147,9 +168,9 @@ __global__ void probe(double* out, int iters, double a0, double b0, const double
 }
 
 template <int MODE>
-void run(int sms, double* out, const double* gsrc) {
+void run(int sms, double* out, const double* gsrc, const CUtensorMap& tmap) {
   const int iters = 2000;
-  const size_t smem = (4096 + 3 * 5136) * sizeof(double);
+  const size_t smem = (4096 + 3 * 5136 + 256) * sizeof(double);
   cudaFuncSetAttribute(probe<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   for (int warps : {8, 16}) {
     const int threads = warps > 32 ? warps * 16 : warps * 32;  // <= 1024 threads per block
@@ -160,7 +181,7 @@ void run(int sms, double* out, const double* gsrc) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
       cudaEventRecord(e0);
-      probe<MODE><<<sms * blocks_per_sm, threads, smem>>>(out, iters, 1.0000001, 1e-9, gsrc);
+      probe<MODE><<<sms * blocks_per_sm, threads, smem>>>(out, iters, 1.0000001, 1e-9, gsrc, tmap);
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
       float ms;
@@ -182,14 +203,27 @@ int main() {
   double* gsrc;
   cudaMalloc(&gsrc, sizeof(double) * 1024 * 1024);
   cudaMemset(gsrc, 0, sizeof(double) * 1024 * 1024);
-  run<0>(prop.multiProcessorCount, out, gsrc);
-  run<1>(prop.multiProcessorCount, out, gsrc);
-  run<2>(prop.multiProcessorCount, out, gsrc);
-  run<3>(prop.multiProcessorCount, out, gsrc);
-  run<4>(prop.multiProcessorCount, out, gsrc);
-  run<5>(prop.multiProcessorCount, out, gsrc);
-  run<6>(prop.multiProcessorCount, out, gsrc);
-  run<7>(prop.multiProcessorCount, out, gsrc);
-  run<8>(prop.multiProcessorCount, out, gsrc);
+  CUtensorMap tmap;
+  {
+    cuInit(0);
+    cuuint64_t gdim[2] = {1024, 1024};           // k (contiguous), rows
+    cuuint64_t gstr[1] = {1024 * sizeof(double)};
+    cuuint32_t box[2] = {16, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = cuTensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, gsrc, gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("cuTensorMapEncodeTiled -> %d\n", (int)r);
+  }
+  run<0>(prop.multiProcessorCount, out, gsrc, tmap);
+  run<1>(prop.multiProcessorCount, out, gsrc, tmap);
+  run<2>(prop.multiProcessorCount, out, gsrc, tmap);
+  run<3>(prop.multiProcessorCount, out, gsrc, tmap);
+  run<4>(prop.multiProcessorCount, out, gsrc, tmap);
+  run<5>(prop.multiProcessorCount, out, gsrc, tmap);
+  run<6>(prop.multiProcessorCount, out, gsrc, tmap);
+  run<7>(prop.multiProcessorCount, out, gsrc, tmap);
+  run<8>(prop.multiProcessorCount, out, gsrc, tmap);
+  run<9>(prop.multiProcessorCount, out, gsrc, tmap);
   return 0;
 }
