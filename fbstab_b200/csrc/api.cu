@@ -377,7 +377,9 @@ bool EncodeTensorMapRows(CUtensorMap* tm, const double* A, int nv, long long row
   const cuuint32_t estr[2] = {1, 1};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A, gdim, gstr, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            EnvInt("FBSTAB_TMA_L2_PROMO", 256) == 256   ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+            : EnvInt("FBSTAB_TMA_L2_PROMO", 256) == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                        : CU_TENSOR_MAP_L2_PROMOTION_NONE,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

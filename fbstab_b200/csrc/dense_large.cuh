@@ -293,7 +293,63 @@ struct DenseLargeProblem : DenseProblem {
   // In-place lower Cholesky of the bs x bs diagonal block at (c0,c0) of K,
   // right-looking in shared memory; the factor is left in D (stride DP) and
   // written back.  false on a pivot <= 0 (Eigen LLT's failure rule).
+  // bs == NB fast path: thread (i, q) = (tid % 64, tid / 64) keeps the entries
+  // (i, q + 4m) of the block in registers; a step publishes the scaled column
+  // through shared memory and every thread updates its own entries.  No
+  // read-modify-write of shared memory, two light barriers per step, and the
+  // same operations in the same order as the general path (bit-identical).
+  __device__ __noinline__ bool factor_diag_full(int c0, double* D, double* dg) {
+    constexpr int BS = dl::NB, NQ = dl::kThreads / 64, NM = BS / NQ;
+    const int tid = threadIdx.x, i = tid & 63, q = tid >> 6;
+    double a[NM];
+#pragma unroll
+    for (int m = 0; m < NM; m++) {
+      const int k = q + NQ * m;
+      a[m] = (k <= i) ? K[(c0 + i) + (size_t)(c0 + k) * n] : 0.0;
+    }
+    double* col = D;  // the block itself is only assembled in D after the loop
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < BS; j++) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int qj = j % NQ, mj = j / NQ;
+      if (i == j && q == qj) {
+        a[mj] = sqrt(a[mj]);
+        dg[0] = a[mj];
+      }
+      __syncthreads();
+      const double sd = dg[0];
+      if (!(sd > 0.0)) ok = false;  // pivot <= 0 or NaN
+      if (q == qj && i > j) {
+        a[mj] = a[mj] / sd;
+        col[i] = a[mj];
+      }
+      __syncthreads();
+      if (i > j) {
+        const double lij = col[i];
+#pragma unroll
+        for (int m = 0; m < NM; m++) {
+          if (NQ * m + NQ - 1 > j) {  // some thread group still has column q + NQ*m > j
+            const int k = q + NQ * m;
+            if (k > j && k <= i) a[m] = fma(-lij, col[k], a[m]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < NM; m++) {
+      const int k = q + NQ * m;
+      D[i + k * dl::DP] = (k <= i) ? a[m] : 0.0;
+      if (k <= i) K[(c0 + i) + (size_t)(c0 + k) * n] = a[m];
+    }
+    __syncthreads();
+    return ok;
+  }
+
   __device__ __noinline__ bool factor_diag(int c0, int bs, double* D, double* dg) {
+    if (bs == dl::NB) return factor_diag_full(c0, D, dg);
     const int tid = threadIdx.x;
     for (int e = tid; e < bs * bs; e += dl::kThreads) {  // all copies in flight at once
       const int i = e % bs, j = e / bs;
