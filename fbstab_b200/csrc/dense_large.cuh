@@ -546,9 +546,20 @@ struct DenseLargeProblem : DenseProblem {
     FBS_LAP(1);
     // rows of G below E, and S initialised to sigma I   (:67-69 with the sign of
     // the Schur complement folded into the updates)
-    for (int e = tid; e < nl * n; e += dl::kThreads) {
-      const int r = e % nl, c = e / nl;
-      K[nz + r + (size_t)c * n] = (c < nz) ? G[r + (size_t)c * nl] : ((c - nz == r) ? sigma : 0.0);
+    for (int e0 = tid; e0 < nl * n; e0 += 8 * dl::kThreads) {  // 8 loads in flight per thread
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + u * dl::kThreads;
+        const int r = e % nl, c = e / nl;
+        t[u] = (e < nl * n && c < nz) ? __ldg(G + r + (size_t)c * nl) : ((c - nz == r) ? sigma : 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + u * dl::kThreads;
+        const int r = e % nl, c = e / nl;
+        if (e < nl * n) K[nz + r + (size_t)c * n] = t[u];
+      }
     }
     __syncthreads();
     FBS_LAP(2);
@@ -711,12 +722,22 @@ struct DenseLargeProblem : DenseProblem {
         __syncthreads();
         if (tid < bs) r1[c0 + tid] = ub[tid];
         // u(j) -= sum_i L(c0+i, j) u(c0+i) for the columns j left of the block
-        for (int j = cbeg + warp; j < c0; j += nw) {
-          const double* col = K + (size_t)j * n + c0;
-          double s = 0.0;
-          for (int i = lane; i < bs; i += 32) s = fma(col[i], ub[i], s);
-          s = warp_sum(s);
-          if (lane == 0) r1[j] -= s;
+        for (int j0 = cbeg + warp; j0 < c0; j0 += 4 * nw) {  // four columns in flight per warp
+          double s[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int i = lane; i < bs; i += 32) {
+            const double ui = ub[i];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int j = j0 + u * nw;
+              if (j < c0) s[u] = fma(K[(size_t)j * n + c0 + i], ui, s[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int j = j0 + u * nw;
+            const double su = warp_sum(s[u]);
+            if (lane == 0 && j < c0) r1[j] -= su;
+          }
         }
         __syncthreads();
       }
@@ -730,12 +751,22 @@ struct DenseLargeProblem : DenseProblem {
     forward(nz, n, n);
     backward(nz, n);
     // u <- u - W dl, W = (K(nz:n, 0:nz))'
-    for (int j = warp; j < nz; j += nw) {
-      const double* col = K + (size_t)j * n + nz;
-      double s = 0.0;
-      for (int i = lane; i < nl; i += 32) s = fma(col[i], r1[nz + i], s);
-      s = warp_sum(s);
-      if (lane == 0) r1[j] -= s;
+    for (int j0 = warp; j0 < nz; j0 += 4 * nw) {
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = lane; i < nl; i += 32) {
+        const double di = r1[nz + i];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u * nw;
+          if (j < nz) s[u] = fma(K[(size_t)j * n + nz + i], di, s[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = j0 + u * nw;
+        const double su = warp_sum(s[u]);
+        if (lane == 0 && j < nz) r1[j] -= su;
+      }
     }
     __syncthreads();
     FBS_LAP(8);
