@@ -2,11 +2,13 @@
 // (nz <= 32, nl <= 8, nv <= 64; BASELINE config 2 is exactly 32/8/64).
 //
 // One warp owns one QP instance for its whole solve:
-//  * the problem matrices (H, A, G: 26 KB) are staged ONCE into the warp's slab
-//    of shared memory (zero padded to 32/8/64, rows contiguous with a padded
-//    leading dimension of 34 so that row reads, column reads and the DMMA
-//    fragment reads are all bank-conflict free or at worst 2-way); every
-//    access uses explicit shared-space instructions (LDS/STS);
+//  * the problem matrices are staged ONCE into the warp's slab of shared memory
+//    (zero padded to 32/8/64): A and G with rows contiguous and a padded
+//    leading dimension of 34, so that row reads, column reads and the DMMA
+//    fragment reads are all bank-conflict free or at worst 2-way; H as its
+//    packed lower triangle (H is symmetric; 4.1 KB instead of 8.5 KB), which is
+//    what lets EIGHT slabs -- two warps per SM sub-partition -- fit the 227 KB
+//    of an SM.  Every access uses explicit shared-space instructions (LDS/STS);
 //  * every iterate / residual vector and f, h, b live in registers: lane j owns
 //    entry j of z-type vectors, lanes 0..7 own l, lane k owns rows k and k+32
 //    of v-type vectors;
@@ -43,11 +45,12 @@ constexpr int NL = 8;
 constexpr int NV = 64;
 constexpr int NVR = NV / 32;
 constexpr int LD = 34;  // leading dimension of Hs/As/Gs rows
-constexpr int kWarps = 7;  // independent warps (= instances in flight) per CTA
+constexpr int kWarps = 8;  // independent warps (= instances in flight) per CTA
 
 // shared-memory layout of one warp's slab (in doubles)
-constexpr int OFF_H = 0;                 // Hs[j + LD*i] = H(i,j)
-constexpr int OFF_A = OFF_H + NZ * LD;   // As[j + LD*k] = A(k,j)
+constexpr int OFF_H = 0;                 // Hp[i(i+1)/2 + j] = H(i,j), j <= i (packed lower)
+constexpr int H_SIZE = NZ * (NZ + 1) / 2;
+constexpr int OFF_A = OFF_H + H_SIZE;    // As[j + LD*k] = A(k,j)
 constexpr int OFF_G = OFF_A + NV * LD;   // Gs[j + LD*r] = G(r,j)
 constexpr int OFF_ZB = OFF_G + NL * LD;  // broadcast copies: z(32) l(8) v(64)
 constexpr int OFF_LB = OFF_ZB + NZ;
@@ -150,7 +153,28 @@ struct Warp {
     }
     return s0 + s1;
   }
-  __device__ __forceinline__ double Hz() const { return row_dot(sb + D(OFF_H + LD * lane)); }
+  // H(i,j) from the packed lower triangle (H(j,i) above the diagonal)
+  __device__ __forceinline__ double Hel(int i, int j) const {
+    const int r = max(i, j), c = min(i, j);
+    return lds(sb + D(OFF_H + (r * (r + 1) >> 1) + c));
+  }
+  // (H zb)[lane]: same terms in the same order as row_dot (even / odd partial sums)
+  __device__ __forceinline__ double Hz() const {
+    const unsigned zb = sb + D(OFF_ZB);
+    const unsigned hrow = sb + D(OFF_H + (lane * (lane + 1) >> 1));  // H(lane, 0..lane)
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NZ; j += 2) {
+      const double2 zz = lds2(zb + D(j));
+      // column part: H(j, lane) for j > lane sits at j(j+1)/2 + lane
+      const double h0 = lds(j <= lane ? hrow + D(j) : sb + D(OFF_H + (j * (j + 1) >> 1) + lane));
+      const double h1 = lds(j + 1 <= lane ? hrow + D(j + 1)
+                                          : sb + D(OFF_H + ((j + 1) * (j + 2) >> 1) + lane));
+      s0 = fma(h0, zz.x, s0);
+      s1 = fma(h1, zz.y, s1);
+    }
+    return s0 + s1;
+  }
   // (G' lb)[lane]
   __device__ __forceinline__ double GTl() const {
     const unsigned gc = sb + D(OFF_G + lane);
@@ -325,9 +349,9 @@ struct Warp {
       for (int I = 0; I < 4; I++)
 #pragma unroll
         for (int J = 0; J <= I; J++) {
-          const double2 hh = lds2(sb + D(OFF_H + LD * (8 * I + r8) + 8 * J + 2 * c4));
-          C[I][J][0] = hh.x + ((I == J && r8 == 2 * c4) ? sigma : 0.0);
-          C[I][J][1] = hh.y + ((I == J && r8 == 2 * c4 + 1) ? sigma : 0.0);
+          const int hr = 8 * I + r8, hc = 8 * J + 2 * c4;
+          C[I][J][0] = Hel(hr, hc) + ((I == J && r8 == 2 * c4) ? sigma : 0.0);
+          C[I][J][1] = Hel(hr, hc + 1) + ((I == J && r8 == 2 * c4 + 1) ? sigma : 0.0);
         }
 #pragma unroll 1
       for (int kc = 0; kc < NV / 4; kc++) {
@@ -512,13 +536,33 @@ struct Warp {
       }
     }
   }
+  // The lower triangle of the column-major nz x nz matrix H into the packed layout.
+  __device__ __forceinline__ void stage_lower(const double* src, int rows) {
+    const int n = rows * rows;
+    for (int e0 = 0; e0 < n; e0 += 256) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + lane + 32 * u;
+        t[u] = (e < n) ? __ldg(src + e) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + lane + 32 * u;
+        if (e < n) {
+          const int c = e / rows, r = e - c * rows;
+          if (r >= c) sts(sb + D(OFF_H + (r * (r + 1) >> 1) + c), t[u]);
+        }
+      }
+    }
+  }
   __device__ __forceinline__ void load(const Args& a_, int inst) {
     __syncwarp();
     if (nz < NZ || nl < NL || nv < NV) {  // zero padding of the unused part
       for (int e = 2 * lane; e < OFF_ZB; e += 64) sts2(sb + D(e), 0.0, 0.0);
       __syncwarp();
     }
-    stage_matrix(a_.H + (size_t)inst * nz * nz, nz, nz, OFF_H);
+    stage_lower(a_.H + (size_t)inst * nz * nz, nz);
     stage_matrix(a_.A + (size_t)inst * nv * nz, nv, nz, OFF_A);
     stage_matrix(a_.G + (size_t)inst * nl * nz, nl, nz, OFF_G);
     fr = (lane < nz) ? __ldg(a_.f + (size_t)inst * nz + lane) : 0.0;

@@ -139,7 +139,9 @@ int fbstab_dense_batch_get_options(const fbstab_dense_batch* handle,
                                    fbstab_options* o);
 /* z,l,v: warm start in, solution out (or the infeasibility certificate, as in
  * fbstab_algorithm-impl.h:209).  y: out only (input ignored, impl:342).
- * stream: a cudaStream_t (NULL = default stream). */
+ * stream: a cudaStream_t (NULL = default stream).
+ * H must be symmetric, as the QP requires (README.md:2-18 of the reference):
+ * the small-problem path (nz <= 32) keeps only its lower triangle on chip. */
 int fbstab_dense_batch_solve(fbstab_dense_batch* handle, int batch,
                              const double* H, const double* f, const double* G,
                              const double* h, const double* A, const double* b,
