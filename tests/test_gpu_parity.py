@@ -458,7 +458,8 @@ def test_dense_config5_sample(fb, oracle):
 
 
 @pytest.mark.parametrize("sizes,B", [((136, 24, 200), 6), ((200, 70, 130), 4),
-                                     ((128, 0, 64), 4), ((257, 65, 300), 3)])
+                                     ((128, 0, 64), 4), ((257, 65, 300), 3),
+                                     ((130, 9, 151), 3)])
 def test_dense_large_path_parity(fb, oracle, sizes, B):
     """The DMMA path (dense_large.cuh) on ragged sizes -- tiles, Cholesky blocks
     and panels all partially filled -- against the oracle's Cholesky + Schur
@@ -507,6 +508,24 @@ def test_dense_large_path_parity(fb, oracle, sizes, B):
     for i in range(B):
         tol = 1e-7 if same[i] else 1e-5
         assert rel_err(z[i * nz:(i + 1) * nz], oz[i * nz:(i + 1) * nz]) <= tol
+
+
+def test_dense_large_tma_equals_cp_async(fb, monkeypatch):
+    """The TMA tensor-map operand staging and the cp.async staging of the large
+    path feed the same DMMAs in the same order: results are bit-identical."""
+    nz, nl, nv, B = 200, 40, 260, 5
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=13)
+    res = []
+    for tma in ("1", "0"):
+        monkeypatch.setenv("FBSTAB_DENSE_LARGE_TMA", tma)
+        s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+        assert s.path.startswith("dense-large"), s.path
+        z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+        out, y = s.solve_batch(d, z, l, v)
+        assert (out["eflag"] == 0).all()
+        res.append((z, l, v, y, out["newton_iters"].copy()))
+    for a, b_ in zip(res[0], res[1]):
+        assert np.array_equal(a, b_)
 
 
 def test_device_pointers_and_stream(fb):
