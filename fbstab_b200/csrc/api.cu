@@ -306,6 +306,7 @@ __device__ inline void SetupDenseLarge(const DenseLargeArgs& a, int inst, double
   SetupDenseT(a, inst, ws, p);
   p->hdr = (fbs::dl::SmemHeader*)dyn_smem;
   p->sm = DenseLargeScratch(dyn_smem);
+  p->rpiv = p->tmp;  // the generic policy's scratch of n doubles
   p->tmA = a.use_tma ? (const void*)&a.tmA : nullptr;
   p->tma_row0 = (a.inst0 + inst) * a.nz;
   if (a.use_tma && a.xt) {

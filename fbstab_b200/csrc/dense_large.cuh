@@ -282,6 +282,7 @@ __device__ __forceinline__ void init_acc(double (&acc)[4][4][2], F f) {
 }  // namespace dl
 
 struct DenseLargeProblem : DenseProblem {
+  double* rpiv = nullptr;  // n reciprocal pivots 1 / L(j,j) of the current factor (global)
   double* sm;  // dl::kSmemDoubles of dynamic shared memory (1024-byte aligned)
   dl::SmemHeader* hdr = nullptr;  // mbarriers + chunk counter of the TMA ring
   const void* tmA = nullptr;      // batch-wide tensor map of A, or nullptr (cp.async staging)
@@ -343,6 +344,11 @@ struct DenseLargeProblem : DenseProblem {
       const int k = q + NQ * m;
       D[i + k * dl::DP] = (k <= i) ? a[m] : 0.0;
       if (k <= i) K[(c0 + i) + (size_t)(c0 + k) * n] = a[m];
+      if (k == i) {  // reciprocal pivot: the substitutions multiply instead of dividing
+        const double rp = 1.0 / a[m];
+        dg[i] = rp;
+        rpiv[c0 + i] = rp;
+      }
     }
     __syncthreads();
     return ok;
@@ -378,7 +384,10 @@ struct DenseLargeProblem : DenseProblem {
       }
       __syncthreads();
     }
-    for (int j = tid; j < bs; j += dl::kThreads) D[j + j * dl::DP] = dg[j];
+    for (int j = tid; j < bs; j += dl::kThreads) {
+      D[j + j * dl::DP] = dg[j];
+      rpiv[c0 + j] = 1.0 / dg[j];
+    }
     __syncthreads();
     for (int e = tid; e < bs * bs; e += dl::kThreads) {
       const int i = e % bs, j = e / bs;
@@ -394,8 +403,8 @@ struct DenseLargeProblem : DenseProblem {
   // once), a thread keeps its half of the row (the x_k with k = half mod 2) in
   // registers through the fully unrolled substitution and stores the result
   // straight to global memory.  Same operation order as the general path.
-  __device__ __noinline__ void panel_solve_full(int c0, const double* D, double* Tm,
-                                                double* xt_out) {
+  __device__ __noinline__ void panel_solve_full(int c0, const double* D, const double* dg,
+                                                double* Tm, double* xt_out) {
     constexpr int BS = dl::NB;
     const int tid = threadIdx.x;
     const int half = tid & 1, rl = tid >> 1;
@@ -424,7 +433,7 @@ struct DenseLargeProblem : DenseProblem {
           s = fma(x[m], ljk, s);
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        const double xj = (x[j >> 1] - s) / D[j + j * dl::DP];
+        const double xj = (x[j >> 1] - s) * dg[j];  // dg: reciprocal pivots
         if (half == (j & 1)) x[j >> 1] = xj;
       }
       if (rl < rows) {
@@ -440,10 +449,10 @@ struct DenseLargeProblem : DenseProblem {
     }
   }
 
-  __device__ __noinline__ void panel_solve(int c0, int bs, const double* D, double* Tm,
-                                           double* xt_out) {
+  __device__ __noinline__ void panel_solve(int c0, int bs, const double* D, const double* dg,
+                                           double* Tm, double* xt_out) {
     if (bs == dl::NB) {
-      panel_solve_full(c0, D, Tm, xt_out);
+      panel_solve_full(c0, D, dg, Tm, xt_out);
       return;
     }
     const int tid = threadIdx.x;
@@ -574,7 +583,7 @@ struct DenseLargeProblem : DenseProblem {
       ok = factor_diag(c0, bs, D, dg) && ok;
       FBS_LAP(3);
       const bool tmaX = tmX != nullptr && bs == dl::NB;
-      panel_solve(c0, bs, D, Tm, tmaX ? xt : nullptr);
+      panel_solve(c0, bs, D, dg, Tm, tmaX ? xt : nullptr);
       FBS_LAP(4);
       unsigned seq = 0;
       if (tmaX) {
@@ -639,8 +648,8 @@ struct DenseLargeProblem : DenseProblem {
   // One warp: solves the bs x bs lower-triangular system Lkk u = a (forward)
   // or Lkk' u = a (backward) for the diagonal block at c0; a, u in shared memory.
   // D: the block staged in shared memory (stride DP).
-  __device__ __forceinline__ void diag_trsv(const double* D, int bs, double* a,
-                                            bool transposed) {
+  __device__ __forceinline__ void diag_trsv(const double* D, const double* rp, int bs,
+                                            double* a, bool transposed) {
     const int lane = threadIdx.x & 31;
     double v0 = (lane < bs) ? a[lane] : 0.0;
     double v1 = (lane + 32 < bs) ? a[lane + 32] : 0.0;
@@ -648,7 +657,7 @@ struct DenseLargeProblem : DenseProblem {
       for (int j = 0; j < bs; j++) {
         const double* col = D + j * dl::DP;
         const double aj = __shfl_sync(0xffffffffu, j < 32 ? v0 : v1, j & 31);
-        const double uj = aj / col[j];
+        const double uj = aj * rp[j];
         if (lane == (j & 31)) (j < 32 ? v0 : v1) = uj;
         if (lane > j && lane < bs) v0 = fma(-col[lane], uj, v0);
         if (lane + 32 > j && lane + 32 < bs) v1 = fma(-col[lane + 32], uj, v1);
@@ -657,7 +666,7 @@ struct DenseLargeProblem : DenseProblem {
       for (int j = bs - 1; j >= 0; j--) {
         // row j of Lkk' is L(j, i), i < j
         const double aj = __shfl_sync(0xffffffffu, j < 32 ? v0 : v1, j & 31);
-        const double uj = aj / D[j + j * dl::DP];
+        const double uj = aj * rp[j];
         if (lane == (j & 31)) (j < 32 ? v0 : v1) = uj;
         if (lane < j) v0 = fma(-D[j + lane * dl::DP], uj, v0);
         if (lane + 32 < j) v1 = fma(-D[j + (lane + 32) * dl::DP], uj, v1);
@@ -673,8 +682,12 @@ struct DenseLargeProblem : DenseProblem {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = dl::kThreads / 32;
     double* ub = sm;           // current block of the right-hand side (NB doubles)
     double* Db = sm + dl::NB;  // its diagonal block of the factor (NB x DP)
+    double* rb = Db + dl::NB * dl::DP;  // reciprocal pivots of the block (NB doubles)
     auto stage_block = [&](int c0, int bs) {
-      if (tid < bs) ub[tid] = r1[c0 + tid];
+      if (tid < bs) {
+        ub[tid] = r1[c0 + tid];
+        rb[tid] = rpiv[c0 + tid];
+      }
       for (int e = tid; e < bs * bs; e += dl::kThreads) {
         const int i = e % bs, j = e / bs;
         if (i >= j) dl::cp8(Db + i + j * dl::DP, K + (c0 + i) + (size_t)(c0 + j) * n, true);
@@ -701,7 +714,7 @@ struct DenseLargeProblem : DenseProblem {
       for (int c0 = cbeg; c0 < cend; c0 += dl::NB) {
         const int bs = min(dl::NB, cend - c0);
         stage_block(c0, bs);
-        if (warp == 0) diag_trsv(Db, bs, ub, false);
+        if (warp == 0) diag_trsv(Db, rb, bs, ub, false);
         __syncthreads();
         if (tid < bs) r1[c0 + tid] = ub[tid];
         for (int r = c0 + bs + tid; r < rend; r += dl::kThreads) {
@@ -718,7 +731,7 @@ struct DenseLargeProblem : DenseProblem {
       for (int c0 = last; c0 >= cbeg; c0 -= dl::NB) {
         const int bs = min(dl::NB, cend - c0);
         stage_block(c0, bs);
-        if (warp == 0) diag_trsv(Db, bs, ub, true);
+        if (warp == 0) diag_trsv(Db, rb, bs, ub, true);
         __syncthreads();
         if (tid < bs) r1[c0 + tid] = ub[tid];
         // u(j) -= sum_i L(c0+i, j) u(c0+i) for the columns j left of the block
