@@ -23,9 +23,42 @@ namespace fbs {
 
 // ---- small dense helpers (column-major, ld = rows), team-cooperative -------
 
+// Convention of every Cholesky factor in this file (and in mpc_lane.cu): the
+// diagonal slot holds the RECIPROCAL of the pivot, so that the ~40 dependent
+// divisions per stage of the triangular solves become multiplications (an FP64
+// division is a chain of ~12 dependent operations).  Results differ from the
+// dividing form by rounding only.
+//
+// Systems of at most 32 rows are factored and solved by ONE warp with
+// warp-level synchronisation (the team's other warps wait at a single barrier
+// afterwards): the team versions needed two CTA barriers per Cholesky column
+// and one per substitution step, ~260 barriers per stage and Newton step at
+// nx = 18, and the kernel spent most of its time in them
+// (profiles/r1_mpc_cta_barriers.txt).
+
 // In-place lower Cholesky (Eigen LLT unblocked order).  false on pivot <= 0.
 __device__ __forceinline__ bool team_chol(const Team& t, int T, double* M, int m) {
   bool ok = true;
+  if (m <= 32) {
+    if (t.warp() == 0) {
+      const int lane = t.lane();
+      for (int k = 0; k < m; k++) {
+        // lane i >= k: a = sum_{j<k} M(i,j) M(k,j)   (lane k: the pivot's own sum)
+        double a = 0.0;
+        if (lane >= k && lane < m)
+          for (int j = 0; j < k; j++) a = fma(M[lane + j * m], M[k + j * m], a);
+        const double v = (lane >= k && lane < m) ? M[lane + k * m] : 0.0;
+        const double x = __shfl_sync(0xffffffffu, v - a, k);
+        if (!(x > 0.0)) ok = false;
+        const double rx = 1.0 / sqrt(x);
+        if (lane > k && lane < m) M[lane + k * m] = (v - a) * rx;
+        if (lane == k) M[k + k * m] = rx;
+        __syncwarp();
+      }
+    }
+    ok = __syncthreads_and(ok);
+    return ok;
+  }
   for (int k = 0; k < m; k++) {
     double s = 0.0;
     for (int j = 0; j < k; j++) {
@@ -34,24 +67,38 @@ __device__ __forceinline__ bool team_chol(const Team& t, int T, double* M, int m
     }
     double x = M[k + k * m] - s;
     if (!(x > 0.0)) ok = false;
-    x = sqrt(x);
+    const double rx = 1.0 / sqrt(x);
     for (int i = k + 1 + t.rank(); i < m; i += T) {
       double a = 0.0;
       for (int j = 0; j < k; j++) a = fma(M[i + j * m], M[k + j * m], a);
-      M[i + k * m] = (M[i + k * m] - a) / x;
+      M[i + k * m] = (M[i + k * m] - a) * rx;
     }
     t.sync();
-    if (t.rank() == 0) M[k + k * m] = x;  // after everyone has read the old pivot
+    if (t.rank() == 0) M[k + k * m] = rx;  // after everyone has read the old pivot
   }
   t.sync();
   return ok;
 }
 
-// y <- L^-1 x (lower, non-unit, column oriented).  x is destroyed.
+// y <- L^-1 x (lower, reciprocal diagonal, column oriented).  x is destroyed.
 __device__ __forceinline__ void trsv_l(const Team& t, int T, const double* L, int m, double* x,
                               double* y) {
+  if (m <= 32) {
+    if (t.warp() == 0) {
+      const int lane = t.lane();
+      double xi = (lane < m) ? x[lane] : 0.0;
+      for (int j = 0; j < m; j++) {
+        const double xj = __shfl_sync(0xffffffffu, xi, j) * L[j + j * m];
+        if (lane == j) xi = xj;
+        if (lane > j && lane < m) xi = fma(-L[lane + j * m], xj, xi);
+      }
+      if (lane < m) y[lane] = xi;
+    }
+    t.sync();
+    return;
+  }
   for (int j = 0; j < m; j++) {
-    const double xj = x[j] / L[j + j * m];
+    const double xj = x[j] * L[j + j * m];
     if (t.rank() == 0) y[j] = xj;
     for (int i = j + 1 + t.rank(); i < m; i += T)
       x[i] = fma(-L[i + j * m], xj, x[i]);
@@ -61,8 +108,22 @@ __device__ __forceinline__ void trsv_l(const Team& t, int T, const double* L, in
 // y <- L^-T x.  x is destroyed.
 __device__ __forceinline__ void trsv_lt(const Team& t, int T, const double* L, int m, double* x,
                                double* y) {
+  if (m <= 32) {
+    if (t.warp() == 0) {
+      const int lane = t.lane();
+      double xr = (lane < m) ? x[lane] : 0.0;
+      for (int i = m - 1; i >= 0; i--) {
+        const double xi = __shfl_sync(0xffffffffu, xr, i) * L[i + i * m];
+        if (lane == i) xr = xi;
+        if (lane < i) xr = fma(-L[i + lane * m], xi, xr);
+      }
+      if (lane < m) y[lane] = xr;
+    }
+    t.sync();
+    return;
+  }
   for (int i = m - 1; i >= 0; i--) {
-    const double xi = x[i] / L[i + i * m];
+    const double xi = x[i] * L[i + i * m];
     if (t.rank() == 0) y[i] = xi;
     for (int r = t.rank(); r < i; r += T)
       x[r] = fma(-L[i + r * m], xi, x[r]);
@@ -76,7 +137,7 @@ __device__ __forceinline__ void row_trsm_lt(const double* L, int m,
   for (int j = 0; j < m; j++) {
     double s = src[r + j * rows];
     for (int k = 0; k < j; k++) s = fma(-X[r + k * rows], L[j + k * m], s);
-    X[r + j * rows] = s / L[j + j * m];
+    X[r + j * rows] = s * L[j + j * m];
   }
 }
 
@@ -396,7 +457,7 @@ struct MpcProblem {
     }
     // L(0) = sqrt(sigma) I, :127
     {
-      const double rs = sqrt(sigma);
+      const double rs = 1.0 / sqrt(sigma);  // reciprocal-diagonal convention
       double* L0 = block(0) + fo.L;
       for (int e = t.rank(); e < nxx; e += T) L0[e] = (e % nx == e / nx) ? rs : 0.0;
     }
@@ -446,14 +507,14 @@ struct MpcProblem {
           double* w = Linv + (size_t)cc * nx;
           for (int k = 0; k < nx; k++) w[k] = (k == cc) ? 1.0 : 0.0;
           for (int j = 0; j < nx; j++) {
-            w[j] /= Li[j + j * nx];
+            w[j] *= Li[j + j * nx];
             const double wj = w[j];
             for (int k = j + 1; k < nx; k++) w[k] = fma(-Li[k + j * nx], wj, w[k]);
           }
           for (int k = nx - 1; k >= 0; k--) {
             double s = w[k];
             for (int j = k + 1; j < nx; j++) s = fma(-Li[j + k * nx], w[j], s);
-            w[k] = s / Li[k + k * nx];
+            w[k] = s * Li[k + k * nx];
           }
         }
       }
