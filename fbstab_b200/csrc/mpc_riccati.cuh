@@ -42,16 +42,23 @@ __device__ __forceinline__ bool team_chol(const Team& t, int T, double* M, int m
   if (m <= 32) {
     if (t.warp() == 0) {
       const int lane = t.lane();
+      // lane i keeps the running diagonal M(i,i) - sum_{j<k} M(i,j)^2 in a
+      // register, so the pivot chain of a step is one FMA, the reciprocal
+      // square root, a shuffle and a multiply; the column's dot products do not
+      // depend on the pivot and overlap with it
+      double diag = (lane < m) ? M[lane + lane * m] : 1.0;
       for (int k = 0; k < m; k++) {
-        // lane i >= k: a = sum_{j<k} M(i,j) M(k,j)   (lane k: the pivot's own sum)
         double a = 0.0;
-        if (lane >= k && lane < m)
+        if (lane > k && lane < m)
           for (int j = 0; j < k; j++) a = fma(M[lane + j * m], M[k + j * m], a);
-        const double v = (lane >= k && lane < m) ? M[lane + k * m] : 0.0;
-        const double x = __shfl_sync(0xffffffffu, v - a, k);
+        const double x = __shfl_sync(0xffffffffu, diag, k);
         if (!(x > 0.0)) ok = false;
-        const double rx = 1.0 / sqrt(x);
-        if (lane > k && lane < m) M[lane + k * m] = (v - a) * rx;
+        const double rx = rsqrt(x);
+        if (lane > k && lane < m) {
+          const double l = (M[lane + k * m] - a) * rx;
+          M[lane + k * m] = l;
+          diag = fma(-l, l, diag);
+        }
         if (lane == k) M[k + k * m] = rx;
         __syncwarp();
       }
@@ -139,6 +146,24 @@ __device__ __forceinline__ void row_trsm_lt(const double* L, int m,
     for (int k = 0; k < j; k++) s = fma(-X[r + k * rows], L[j + k * m], s);
     X[r + j * rows] = s * L[j + j * m];
   }
+}
+
+// The same with the row kept in registers (compile-time m): the shared-memory
+// version re-reads every X(r,k) it has just stored, a store -> load round trip
+// per term of a strictly sequential recurrence.
+template <int M>
+__device__ __forceinline__ void row_trsm_lt_reg(const double* L, const double* src, double* X,
+                                                int rows, int r) {
+  double xr[M];
+#pragma unroll
+  for (int j = 0; j < M; j++) {
+    double s = src[r + j * rows];
+#pragma unroll
+    for (int k = 0; k < j; k++) s = fma(-xr[k], L[j + k * M], s);
+    xr[j] = s * L[j + j * M];
+  }
+#pragma unroll
+  for (int j = 0; j < M; j++) X[r + j * rows] = xr[j];
 }
 
 constexpr int kRing = 3;  // slots per ring (prefetch distance 2 stages)
@@ -504,6 +529,29 @@ struct MpcProblem {
         } else {
           // column cc of inv(L L'): forward then backward substitution
           const int cc = e - nxx - nuu - nux;
+          if (KNX > 0) {  // compile-time size: the column lives in registers
+            constexpr int NXR = KNX > 0 ? KNX : 1;
+            double wr[NXR];
+#pragma unroll
+            for (int k = 0; k < NXR; k++) wr[k] = (k == cc) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = 0; j < NXR; j++) {
+              wr[j] *= Li[j + j * NXR];
+              const double wj = wr[j];
+#pragma unroll
+              for (int k = j + 1; k < NXR; k++) wr[k] = fma(-Li[k + j * NXR], wj, wr[k]);
+            }
+#pragma unroll
+            for (int k = NXR - 1; k >= 0; k--) {
+              double s = wr[k];
+#pragma unroll
+              for (int j = k + 1; j < NXR; j++) s = fma(-Li[j + k * NXR], wr[j], s);
+              wr[k] = s * Li[k + k * NXR];
+            }
+#pragma unroll
+            for (int k = 0; k < NXR; k++) Linv[(size_t)cc * NXR + k] = wr[k];
+            continue;
+          }
           double* w = Linv + (size_t)cc * nx;
           for (int k = 0; k < nx; k++) w[k] = (k == cc) ? 1.0 : 0.0;
           for (int j = 0; j < nx; j++) {
@@ -528,7 +576,14 @@ struct MpcProblem {
       ok = team_chol(t, T, Mi, nx) && ok;
       // AM = A M^-T, SM = St M^-T, :149-161
       for (int w = t.rank(); w < nx + nu; w += T) {
-        if (w < nx) {
+        if (KNX > 0) {
+          constexpr int NXR = KNX > 0 ? KNX : 1;
+          if (w < nx) {
+            if (i < N) row_trsm_lt_reg<NXR>(Mi, sd.A, AMi, nx, w);
+          } else {
+            row_trsm_lt_reg<NXR>(Mi, St, SMi, nu, w - nx);
+          }
+        } else if (w < nx) {
           if (i < N) row_trsm_lt(Mi, nx, sd.A, AMi, nx, w);
         } else {
           row_trsm_lt(Mi, nx, St, SMi, nu, w - nx);
@@ -555,7 +610,12 @@ struct MpcProblem {
             for (int k = 0; k < nx; k++) s = fma(AMi[rr + k * nx], SMi[j + k * nu], s);
             Pi[rr + j * nx] = s - sd.B[rr + j * nx];
           }
-          row_trsm_lt(SGi, nu, Pi, Pi, nx, rr);
+          if (KNU > 0) {
+            constexpr int NUR = KNU > 0 ? KNU : 1;
+            row_trsm_lt_reg<NUR>(SGi, Pi, Pi, nx, rr);
+          } else {
+            row_trsm_lt(SGi, nu, Pi, Pi, nx, rr);
+          }
         }
         // the slot that receives L(i+1) may still be the source of the bulk
         // store of block i-2
