@@ -391,6 +391,87 @@ def test_mpc_lane_path_parity(fb, oracle, kind, N, B, rho):
     assert np.abs(out2["newton_iters"] - out["newton_iters"][:nb]).max() <= 2
 
 
+def _random_time_varying_ocp(N, nx, nu, nc, B, seed):
+    """Strictly convex OCPs whose matrices differ from stage to stage AND from
+    instance to instance (the reference's fixtures are all time-invariant, which
+    would hide any stage- or slot-indexing error), in the wire format."""
+    rng = np.random.default_rng(seed)
+    K = N + 1
+
+    def spd(n, count):
+        M = rng.normal(size=(count, n, n))
+        return M @ M.transpose(0, 2, 1) / n + np.eye(n)
+
+    cm = lambda a: np.ascontiguousarray(a.transpose(0, 2, 1)).reshape(-1)  # column-major
+    d = {}
+    d["Q"] = cm(spd(nx, B * K))
+    d["R"] = cm(spd(nu, B * K))
+    d["S"] = cm(0.1 * rng.normal(size=(B * K, nu, nx)))
+    d["q"] = rng.normal(size=B * K * nx)
+    d["r"] = rng.normal(size=B * K * nu)
+    d["A"] = cm(np.eye(nx) + 0.3 * rng.normal(size=(B * N, nx, nx)) / np.sqrt(nx))
+    d["B"] = cm(rng.normal(size=(B * N, nx, nu)))
+    d["c"] = 0.1 * rng.normal(size=B * N * nx)
+    E = rng.normal(size=(B, K, nc, nx))
+    E[:, 0] = 0.0  # the initial state is fixed: no state constraint on stage 0
+    d["E"] = cm(E.reshape(B * K, nc, nx))
+    d["L"] = cm(rng.normal(size=(B * K, nc, nu)))
+    d["d"] = -(0.8 + rng.uniform(size=B * K * nc))  # E x + L u + d <= 0: several active
+    d["x0"] = 0.3 * rng.normal(size=B * nx)
+    return (N, nx, nu, nc), d
+
+
+@pytest.mark.parametrize("shape,N,B", [((4, 1, 4), 9, 40), ((2, 1, 6), 8, 40),
+                                       ((6, 3, 12), 7, 24), ((18, 5, 10), 6, 12),
+                                       ((3, 2, 5), 7, 24), ((5, 1, 3), 5, 16),
+                                       ((4, 1, 4), 9, 288), ((2, 1, 6), 8, 300)])
+def test_mpc_time_varying_data(fb, oracle, shape, N, B):
+    """Stage data that varies over the horizon and over the batch, every MPC
+    kernel (specialised and generic CTA instantiations, TMA rings with ragged
+    8-byte pieces, lane kernel for B >= 256) against the oracle."""
+    dims, d = _random_time_varying_ocp(N, *shape, B, seed=100 + N + B)
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    if B >= 256:
+        assert s.path.startswith("mpc-lane"), s.path
+    z, l, v = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, oz, ol, ov, oy = oracle.mpc_solve_batch(
+        *dims, [d[k] for k in fb.problems.MPC_FIELDS], nthreads=8)
+    assert (out["status"] == 0).all()
+    assert (out["eflag"] == oo["eflag"]).all(), (out["eflag"], oo["eflag"])
+    assert (oo["eflag"] == 0).mean() >= 0.9, "the generator should produce solvable OCPs"
+    same = _same_traj(out, oo)
+    assert same.mean() >= 0.85, f"trajectory differs on {(~same).sum()} of {B}"
+    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 3
+    Z, OZ = z.reshape(B, -1), oz.reshape(B, -1)
+    V, OV = v.reshape(B, -1), ov.reshape(B, -1)
+    for i in np.nonzero(out["eflag"] == 0)[0]:
+        tol = SOL_TOL if same[i] else 1e-4
+        assert rel_err(Z[i], OZ[i]) <= tol, (i, rel_err(Z[i], OZ[i]), same[i])
+        assert rel_err(V[i], OV[i]) <= tol * 100, (i, rel_err(V[i], OV[i]))
+
+
+@pytest.mark.parametrize("place", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape,N,B", [((18, 5, 10), 8, 6), ((6, 3, 12), 9, 8)])
+def test_mpc_time_varying_all_placements(fb, oracle, monkeypatch, place, shape, N, B):
+    """Every shared-memory placement of the CTA kernel (everything resident ...
+    only the sweep's working set, factor blocks streamed through the TMA ring)
+    on time- and instance-varying data: same answers as the oracle."""
+    monkeypatch.setenv("FBSTAB_MPC_PLACE", str(place))
+    dims, d = _random_time_varying_ocp(N, *shape, B, seed=7 + place)
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    z, l, v = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, oz, *_ = oracle.mpc_solve_batch(*dims, [d[k] for k in fb.problems.MPC_FIELDS],
+                                        nthreads=4)
+    assert (out["status"] == 0).all()
+    assert (out["eflag"] == oo["eflag"]).all(), (s.path, out["eflag"], oo["eflag"])
+    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 2
+    Z, OZ = z.reshape(B, -1), oz.reshape(B, -1)
+    for i in np.nonzero(out["eflag"] == 0)[0]:
+        assert rel_err(Z[i], OZ[i]) <= 1e-6, (s.path, i, rel_err(Z[i], OZ[i]))
+
+
 def test_mpc_maxiter_matches_reference_behaviour(fb, oracle):
     """Spacecraft N=100 with default options runs into the Newton cap in the
     reference algorithm (SURVEY.md 8(d) open issue): the engine must report
