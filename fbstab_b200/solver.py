@@ -44,7 +44,10 @@ class _Base:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            getattr(capi.lib(), f"fbstab_{self._prefix}_batch_destroy")(h)
+            try:
+                getattr(capi.lib(), f"fbstab_{self._prefix}_batch_destroy")(h)
+            except TypeError:  # interpreter shutdown: the module globals are gone
+                pass
             self._h = None
 
     # -- options: UpdateOptions / DefaultOptions / ReliableOptions ----------
