@@ -553,6 +553,8 @@ struct fbstab_mpc_batch : HandleBase {
   fbs::MpcPlan plan;
   // lane-per-instance path (small stages, large batches)
   double* lane_ws = nullptr;
+  double* lane_sdata = nullptr;  // common stage data (shared-data fast path)
+  int* lane_mismatch = nullptr;
   int lane_warps = 0;
   int lane_min = 0;
   char lane_name[160];
@@ -972,10 +974,22 @@ int fbstab_mpc_batch_create(int N, int nx, int nu, int nc, int max_batch,
     const size_t bytes = (size_t)warps * fbs::MpcLaneWsDoublesPerWarp(N, nx, nu, nc) * 8;
     if (cudaMalloc(&h->lane_ws, bytes) == cudaSuccess) {
       h->lane_warps = warps;
+      if (EnvInt("FBSTAB_MPC_SHARED", 1)) {
+        if (cudaMalloc(&h->lane_sdata, fbs::MpcLaneSharedDoubles(N, nx, nu, nc) * 8) !=
+                cudaSuccess ||
+            cudaMalloc(&h->lane_mismatch, sizeof(int)) != cudaSuccess) {
+          cudaGetLastError();
+          if (h->lane_sdata) cudaFree(h->lane_sdata);
+          h->lane_sdata = nullptr;
+          h->lane_mismatch = nullptr;
+        }
+      }
       snprintf(h->lane_name, sizeof(h->lane_name),
                "mpc-lane<nx,nu,nc> (lane per instance, %d warps, %.0f MB interleaved "
-               "workspace; batches < %d: %s)",
-               warps, bytes / 1e6, h->lane_min, "mpc-riccati-cta");
+               "workspace%s; batches < %d: %s)",
+               warps, bytes / 1e6,
+               h->lane_sdata ? ", common stage data detected on the device and shared" : "",
+               h->lane_min, "mpc-riccati-cta");
       h->path = h->lane_name;
     } else {
       cudaGetLastError();
@@ -991,6 +1005,8 @@ int fbstab_mpc_batch_destroy(fbstab_mpc_batch* h) {
   cudaSetDevice(h->device);
   fbs::MpcPlanFree(&h->plan);
   if (h->lane_ws) cudaFree(h->lane_ws);
+  if (h->lane_sdata) cudaFree(h->lane_sdata);
+  if (h->lane_mismatch) cudaFree(h->lane_mismatch);
   h->FreeAll();
   delete h;
   return FBSTAB_OK;
@@ -1076,7 +1092,8 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
     const bool lane = h->lane_ws && n >= h->lane_min;
     if (lane ? fbs::MpcLaneLaunch(h->N, h->nx, h->nu, h->nc, n, h->lane_warps, c, dz + o * nz,
                                   dl + o * nl, dv + o * nv, dy + o * nv, dout + lo, h->opts,
-                                  h->lane_ws, h->counter, st.stream)
+                                  h->lane_ws, h->counter, h->lane_mismatch, h->lane_sdata,
+                                  st.stream)
              : fbs::MpcLaunch(h->plan, n, c, dz + o * nz, dl + o * nl, dv + o * nv,
                               dy + o * nv, dout + lo, h->opts, -1, nullptr, h->counter,
                               st.stream))

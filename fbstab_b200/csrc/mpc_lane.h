@@ -14,9 +14,14 @@ bool MpcLaneSupported(int nx, int nu, int nc);
 size_t MpcLaneWsDoublesPerWarp(int N, int nx, int nu, int nc);
 // Launches min(max_warps, ceil(batch/32)) single-warp CTAs; `ws` holds
 // max_warps * MpcLaneWsDoublesPerWarp doubles.  Returns 0 on success.
+// `mismatch` (one int) and `sdata` (MpcLaneSharedDoubles doubles), both device
+// memory or both nullptr: enable the common-stage-data fast path -- a pass over
+// the inputs checks on the device whether every instance carries the stage
+// data of instance 0, and the kernel then reads it from one shared array.
+size_t MpcLaneSharedDoubles(int N, int nx, int nu, int nc);
 int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps,
                   const MpcData& data, double* z, double* l, double* v, double* y,
                   fbstab_out* out, const fbstab_options& opts, double* ws, int* counter,
-                  cudaStream_t stream);
+                  int* mismatch, double* sdata, cudaStream_t stream);
 
 }  // namespace fbs

@@ -502,6 +502,40 @@ def test_closed_loop_mpc_parity(fb, oracle, kind, N, B, T, rho):
     assert rel_err(cold["U"][ok], ref["U"][ok]) <= 1e-5
 
 
+@pytest.mark.parametrize("kind,N,B,rho", [("servo_motor", 20, 384, 0.02),
+                                         ("double_integrator", 15, 300, 0.6)])
+def test_mpc_lane_shared_data_path_is_bit_identical(fb, monkeypatch, kind, N, B, rho):
+    """Batches whose instances all carry the same stage data (detected on the
+    device) run the lane kernel without the per-lane data copy; the arithmetic
+    is the same, so the results equal the general path bit for bit -- and a
+    batch with ONE perturbed matrix entry must fall back to the general path
+    and see that entry."""
+    dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=rho)
+    res = {}
+    for shared in ("1", "0"):
+        monkeypatch.setenv("FBSTAB_MPC_SHARED", shared)
+        s = fb.FBstabMpc(*dims, max_batch=B)
+        assert s.path.startswith("mpc-lane"), s.path
+        z, l, v = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+        out, y = s.solve_batch(d, z, l, v)
+        res[shared] = (z, l, v, y, out["eflag"].copy(), out["newton_iters"].copy())
+    for a, b_ in zip(res["1"], res["0"]):
+        assert np.array_equal(a, b_)
+    # one instance with a different cost matrix: detection must say "not shared"
+    monkeypatch.setenv("FBSTAB_MPC_SHARED", "1")
+    d2 = {k: a.copy() for k, a in d.items()}
+    nx = dims[1]
+    per = d2["Q"].size // B
+    d2["Q"][(B - 3) * per + 2 * nx * nx] *= 3.0  # Q(2)(0,0) of instance B-3
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    z2, l2, v2 = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+    s.solve_batch(d2, z2, l2, v2)
+    Z, Z2 = res["1"][0].reshape(B, -1), z2.reshape(B, -1)
+    assert not np.array_equal(Z[B - 3], Z2[B - 3])
+    keep = np.arange(B) != B - 3
+    assert np.array_equal(Z[keep], Z2[keep])
+
+
 def test_mpc_maxiter_matches_reference_behaviour(fb, oracle):
     """Spacecraft N=100 with default options runs into the Newton cap in the
     reference algorithm (SURVEY.md 8(d) open issue): the engine must report
