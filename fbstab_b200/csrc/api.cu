@@ -557,7 +557,7 @@ struct fbstab_mpc_batch : HandleBase {
   int* lane_mismatch = nullptr;
   int lane_warps = 0;
   int lane_min = 0;
-  char lane_name[160];
+  char lane_name[320];
 };
 
 namespace {
