@@ -263,6 +263,23 @@ __device__ __forceinline__ void for_each_acc(const double (&acc)[4][4][2], F f) 
     }
 }
 
+// s + sum_k a[k*sa] * x[k*sx], k = 0..n-1, accumulated in order (one chain, so
+// bit-identical to the plain loop) with eight loads of `a` in flight: the
+// streaming mat-vecs read H, G and A straight from HBM and are latency-bound.
+__device__ __forceinline__ double dot_stream(const double* __restrict__ a, size_t sa,
+                                             const double* x, int sx, int n, double s) {
+  int k = 0;
+  for (; k + 8 <= n; k += 8) {
+    double t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) t[u] = __ldg(a + (size_t)(k + u) * sa);
+#pragma unroll
+    for (int u = 0; u < 8; u++) s = fma(t[u], x[(k + u) * sx], s);
+  }
+  for (; k < n; k++) s = fma(__ldg(a + (size_t)k * sa), x[k * sx], s);
+  return s;
+}
+
 // Preloads this thread's accumulator entries: acc = f(tile_row, tile_col).
 template <class F>
 __device__ __forceinline__ void init_acc(double (&acc)[4][4][2], F f) {
@@ -290,6 +307,41 @@ struct DenseLargeProblem : DenseProblem {
   const void* tmX = nullptr;      // tensor map of the row-major panel copies, or nullptr
   double* xt = nullptr;           // this CTA's panel copy Xt[r * NB + k], r = row of K
   int xt_row0 = 0;                // dim-1 coordinate of this CTA's row 0 in tmX
+
+  // DenseProblem::kkt / ::margin with eight loads in flight per thread (same
+  // sums in the same order as the base class)
+  __device__ void kkt(const Team& t, const Vars& x, double* oz, double* ol) const {
+    FBS_LAP(15);
+    for (int i = t.rank(); i < n; i += t.size()) {
+      if (i < nz) {
+        oz[i] = f[i] + dl::dot_stream(H + i, (size_t)nz, x.z, 1, nz, 0.0);
+      } else {
+        const int k = i - nz;
+        ol[k] = h[k] - dl::dot_stream(G + k, (size_t)nl, x.z, 1, nz, 0.0);
+      }
+    }
+    t.sync();
+    FBS_LAP(11);
+    const int lane = t.lane();
+    for (int i = t.warp(); i < nz; i += t.nwarps()) {
+      double s1 = (lane < nl) ? dl::dot_stream(G + (size_t)i * nl + lane, 32, x.l + lane, 32,
+                                               (nl - lane + 31) / 32, 0.0)
+                              : 0.0;
+      double s2 = (lane < nv) ? dl::dot_stream(A + (size_t)i * nv + lane, 32, x.v + lane, 32,
+                                               (nv - lane + 31) / 32, 0.0)
+                              : 0.0;
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) oz[i] = (oz[i] + s1) + s2;
+    }
+    t.sync();
+    FBS_LAP(12);
+  }
+  __device__ void margin(const Team& t, const double* z, double* y) const {
+    for (int i = t.rank(); i < nv; i += t.size())
+      y[i] = bvec[i] - dl::dot_stream(A + i, (size_t)nv, z, 1, nz, 0.0);
+    t.sync();
+  }
 
   // In-place lower Cholesky of the bs x bs diagonal block at (c0,c0) of K,
   // right-looking in shared memory; the factor is left in D (stride DP) and
@@ -701,9 +753,9 @@ struct DenseLargeProblem : DenseProblem {
     for (int i = tid; i < nl; i += dl::kThreads) r1[nz + i] = rl[i];
     __syncthreads();
     for (int i = warp; i < nz; i += nw) {
-      const double* a = A + (size_t)i * nv;
-      double s = 0.0;
-      for (int k = lane; k < nv; k += 32) s = fma(a[k], r2[k], s);
+      // lane's terms k = lane, lane+32, ...: (nv - lane + 31) / 32 of them
+      double s = dl::dot_stream(A + (size_t)i * nv + lane, 32, r2 + lane, 32,
+                                (nv - lane + 31) / 32, 0.0);
       s = warp_sum(s);
       if (lane == 0) r1[i] = (-rz[i]) - s;
     }
@@ -790,8 +842,7 @@ struct DenseLargeProblem : DenseProblem {
     __syncthreads();
     // dv = (rv + gamma .* (A dz)) ./ mus ; dy = b - A dz
     for (int i = tid; i < nv; i += dl::kThreads) {
-      double s = 0.0;
-      for (int j = 0; j < nz; j++) s = fma(A[i + (size_t)j * nv], dx.z[j], s);
+      const double s = dl::dot_stream(A + i, (size_t)nv, dx.z, 1, nz, 0.0);
       dx.v[i] = (gamma[i] * s + (-rv[i])) / mus[i];
       dx.y[i] = bvec[i] - s;
     }
