@@ -269,7 +269,7 @@ struct Warp {
   // which at most W trailing columns are still non-zero.  Every step the row
   // registers rotate left by one, so a[0] is always the entry in the pivot
   // column and the loop body is the same for every k.  The loop is kept
-  // ROLLED on purpose: seven warps run different instances at different
+  // ROLLED on purpose: the CTA's warps run different instances at different
   // program counters, and a fully unrolled elimination (10.5k SASS
   // instructions) measured 43% of all stall samples on instruction fetch
   // (profiles/r1_dense_small_unrolled_elimination.txt).  Lane k broadcasts its
