@@ -57,8 +57,13 @@ __device__ inline void TakeVars(double*& p, int nz, int nl, int nv, Vars* v) {
   v->y = Take(p, nv);
 }
 
-template <int KNX, int KNU, int KNC, int KT>
-__global__ void __launch_bounds__(KT ? KT : 128, KT == 32 ? 16 : KT == 64 ? 8 : 3)
+// MINB > 0: an instantiation compiled for more resident CTAs per SM (fewer
+// registers per thread, some spills): chosen when it lets the whole batch run
+// in fewer waves -- every instance of a batch takes about equally long, so a
+// half-empty last wave costs a full instance time.
+template <int KNX, int KNU, int KNC, int KT, int MINB = 0>
+__global__ void __launch_bounds__(KT ? KT : 128,
+                                  MINB ? MINB : (KT == 32 ? 16 : KT == 64 ? 8 : 3))
 mpc_riccati_kernel(const __grid_constant__ MpcArgs a) {
   extern __shared__ __align__(16) double dyn_smem[];
   __shared__ double red[4 * kRedSlots];  // blockDim <= 128
@@ -160,6 +165,7 @@ typedef void (*MpcKernel)(const MpcArgs);
 struct Variant {
   int nx, nu, nc, block;
   MpcKernel fn;
+  int minb;  // > 0: the dense-occupancy instantiation of the shape
 };
 // Compile-time specialisations for the OCP shapes of the BASELINE configs
 // (servo motor, double integrator, spacecraft, copolymerisation); every other
@@ -168,6 +174,7 @@ const Variant kVariants[] = {
     {4, 1, 4, 32, mpc_riccati_kernel<4, 1, 4, 32>},
     {2, 1, 6, 32, mpc_riccati_kernel<2, 1, 6, 32>},
     {6, 3, 12, 32, mpc_riccati_kernel<6, 3, 12, 32>},
+    {6, 3, 12, 32, mpc_riccati_kernel<6, 3, 12, 32, 28>, 28},
     {6, 3, 12, 64, mpc_riccati_kernel<6, 3, 12, 64>},
     {18, 5, 10, 128, mpc_riccati_kernel<18, 5, 10, 128>},
     {18, 5, 10, 64, mpc_riccati_kernel<18, 5, 10, 64>},
@@ -226,8 +233,42 @@ void Footprint(MpcLayout* L) {
 
 }  // namespace
 
+namespace {
+int PlanInitImpl(MpcPlan* p, int N, int nx, int nu, int nc, int max_batch, int sm_count,
+                 const char** err, const Variant* force_variant, int force_ring);
+}
+
 int MpcPlanInit(MpcPlan* p, int N, int nx, int nu, int nc, int max_batch,
                 int sm_count, const char** err) {
+  int rc = PlanInitImpl(p, N, nx, nu, nc, max_batch, sm_count, err, nullptr, -1);
+  if (rc || !EnvInt("FBSTAB_MPC_DENSE_OCCUPANCY", 1) || EnvInt("FBSTAB_MPC_GENERIC", 0) ||
+      EnvInt("FBSTAB_MPC_BLOCK", 0) || EnvInt("FBSTAB_MPC_PLACE", -1) >= 0)
+    return rc;
+  const int waves = (max_batch + p->grid_max - 1) / std::max(p->grid_max, 1);
+  if (waves < 2) return rc;
+  for (const Variant& v : kVariants) {
+    if (v.minb <= 0 || v.nx != nx || v.nu != nu || v.nc != nc) continue;
+    // fewer registers per thread and the stage data read in place (no ring in
+    // shared memory): more CTAs per SM; taken only if that saves a wave
+    MpcPlan q;
+    const char* e2 = "";
+    if (PlanInitImpl(&q, N, nx, nu, nc, max_batch, sm_count, &e2, &v, 0) != FBSTAB_OK) {
+      MpcPlanFree(&q);
+      continue;
+    }
+    if ((max_batch + q.grid_max - 1) / q.grid_max < waves) {
+      MpcPlanFree(p);
+      *p = q;
+      return FBSTAB_OK;
+    }
+    MpcPlanFree(&q);
+  }
+  return rc;
+}
+
+namespace {
+int PlanInitImpl(MpcPlan* p, int N, int nx, int nu, int nc, int max_batch, int sm_count,
+                 const char** err, const Variant* force_variant, int force_ring) {
   MpcLayout base;
   memset(&base, 0, sizeof(base));
   base.N = N;
@@ -237,7 +278,7 @@ int MpcPlanInit(MpcPlan* p, int N, int nx, int nu, int nc, int max_batch,
   base.nz = (N + 1) * (nx + nu);
   base.nl = (N + 1) * nx;
   base.nv = (N + 1) * nc;
-  base.data_ring = EnvInt("FBSTAB_MPC_RING", 1);
+  base.data_ring = force_ring >= 0 ? force_ring : EnvInt("FBSTAB_MPC_RING", 1);
   p->block = EnvInt("FBSTAB_MPC_BLOCK", (nx + nu) <= 12 ? 32 : 64);
   if (p->block < 32 || p->block > 128 || p->block % 32) {
     *err = "FBSTAB_MPC_BLOCK must be 32, 64, 96 or 128";
@@ -248,7 +289,7 @@ int MpcPlanInit(MpcPlan* p, int N, int nx, int nu, int nc, int max_batch,
   if (!EnvInt("FBSTAB_MPC_GENERIC", 0)) {
     const int want_block = EnvInt("FBSTAB_MPC_BLOCK", 0);
     for (const Variant& v : kVariants) {
-      if (v.nx != nx || v.nu != nu || v.nc != nc) continue;
+      if (v.nx != nx || v.nu != nu || v.nc != nc || v.minb > 0) continue;
       // the first instantiation of a shape is its default; a later one is
       // taken only when its block size was asked for
       if (!special || v.block == want_block) {
@@ -257,6 +298,11 @@ int MpcPlanInit(MpcPlan* p, int N, int nx, int nu, int nc, int max_batch,
       }
       special = true;
     }
+  }
+  if (force_variant) {
+    fn = force_variant->fn;
+    p->block = force_variant->block;
+    special = true;
   }
   p->kernel = (const void*)fn;
   // placements, most resident first: A everything in shared memory; B factor
@@ -336,6 +382,7 @@ int MpcPlanInit(MpcPlan* p, int N, int nx, int nu, int nc, int max_batch,
            p->ctas_per_sm, p->smem_bytes / 1024);
   return FBSTAB_OK;
 }
+}  // namespace
 
 void MpcPlanFree(MpcPlan* p) {
   if (p->ws) cudaFree(p->ws);
