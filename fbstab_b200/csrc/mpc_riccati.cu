@@ -57,13 +57,16 @@ __device__ inline void TakeVars(double*& p, int nz, int nl, int nv, Vars* v) {
   v->y = Take(p, nv);
 }
 
+#ifndef FBS_MPC_MINB128
+#define FBS_MPC_MINB128 3
+#endif
 // MINB > 0: an instantiation compiled for more resident CTAs per SM (fewer
 // registers per thread, some spills): chosen when it lets the whole batch run
 // in fewer waves -- every instance of a batch takes about equally long, so a
 // half-empty last wave costs a full instance time.
 template <int KNX, int KNU, int KNC, int KT, int MINB = 0>
 __global__ void __launch_bounds__(KT ? KT : 128,
-                                  MINB ? MINB : (KT == 32 ? 16 : KT == 64 ? 8 : 3))
+                                  MINB ? MINB : (KT == 32 ? 16 : KT == 64 ? 8 : FBS_MPC_MINB128))
 mpc_riccati_kernel(const __grid_constant__ MpcArgs a) {
   extern __shared__ __align__(16) double dyn_smem[];
   __shared__ double red[4 * kRedSlots];  // blockDim <= 128
@@ -99,7 +102,7 @@ mpc_riccati_kernel(const __grid_constant__ MpcArgs a) {
     p.sb = Take(sp, m);
     p.sc = Take(sp, m);
     p.dslot0 = sp;
-    if (lay.data_ring) sp += (size_t)kRing * lay.SD;
+    if (lay.data_ring) sp += (size_t)kDataRing * lay.SD;
     if (lay.fac_smem) {
       p.fac = sp;
       sp += (size_t)K * lay.FS;
@@ -215,7 +218,7 @@ void Footprint(MpcLayout* L) {
   L->SD = o;
   size_t smem = 2 * (size_t)Even(nxx) + Even(nuu) + Even(nux) + 3 * (size_t)Even(m);
   size_t ws = 0;
-  if (L->data_ring) smem += (size_t)kRing * L->SD;
+  if (L->data_ring) smem += (size_t)kDataRing * L->SD;
   if (L->fac_smem) {
     smem += (size_t)K * L->FS;
   } else {
