@@ -66,7 +66,7 @@ __device__ inline void TakeVars(double*& p, int nz, int nl, int nv, Vars* v) {
 // half-empty last wave costs a full instance time.
 template <int KNX, int KNU, int KNC, int KT, int MINB = 0>
 __global__ void __launch_bounds__(KT ? KT : 128,
-                                  MINB ? MINB : (KT == 32 ? 16 : KT == 64 ? 8 : FBS_MPC_MINB128))
+                                  MINB ? MINB : (KT == 32 ? 16 : KT == 64 ? 8 : KT == 96 ? 4 : FBS_MPC_MINB128))
 mpc_riccati_kernel(const __grid_constant__ MpcArgs a) {
   extern __shared__ __align__(16) double dyn_smem[];
   __shared__ double red[4 * kRedSlots];  // blockDim <= 128
@@ -179,6 +179,9 @@ const Variant kVariants[] = {
     {6, 3, 12, 32, mpc_riccati_kernel<6, 3, 12, 32>},
     {6, 3, 12, 32, mpc_riccati_kernel<6, 3, 12, 32, 28>, 28},
     {6, 3, 12, 64, mpc_riccati_kernel<6, 3, 12, 64>},
+    // 96 threads: 168 registers x 96 and 51 KB let FOUR instances share an SM
+    // (128 threads: three; the recursion's critical path is one warp either way)
+    {18, 5, 10, 96, mpc_riccati_kernel<18, 5, 10, 96>},
     {18, 5, 10, 128, mpc_riccati_kernel<18, 5, 10, 128>},
     {18, 5, 10, 64, mpc_riccati_kernel<18, 5, 10, 64>},
 };
