@@ -86,7 +86,7 @@ __device__ __forceinline__ bool chol(double (&A)[M][M]) {
     for (int j = 0; j < k; j++) s = fma(A[k][j], A[k][j], s);
     double x = A[k][k] - s;
     if (!(x > 0.0)) ok = false;
-    const double rx = 1.0 / sqrt(x);
+    const double rx = rsqrt(x);  // MUFU.RSQ64H + Newton: a third of the sqrt + division chain
 #pragma unroll
     for (int i = k + 1; i < M; i++) {
       double a = 0.0;
