@@ -555,6 +555,7 @@ struct fbstab_mpc_batch : HandleBase {
   double* lane_ws = nullptr;
   double* lane_sdata = nullptr;  // common stage data (shared-data fast path)
   int* lane_mismatch = nullptr;
+  int* cta_mismatch = nullptr;  // common-stage-data flag of the CTA path
   int lane_warps = 0;
   int lane_min = 0;
   char lane_name[320];
@@ -965,6 +966,10 @@ int fbstab_mpc_batch_create(int N, int nx, int nu, int nc, int max_batch,
     return rc;
   }
   h->path = h->plan.name;
+  if (EnvInt("FBSTAB_MPC_SHARED", 1) && cudaMalloc(&h->cta_mismatch, sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    h->cta_mismatch = nullptr;
+  }
   // Small stages: one LANE per instance once the batch fills the machine.
   h->lane_min = EnvInt("FBSTAB_MPC_LANE_MIN", 256);
   if (fbs::MpcLaneSupported(nx, nu, nc) && EnvInt("FBSTAB_MPC_LANE", 1) &&
@@ -1007,6 +1012,7 @@ int fbstab_mpc_batch_destroy(fbstab_mpc_batch* h) {
   if (h->lane_ws) cudaFree(h->lane_ws);
   if (h->lane_sdata) cudaFree(h->lane_sdata);
   if (h->lane_mismatch) cudaFree(h->lane_mismatch);
+  if (h->cta_mismatch) cudaFree(h->cta_mismatch);
   h->FreeAll();
   delete h;
   return FBSTAB_OK;
@@ -1094,9 +1100,12 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
                                   dl + o * nl, dv + o * nv, dy + o * nv, dout + lo, h->opts,
                                   h->lane_ws, h->counter, h->lane_mismatch, h->lane_sdata,
                                   st.stream)
-             : fbs::MpcLaunch(h->plan, n, c, dz + o * nz, dl + o * nl, dv + o * nv,
-                              dy + o * nv, dout + lo, h->opts, -1, nullptr, h->counter,
-                              st.stream))
+             : ((h->cta_mismatch && n > 1 &&
+                 fbs::MpcSharedDetect(h->N, h->nx, h->nu, h->nc, n, c, h->cta_mismatch,
+                                      st.stream)) ||
+                fbs::MpcLaunch(h->plan, n, c, dz + o * nz, dl + o * nl, dv + o * nv,
+                               dy + o * nv, dout + lo, h->opts, -1, nullptr, h->counter,
+                               n > 1 ? h->cta_mismatch : nullptr, st.stream)))
       return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
     CUDA_TRY(cudaGetLastError());
     return FBSTAB_OK;
@@ -1137,7 +1146,7 @@ int fbstab_mpc_batch_component(fbstab_mpc_batch* h, int comp, int batch,
   if ((rc = StageComponentIo(h, &st, batch, io, &dio))) return rc;
   CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
   if (fbs::MpcLaunch(h->plan, batch, a, nullptr, nullptr, nullptr, nullptr, nullptr,
-                     h->opts, comp, &dio, h->counter, st.stream))
+                     h->opts, comp, &dio, h->counter, nullptr, st.stream))
     return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
   CUDA_TRY(cudaGetLastError());
   h->last_launches = 1;

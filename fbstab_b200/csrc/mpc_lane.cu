@@ -1400,6 +1400,16 @@ size_t MpcLaneWsDoublesPerWarp(int N, int nx, int nu, int nc) {
   return 32 * (3 * (nz + nl + 2 * nv) + (nz + nl + nv) + 2 * nv + K * (fs + dat));
 }
 
+int MpcSharedDetect(int N, int nx, int nu, int nc, int batch, const MpcData& data,
+                    int* mismatch, cudaStream_t stream) {
+  const size_t K = N + 1;
+  if (cudaMemsetAsync(mismatch, 0, sizeof(int), stream) != cudaSuccess) return 1;
+  mpc_shared_detect<<<1184, 256, 0, stream>>>(
+      data, batch, K * nx * nx, K * nu * nu, K * nu * nx, K * nx, K * nu, (size_t)N * nx * nx,
+      (size_t)N * nx * nu, (size_t)N * nx, K * nc * nx, K * nc * nu, K * nc, mismatch);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 size_t MpcLaneSharedDoubles(int N, int nx, int nu, int nc) {
   const size_t dat = 2 * (size_t)nx * nx + (size_t)nu * nu + 2 * (size_t)nu * nx + 2 * nx + nu +
                      (size_t)nc * nx + (size_t)nc * nu + nc;
@@ -1435,11 +1445,7 @@ int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps, const
   if (mismatch && sdata) {
     // common-stage-data detection: one pass over the inputs, then exactly one of
     // the two kernels below does the work (no host round trip)
-    const size_t K = N + 1;
-    if (cudaMemsetAsync(mismatch, 0, sizeof(int), stream) != cudaSuccess) return 1;
-    mpc_shared_detect<<<1184, 256, 0, stream>>>(
-        data, batch, K * nx * nx, K * nu * nu, K * nu * nx, K * nx, K * nu, (size_t)N * nx * nx,
-        (size_t)N * nx * nu, (size_t)N * nx, K * nc * nx, K * nc * nu, K * nc, mismatch);
+    if (MpcSharedDetect(N, nx, nu, nc, batch, data, mismatch, stream)) return 1;
     var->build<<<32, 256, 0, stream>>>(data, N, mismatch, sdata);
     a.mismatch = mismatch;
     a.sdata = sdata;

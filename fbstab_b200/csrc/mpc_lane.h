@@ -19,6 +19,10 @@ size_t MpcLaneWsDoublesPerWarp(int N, int nx, int nu, int nc);
 // the inputs checks on the device whether every instance carries the stage
 // data of instance 0, and the kernel then reads it from one shared array.
 size_t MpcLaneSharedDoubles(int N, int nx, int nu, int nc);
+// One pass over the inputs: *mismatch (device int) = 0 iff every instance of the
+// batch carries the stage data (everything but x0) of instance 0.
+int MpcSharedDetect(int N, int nx, int nu, int nc, int batch, const MpcData& data,
+                    int* mismatch, cudaStream_t stream);
 int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps,
                   const MpcData& data, double* z, double* l, double* v, double* y,
                   fbstab_out* out, const fbstab_options& opts, double* ws, int* counter,

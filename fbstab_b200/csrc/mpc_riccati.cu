@@ -40,6 +40,10 @@ struct MpcArgs {
   MpcLayout lay;
   MpcData data;
   CommonArgs c;
+  // *mismatch == 0 (device flag written by MpcSharedDetect before the launch):
+  // every instance carries the stage data of instance 0, and all CTAs then read
+  // that one copy -- L2 / L1 resident instead of a DRAM stream per instance
+  const int* mismatch;
 };
 
 __host__ __device__ inline int Even(int n) { return (n + 1) & ~1; }
@@ -136,13 +140,14 @@ mpc_riccati_kernel(const __grid_constant__ MpcArgs a) {
   }
   __syncthreads();
 
+  const bool shared_data = a.mismatch != nullptr && *a.mismatch == 0;
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(c.counter, 1);
     __syncthreads();
     const int inst = s_inst;
     __syncthreads();
     if (inst >= c.batch) break;
-    const size_t i = (size_t)inst;
+    const size_t i = shared_data ? 0 : (size_t)inst;
     p.Q = a.data.Q + i * K * nx * nx;
     p.R = a.data.R + i * K * nu * nu;
     p.S = a.data.S + i * K * nu * nx;
@@ -154,10 +159,11 @@ mpc_riccati_kernel(const __grid_constant__ MpcArgs a) {
     p.E = a.data.E + i * K * nc * nx;
     p.L = a.data.L + i * K * nc * nu;
     p.d = a.data.d + i * K * nc;
-    p.x0 = a.data.x0 + i * nx;
+    p.x0 = a.data.x0 + (size_t)inst * nx;
     if (c.comp < 0) {
-      solve_instance(t, p, c.opts, w, c.z + i * nz, c.l + i * nl, c.v + i * nv,
-                     c.y + i * nv, c.out + inst);
+      const size_t io = (size_t)inst;
+      solve_instance(t, p, c.opts, w, c.z + io * nz, c.l + io * nl, c.v + io * nv,
+                     c.y + io * nv, c.out + inst);
     } else {
       RunComponent(t, p, c, inst, w);
     }
@@ -398,8 +404,9 @@ void MpcPlanFree(MpcPlan* p) {
 int MpcLaunch(const MpcPlan& p, int batch, const MpcData& data, double* z,
               double* l, double* v, double* y, fbstab_out* out,
               const fbstab_options& opts, int comp, const fbstab_component_io* io,
-              int* counter, cudaStream_t stream) {
+              int* counter, const int* mismatch, cudaStream_t stream) {
   MpcArgs a;
+  a.mismatch = mismatch;
   a.lay = p.lay;
   a.data = data;
   a.c.batch = batch;

@@ -52,6 +52,6 @@ void MpcPlanFree(MpcPlan* p);
 int MpcLaunch(const MpcPlan& p, int batch, const MpcData& data, double* z,
               double* l, double* v, double* y, fbstab_out* out,
               const fbstab_options& opts, int comp, const fbstab_component_io* io,
-              int* counter, cudaStream_t stream);
+              int* counter, const int* mismatch, cudaStream_t stream);
 
 }  // namespace fbs

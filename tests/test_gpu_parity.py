@@ -536,6 +536,36 @@ def test_mpc_lane_shared_data_path_is_bit_identical(fb, monkeypatch, kind, N, B,
     assert np.array_equal(Z[keep], Z2[keep])
 
 
+@pytest.mark.parametrize("kind,N,B,rho", [("copolymerization", 12, 10, 0.05),
+                                         ("spacecraft", 15, 24, 0.05)])
+def test_mpc_cta_shared_data_is_bit_identical(fb, monkeypatch, kind, N, B, rho):
+    """CTA kernel: when the device-side check finds the same stage data in every
+    instance, all CTAs read instance 0's copy (cache resident) -- same values,
+    same results bit for bit; one perturbed instance switches it off."""
+    dims, d = fb.problems.ocp_batch(kind, N, count=B, config=4, rho=rho)
+    res = {}
+    for shared in ("1", "0"):
+        monkeypatch.setenv("FBSTAB_MPC_SHARED", shared)
+        s = fb.FBstabMpc(*dims, max_batch=B)
+        assert s.path.startswith("mpc-riccati-cta"), s.path
+        z, l, v = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+        out, y = s.solve_batch(d, z, l, v)
+        res[shared] = (z, l, v, y, out["eflag"].copy(), out["newton_iters"].copy())
+    for a, b_ in zip(res["1"], res["0"]):
+        assert np.array_equal(a, b_)
+    monkeypatch.setenv("FBSTAB_MPC_SHARED", "1")
+    d2 = {k: a.copy() for k, a in d.items()}
+    per = d2["R"].size // B
+    d2["R"][(B - 2) * per] *= 2.0  # R(0)(0,0) of instance B-2
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    z2, l2, v2 = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+    s.solve_batch(d2, z2, l2, v2)
+    Z, Z2 = res["1"][0].reshape(B, -1), z2.reshape(B, -1)
+    assert not np.array_equal(Z[B - 2], Z2[B - 2])
+    keep = np.arange(B) != B - 2
+    assert np.array_equal(Z[keep], Z2[keep])
+
+
 def test_mpc_maxiter_matches_reference_behaviour(fb, oracle):
     """Spacecraft N=100 with default options runs into the Newton cap in the
     reference algorithm (SURVEY.md 8(d) open issue): the engine must report
