@@ -404,8 +404,8 @@ def main():
     # DRAM traffic (dram__bytes_read + dram__bytes_write per instance) from the committed
     # ncu --set full captures: profiles/r1_dense_small_ncu_full.txt (29.7 KB), the ncu
     # section of profiles/r1_dense_large_phases.txt (775 GB / 296 instances) and
-    # profiles/r1_mpc_lane_ncu.txt (76.6 GB resp. 9.4 GB / 4,736 instances)
-    per_instance = {"2": 29659.0, "5": 2.618e9, "3a": 1.617e7, "3b": 1.986e6}
+    # profiles/r1_mpc_lane_ncu.txt (34.7 GB / 4,736 instances, common-data path)
+    per_instance = {"2": 29659.0, "5": 2.618e9, "3a": 7.33e6}
     traffic = per_instance[args.config] * B if args.config in per_instance else None
     roofline = {
         "bound": "tensor" if tensor_bound else "fp64", "achieved": ach_tf, "peak": peak,
