@@ -1384,6 +1384,18 @@ const LaneVariant kLaneVariants[] = {
 
 }  // namespace
 
+// Batch size (in units of the CTA kernel's resident instances) from which the
+// lane kernel is the faster one.  With every instance resident at once its time
+// is the latency of one solve, whatever the batch; the CTA kernel needs one
+// (several times shorter) wave per `capacity` instances.  Measured crossovers
+// (tools/sweep_lane_min.py): servo 10 k instances = 4.2 x 2,368, double
+// integrator 2.6 k = 1.1 x.
+double MpcLaneCrossover(int nx, int nu, int nc) {
+  if (nx == 4 && nu == 1 && nc == 4) return 4.2;
+  if (nx == 2 && nu == 1 && nc == 6) return 1.1;
+  return 4.0;
+}
+
 bool MpcLaneSupported(int nx, int nu, int nc) {
   for (const LaneVariant& v : kLaneVariants)
     if (v.nx == nx && v.nu == nu && v.nc == nc) return true;

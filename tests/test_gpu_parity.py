@@ -360,10 +360,11 @@ def test_mpc_batch_parity(fb, oracle, kind, N, B, rho):
                                          ("double_integrator", 50, 512, -0.1),
                                          ("double_integrator", 12, 320, 0.6),
                                          ("servo_motor", 7, 257, 0.3)])
-def test_mpc_lane_path_parity(fb, oracle, kind, N, B, rho):
+def test_mpc_lane_path_parity(fb, oracle, monkeypatch, kind, N, B, rho):
     """The lane-per-instance kernel (mpc_lane.cu: small stages, batches >= 256)
     against the oracle, including batches that mix converged and infeasible
     instances and a batch size that leaves lanes of the last warp idle."""
+    monkeypatch.setenv("FBSTAB_MPC_LANE_MIN", "256")  # the default crossover is thousands
     dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=rho)
     s = fb.FBstabMpc(*dims, max_batch=B)
     assert s.path.startswith("mpc-lane"), s.path
@@ -425,10 +426,11 @@ def _random_time_varying_ocp(N, nx, nu, nc, B, seed):
                                        ((6, 3, 12), 7, 24), ((18, 5, 10), 6, 12),
                                        ((3, 2, 5), 7, 24), ((5, 1, 3), 5, 16),
                                        ((4, 1, 4), 9, 288), ((2, 1, 6), 8, 300)])
-def test_mpc_time_varying_data(fb, oracle, shape, N, B):
+def test_mpc_time_varying_data(fb, oracle, monkeypatch, shape, N, B):
     """Stage data that varies over the horizon and over the batch, every MPC
     kernel (specialised and generic CTA instantiations, TMA rings with ragged
     8-byte pieces, lane kernel for B >= 256) against the oracle."""
+    monkeypatch.setenv("FBSTAB_MPC_LANE_MIN", "256")
     dims, d = _random_time_varying_ocp(N, *shape, B, seed=100 + N + B)
     s = fb.FBstabMpc(*dims, max_batch=B)
     if B >= 256:
@@ -475,11 +477,12 @@ def test_mpc_time_varying_all_placements(fb, oracle, monkeypatch, place, shape, 
 @pytest.mark.parametrize("kind,N,B,T,rho", [("servo_motor", 10, 12, 6, 0.02),
                                            ("double_integrator", 8, 300, 5, -0.1),
                                            ("copolymerization", 6, 6, 4, 0.05)])
-def test_closed_loop_mpc_parity(fb, oracle, kind, N, B, T, rho):
+def test_closed_loop_mpc_parity(fb, oracle, monkeypatch, kind, N, B, T, rho):
     """Receding-horizon simulation: device-resident data and
     warm-started, shifted iterates between the solves, against the same loop
     around the CPU oracle -- same flags at every step, same state and input
     trajectories."""
+    monkeypatch.setenv("FBSTAB_MPC_LANE_MIN", "256")  # B = 300 exercises the lane kernel
     dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=rho)
     cl = fb.ClosedLoopMpc(dims, d)
     got = cl.run(T)
@@ -510,6 +513,7 @@ def test_mpc_lane_shared_data_path_is_bit_identical(fb, monkeypatch, kind, N, B,
     is the same, so the results equal the general path bit for bit -- and a
     batch with ONE perturbed matrix entry must fall back to the general path
     and see that entry."""
+    monkeypatch.setenv("FBSTAB_MPC_LANE_MIN", "256")
     dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=rho)
     res = {}
     for shared in ("1", "0"):
