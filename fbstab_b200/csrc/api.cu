@@ -973,7 +973,7 @@ int fbstab_mpc_batch_create(int N, int nx, int nu, int nc, int max_batch,
   // Small stages: one LANE per instance once the batch is several waves of the
   // CTA kernel (below that the CTA kernel's shorter per-instance latency wins).
   h->lane_min = EnvInt("FBSTAB_MPC_LANE_MIN",
-                       std::max(256, (int)(fbs::MpcLaneCrossover(nx, nu, nc) * h->plan.grid_max)));
+                       std::max(256, (int)(fbs::MpcLaneCrossover(nx, nu, nc) * 16 * h->sm_count)));
   if (fbs::MpcLaneSupported(nx, nu, nc) && EnvInt("FBSTAB_MPC_LANE", 1) &&
       max_batch >= h->lane_min) {
     const int warps = std::min((max_batch + 31) / 32,

@@ -1384,8 +1384,8 @@ const LaneVariant kLaneVariants[] = {
 
 }  // namespace
 
-// Batch size (in units of the CTA kernel's resident instances) from which the
-// lane kernel is the faster one.  With every instance resident at once its time
+// Batch size (in units of 16 instances per SM, the CTA kernel's default
+// residency) from which the lane kernel is the faster one.  With every instance resident at once its time
 // is the latency of one solve, whatever the batch; the CTA kernel needs one
 // (several times shorter) wave per `capacity` instances.  Measured crossovers
 // (tools/sweep_lane_min.py): servo 10 k instances = 4.2 x 2,368, double

@@ -10,8 +10,8 @@ namespace fbs {
 
 // True when (nx,nu,nc) has a compile-time instantiation of the lane kernel.
 bool MpcLaneSupported(int nx, int nu, int nc);
-// Smallest batch, as a multiple of the CTA kernel's resident instances, that
-// the lane kernel solves faster than the CTA kernel (measured per shape).
+// Smallest batch, as a multiple of 16 instances per SM, that the lane kernel
+// solves faster than the CTA kernel (measured per shape).
 double MpcLaneCrossover(int nx, int nu, int nc);
 // Lane-interleaved workspace of one warp (32 instances), in doubles.
 size_t MpcLaneWsDoublesPerWarp(int N, int nx, int nu, int nc);

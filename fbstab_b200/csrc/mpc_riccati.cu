@@ -181,7 +181,9 @@ struct Variant {
 // shape runs the run-time-sized instantiation.
 const Variant kVariants[] = {
     {4, 1, 4, 32, mpc_riccati_kernel<4, 1, 4, 32>},
+    {4, 1, 4, 32, mpc_riccati_kernel<4, 1, 4, 32, 28>, 28},
     {2, 1, 6, 32, mpc_riccati_kernel<2, 1, 6, 32>},
+    {2, 1, 6, 32, mpc_riccati_kernel<2, 1, 6, 32, 28>, 28},
     {6, 3, 12, 32, mpc_riccati_kernel<6, 3, 12, 32>},
     {6, 3, 12, 32, mpc_riccati_kernel<6, 3, 12, 32, 28>, 28},
     {6, 3, 12, 64, mpc_riccati_kernel<6, 3, 12, 64>},
