@@ -491,7 +491,8 @@ def test_closed_loop_mpc_parity(fb, oracle, monkeypatch, kind, N, B, T, rho):
         return oracle.mpc_solve_batch(*dims_, [dd[k] for k in fb.problems.MPC_FIELDS],
                                       x0=x0, nthreads=8)[:4]
 
-    ref = fb.closed_loop_reference(dims, d, T, solve)
+    from oracle.closed_loop_ref import closed_loop_reference
+    ref = closed_loop_reference(dims, d, T, solve)
     assert (got["status"] == 0).all()
     assert (got["eflag"] == ref["eflag"]).all()
     assert np.abs(got["newton_iters"] - ref["newton_iters"]).max() <= 3

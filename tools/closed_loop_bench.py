@@ -12,6 +12,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fbstab_b200 as fb  # noqa: E402
 from oracle import binding as ob  # noqa: E402
+from oracle.closed_loop_ref import closed_loop_reference  # noqa: E402
 
 CASES = [("servo_motor", 50, 16384, 40, 0.02), ("double_integrator", 50, 16384, 40, -0.1)]
 
@@ -30,7 +31,7 @@ def run(kind, N, B, T, rho, cpu_sample=256):
                                   nthreads=nthreads)[:4]
 
     t0 = time.perf_counter()
-    ref = fb.closed_loop_reference(dims, ds, T, solve)
+    ref = closed_loop_reference(dims, ds, T, solve)
     cpu_s = time.perf_counter() - t0
     same = (warm["eflag"][:, :cpu_sample] == ref["eflag"]).all()
     ok = (ref["eflag"] == 0).all(axis=0)
