@@ -1,6 +1,6 @@
 """Checker for fbstab_b200.closed_loop (test infrastructure, like everything
 under oracle/): the same receding-horizon loop in numpy around any batched
-solver -- the tests and tools/closed_loop_bench.py pass the CPU oracle."""
+solver -- the tests and tests/closed_loop_bench.py pass the CPU oracle."""
 import numpy as np
 
 

@@ -1,7 +1,7 @@
 """Closed-loop (receding-horizon) MPC throughput: B plants x T control steps,
 data and iterates resident on the device, warm-started vs cold-started, next to
 the same loop around the CPU oracle on a sample of the plants.
-Usage: python tools/closed_loop_bench.py [kind N B T rho] ...   (default: the config-3 OCPs)"""
+Usage: python tests/closed_loop_bench.py [kind N B T rho] ...   (default: the config-3 OCPs)"""
 import json
 import os
 import sys
