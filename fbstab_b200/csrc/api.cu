@@ -53,13 +53,16 @@ int EnvInt(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-bool IsDevicePtr(const void* p) {
+// Device (or managed) pointer?  *device receives the owning device of a plain
+// device allocation (-1 for managed memory, which every device can read).
+bool IsDevicePtr(const void* p, int* device = nullptr) {
   if (!p) return false;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
+  if (device) *device = a.type == cudaMemoryTypeDevice ? a.device : -1;
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
@@ -103,6 +106,7 @@ struct RangeCopy {  // deferred mode: `stride` bytes per instance
 // kernel of chunk c and the D2H copy of chunk c-1.
 struct Stager {
   cudaStream_t stream;
+  int device = -1;  // the handle's device: device pointers must live there
   bool any_host = false;
   bool defer = false;
   int batch = 1;
@@ -114,7 +118,10 @@ struct Stager {
       return FBSTAB_OK;
     }
     if (!user) return Fail(FBSTAB_ERR_INVALID, "null input pointer");
-    if (IsDevicePtr(user)) {
+    int pd = -1;
+    if (IsDevicePtr(user, &pd)) {
+      if (pd >= 0 && device >= 0 && pd != device)
+        return Fail(FBSTAB_ERR_INVALID, "device pointer belongs to another device than the handle");
       *out = user;
       return FBSTAB_OK;
     }
@@ -135,7 +142,10 @@ struct Stager {
       return FBSTAB_OK;
     }
     if (!user) return Fail(FBSTAB_ERR_INVALID, "null output pointer");
-    if (IsDevicePtr(user)) {
+    int pd = -1;
+    if (IsDevicePtr(user, &pd)) {
+      if (pd >= 0 && device >= 0 && pd != device)
+        return Fail(FBSTAB_ERR_INVALID, "device pointer belongs to another device than the handle");
       *out = user;
       return FBSTAB_OK;
     }
@@ -408,6 +418,12 @@ struct HandleBase {
   static constexpr int kMaxChunks = 32;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
+  // Every launch on a handle shares its instance counter and workspaces, so
+  // launches are ordered even when the caller changes streams between calls:
+  // each call makes its stream wait for the previous call's last kernel
+  // (a no-op when the stream is the same) and records this event behind its own.
+  cudaEvent_t ev_last = nullptr;
+  bool has_last = false;
 
   void FreeAll() {
     cudaSetDevice(device);
@@ -417,6 +433,7 @@ struct HandleBase {
       if (ev_in[i]) cudaEventDestroy(ev_in[i]);
       if (ev_k[i]) cudaEventDestroy(ev_k[i]);
     }
+    if (ev_last) cudaEventDestroy(ev_last);
     if (ws) cudaFree(ws);
     if (counter) cudaFree(counter);
     out_buf.Free();
@@ -450,6 +467,18 @@ int InitDevice(HandleBase* h, int device, int max_batch) {
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
   }
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
+  return FBSTAB_OK;
+}
+
+// Orders this call's work on stream `s` behind the previous call on the handle.
+int OrderBegin(HandleBase* h, cudaStream_t s) {
+  if (h->has_last) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_last, 0));
+  return FBSTAB_OK;
+}
+int OrderEnd(HandleBase* h, cudaStream_t s) {
+  CUDA_TRY(cudaEventRecord(h->ev_last, s));
+  h->has_last = true;
   return FBSTAB_OK;
 }
 
@@ -461,7 +490,7 @@ int InitDevice(HandleBase* h, int device, int max_batch) {
 // on the copy-out stream -- and the call returns when the results are in host
 // memory.
 template <class Launch>
-int RunPipelined(HandleBase* h, Stager* st, int batch, int min_chunk, Launch launch) {
+int RunPipelinedBody(HandleBase* h, Stager* st, int batch, int min_chunk, Launch launch) {
   cudaStream_t cs = st->stream;
   if (!st->any_host) {
     CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), cs));
@@ -492,6 +521,31 @@ int RunPipelined(HandleBase* h, Stager* st, int batch, int min_chunk, Launch lau
   CUDA_TRY(cudaStreamSynchronize(cs));
   h->last_launches = launches;
   return FBSTAB_OK;
+}
+template <class Launch>
+int RunPipelined(HandleBase* h, Stager* st, int batch, int min_chunk, Launch launch) {
+  cudaStream_t cs = st->stream;
+  int rc = OrderBegin(h, cs);
+  if (rc) return rc;
+  if (st->any_host) {
+    // the copy-in stream writes the staging buffers the previous call's kernels
+    // may still read
+    if (h->has_last) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_last, 0));
+  }
+  rc = RunPipelinedBody(h, st, batch, min_chunk, launch);
+  if (rc && st->any_host) {
+    // a mid-pipeline failure: queued copies still target the caller's host buffers
+    // and the staging buffers -- drain before reporting
+    const std::string keep = g_last_error;
+    cudaStreamSynchronize(h->s_in);
+    cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(h->s_out);
+    cudaGetLastError();
+    g_last_error = keep;
+    return rc;
+  }
+  if (rc) return rc;
+  return OrderEnd(h, cs);
 }
 
 // scratch_smem > 0: the kernel uses the dynamic shared memory as scratch and
@@ -632,6 +686,8 @@ void StampSolveTime(fbstab_out* out, int batch, double seconds) {
 extern "C" {
 
 const char* fbstab_last_error(void) { return g_last_error.c_str(); }
+// (internal: lets the other translation units of the library set the thread's error)
+int fbstab_set_last_error_(int code, const char* msg) { return Fail(code, msg ? msg : ""); }
 
 int fbstab_device_count(void) {
   int n = 0;
@@ -828,6 +884,7 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
   const auto t0 = std::chrono::steady_clock::now();
   Stager st;
   st.stream = (cudaStream_t)stream;
+  st.device = h->device;
   st.defer = true;
   st.batch = batch;
   DenseArgs a;
@@ -910,12 +967,14 @@ int fbstab_dense_batch_component(fbstab_dense_batch* h, int comp, int batch,
   CUDA_TRY(cudaSetDevice(h->device));
   Stager st;
   st.stream = (cudaStream_t)stream;
+  st.device = h->device;
   DenseArgs a;
   int rc = DenseStageData(h, &st, batch, H, f, G, hh, A, b, &a);
   if (rc) return rc;
   FillCommon(h, &a.c, batch);
   a.c.comp = comp;
   if ((rc = StageComponentIo(h, &st, batch, io, &a.c.io))) return rc;
+  if ((rc = OrderBegin(h, st.stream))) return rc;
   CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
   if (h->small.enabled) {
     rc = fbs::DenseSmallLaunch(h->small, batch, a.H, a.f, a.G, a.h, a.A, a.b,
@@ -931,6 +990,7 @@ int fbstab_dense_batch_component(fbstab_dense_batch* h, int comp, int batch,
   }
   CUDA_TRY(cudaGetLastError());
   h->last_launches = 1;
+  if ((rc = OrderEnd(h, st.stream))) return rc;
   return st.Finish();
 }
 
@@ -1067,6 +1127,7 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
   const auto t0 = std::chrono::steady_clock::now();
   Stager st;
   st.stream = (cudaStream_t)stream;
+  st.device = h->device;
   st.defer = true;
   st.batch = batch;
   fbs::MpcData a;
@@ -1140,18 +1201,21 @@ int fbstab_mpc_batch_component(fbstab_mpc_batch* h, int comp, int batch,
   CUDA_TRY(cudaSetDevice(h->device));
   Stager st;
   st.stream = (cudaStream_t)stream;
+  st.device = h->device;
   fbs::MpcData a;
   const double* user[12] = {Q, R, S, q, r, A, B, c, E, L, d, x0};
   int rc = MpcStageData(h, &st, batch, user, &a);
   if (rc) return rc;
   fbstab_component_io dio;
   if ((rc = StageComponentIo(h, &st, batch, io, &dio))) return rc;
+  if ((rc = OrderBegin(h, st.stream))) return rc;
   CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(int), st.stream));
   if (fbs::MpcLaunch(h->plan, batch, a, nullptr, nullptr, nullptr, nullptr, nullptr,
                      h->opts, comp, &dio, h->counter, nullptr, st.stream))
     return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
   CUDA_TRY(cudaGetLastError());
   h->last_launches = 1;
+  if ((rc = OrderEnd(h, st.stream))) return rc;
   return st.Finish();
 }
 

@@ -58,7 +58,7 @@ constexpr int OFF_VB = OFF_LB + NL;
 constexpr int OFF_SCR = OFF_VB + NV;  // scratch shared by the phases of a Newton step
 constexpr int SCR_SIZE = 392;  // Gamma (64) | transposition (8*LD) | pivot rows | Schur
 // pivot-row buffers of the elimination live in the scratch (free at that time):
-// 2 x (32 shifted row entries + pivot + pad + 10 augmented)
+// 2 x (32 row entries, pivot first + 10 augmented + pad)
 constexpr int OFF_COL = OFF_SCR;
 constexpr int COL_STRIDE = 44;
 constexpr int SLAB = OFF_SCR + SCR_SIZE;
@@ -104,6 +104,14 @@ __device__ __forceinline__ void sts(unsigned a, double v) {
 __device__ __forceinline__ void sts2(unsigned a, double x, double y) {
   asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
+// 16-byte store under a predicate: no branch, so the store can sit between the
+// DFMAs of an update (only the owning lane writes)
+__device__ __forceinline__ void sts2_if(bool p, unsigned a, double x, double y) {
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.s32 q, %3, 0;\n @q st.shared.v2.f64 [%0], {%1,%2};\n}"
+      ::"r"(a), "d"(x), "d"(y), "r"((int)p)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -118,6 +126,42 @@ __device__ __forceinline__ double bcast(double v, int src) {
 }
 // byte address of double index i in a slab at shared address sb
 __device__ __forceinline__ constexpr unsigned D(int i) { return 8u * (unsigned)i; }
+// a / b from rb = RN(1 / b): one product and Markstein's exact-remainder
+// correction give the correctly rounded quotient (what `a / b` returns), but
+// several quotients share one reciprocal and -- unlike the compiler's inline
+// division -- a zero or tiny quotient (v = 0 on every inactive constraint)
+// does not leave the fast path for the out-of-line IEEE routine: that call
+// was taken eight times per Newton step (profiles/r1_dense_small_ncu_full_8warps.txt).
+__device__ __forceinline__ double div_r(double a, double b, double rb) {
+  const double q = a * rb;
+  const double rem = fma(-b, q, a);
+  return fma(rem, rb, q);
+}
+// PFB gradient -> (gamma, mu), common.cuh::pfb_barrier with the two quotients
+// on one reciprocal.
+__device__ __forceinline__ void pfb_barrier_r(double ys, double v, double alpha,
+                                              double sigma, double* gamma,
+                                              double* mu) {
+  const double r = sqrt(ys * ys + v * v);
+  double ga, gb;
+  if (r < 1e-13) {  // zero_tolerance_
+    const double d = 0.70710678118654752440;  // 1/sqrt(2)
+    ga = alpha * (1.0 - d);
+    gb = ga;
+  } else {
+    const double rr = 1.0 / r;
+    const double qa = div_r(ys, r, rr), qb = div_r(v, r, rr);
+    if (ys > 0.0 && v > 0.0) {
+      ga = alpha * (1.0 - qa) + (1.0 - alpha) * v;
+      gb = alpha * (1.0 - qb) + (1.0 - alpha) * ys;
+    } else {
+      ga = alpha * (1.0 - qa);
+      gb = alpha * (1.0 - qb);
+    }
+  }
+  *gamma = ga;
+  *mu = gb + sigma * ga;
+}
 
 struct Warp {
   unsigned sb;  // shared-space byte address of this warp's slab
@@ -125,7 +169,7 @@ struct Warp {
   int nz, nl, nv;
   double fr, hr, br[NVR];  // f(lane), h(lane), b(lane + 32 m)
   // Newton-step state
-  double gamma[NVR], mus[NVR];
+  double gamma[NVR], mus[NVR], rmu[NVR];  // rmu = RN(1 / mus)
   double a[NZ];      // row `lane` of E, rotated left once per elimination step
   double g[NL + 1];  // column `lane` of G (rows 0..7) and the rhs (row 8)
   double dinv;       // 1 / pivot of row `lane`
@@ -140,40 +184,67 @@ struct Warp {
     for (int m = 0; m < NVR; m++) sts(sb + D(OFF_VB + lane + 32 * m), x.v[m]);
     __syncwarp();
   }
-  // (M zb)[row] for a row-contiguous 32-wide matrix row at shared address `row`
-  __device__ __forceinline__ double row_dot(unsigned row) const {
-    const unsigned zb = sb + D(OFF_ZB);
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int j = 0; j < NZ; j += 2) {
-      const double2 hh = lds2(row + D(j));
-      const double2 zz = lds2(zb + D(j));
-      s0 = fma(hh.x, zz.x, s0);
-      s1 = fma(hh.y, zz.y, s1);
-    }
-    return s0 + s1;
-  }
   // H(i,j) from the packed lower triangle (H(j,i) above the diagonal)
   __device__ __forceinline__ double Hel(int i, int j) const {
     const int r = max(i, j), c = min(i, j);
     return lds(sb + D(OFF_H + (r * (r + 1) >> 1) + c));
   }
-  // (H zb)[lane]: same terms in the same order as row_dot (even / odd partial sums)
-  __device__ __forceinline__ double Hz() const {
+  // (A' vb)[lane] and, with WITH_H, (H zb)[lane] in ONE rolled loop of 16 trips
+  // (4 rows of A and 2 columns of H per trip): six independent accumulation
+  // chains hide the DFMA latency, and the loop body -- not an unrolled copy per
+  // call site -- is what the instruction cache holds.  Each dot product keeps
+  // the partial-sum order of round 1 ((s0 + s1) + (s2 + s3), even / odd), so
+  // the results are bit-identical.
+  template <bool WITH_H>
+  __device__ __forceinline__ double ATv_Hz(double* hz) const {
+    const unsigned ac = sb + D(OFF_A + lane);
+    const unsigned vb = sb + D(OFF_VB);
     const unsigned zb = sb + D(OFF_ZB);
     const unsigned hrow = sb + D(OFF_H + (lane * (lane + 1) >> 1));  // H(lane, 0..lane)
-    double s0 = 0.0, s1 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, h0 = 0.0, h1 = 0.0;
+#pragma unroll 2
+    for (int t = 0; t < NV / 4; t++) {
+      const int k = 4 * t, j = 2 * t;
+      const double2 v0 = lds2(vb + D(k));
+      const double2 v1 = lds2(vb + D(k + 2));
+      const double a0 = lds(ac + D(LD * k)), a1 = lds(ac + D(LD * (k + 1)));
+      const double a2 = lds(ac + D(LD * (k + 2))), a3 = lds(ac + D(LD * (k + 3)));
+      if (WITH_H) {
+        const double2 zz = lds2(zb + D(j));
+        // column part: H(j, lane) for j > lane sits at j(j+1)/2 + lane
+        const double e0 = lds(j <= lane ? hrow + D(j) : sb + D(OFF_H + (j * (j + 1) >> 1) + lane));
+        const double e1 = lds(j + 1 <= lane ? hrow + D(j + 1)
+                                            : sb + D(OFF_H + ((j + 1) * (j + 2) >> 1) + lane));
+        h0 = fma(e0, zz.x, h0);
+        h1 = fma(e1, zz.y, h1);
+      }
+      s0 = fma(a0, v0.x, s0);
+      s1 = fma(a1, v0.y, s1);
+      s2 = fma(a2, v1.x, s2);
+      s3 = fma(a3, v1.y, s3);
+    }
+    if (WITH_H) *hz = h0 + h1;
+    return (s0 + s1) + (s2 + s3);
+  }
+  // (A zb)[lane + 32 m]: 2 NVR chains, rolled
+  __device__ __forceinline__ void Az(double (&o)[NVR]) const {
+    const unsigned zb = sb + D(OFF_ZB);
+    const unsigned arow = sb + D(OFF_A + LD * lane);
+    double t0[NVR], t1[NVR];
 #pragma unroll
+    for (int m = 0; m < NVR; m++) t0[m] = t1[m] = 0.0;
+#pragma unroll 4
     for (int j = 0; j < NZ; j += 2) {
       const double2 zz = lds2(zb + D(j));
-      // column part: H(j, lane) for j > lane sits at j(j+1)/2 + lane
-      const double h0 = lds(j <= lane ? hrow + D(j) : sb + D(OFF_H + (j * (j + 1) >> 1) + lane));
-      const double h1 = lds(j + 1 <= lane ? hrow + D(j + 1)
-                                          : sb + D(OFF_H + ((j + 1) * (j + 2) >> 1) + lane));
-      s0 = fma(h0, zz.x, s0);
-      s1 = fma(h1, zz.y, s1);
+#pragma unroll
+      for (int m = 0; m < NVR; m++) {
+        const double2 aa = lds2(arow + D(LD * 32 * m + j));
+        t0[m] = fma(aa.x, zz.x, t0[m]);
+        t1[m] = fma(aa.y, zz.y, t1[m]);
+      }
     }
-    return s0 + s1;
+#pragma unroll
+    for (int m = 0; m < NVR; m++) o[m] = t0[m] + t1[m];
   }
   // (G' lb)[lane]
   __device__ __forceinline__ double GTl() const {
@@ -187,22 +258,6 @@ struct Warp {
       s0 = fma(lds(gc + D(LD * (r + 1))), ll.y, s0);
     }
     return s0;
-  }
-  // (A' vb)[lane]
-  __device__ __forceinline__ double ATv() const {
-    const unsigned ac = sb + D(OFF_A + lane);
-    const unsigned vb = sb + D(OFF_VB);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < NV; k += 4) {
-      const double2 v0 = lds2(vb + D(k));
-      const double2 v1 = lds2(vb + D(k + 2));
-      s0 = fma(lds(ac + D(LD * k)), v0.x, s0);
-      s1 = fma(lds(ac + D(LD * (k + 1))), v0.y, s1);
-      s2 = fma(lds(ac + D(LD * (k + 2))), v1.x, s2);
-      s3 = fma(lds(ac + D(LD * (k + 3))), v1.y, s3);
-    }
-    return (s0 + s1) + (s2 + s3);
   }
   // (G zb)[lane % 8], same value in the four lanes sharing lane % 8
   __device__ __forceinline__ double Gz() const {
@@ -221,19 +276,15 @@ struct Warp {
     s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
     return s0;
   }
-  // (A zb)[lane + 32 m]
-  __device__ __forceinline__ void Az(double (&o)[NVR]) const {
-#pragma unroll
-    for (int m = 0; m < NVR; m++) o[m] = row_dot(sb + D(OFF_A + LD * (lane + 32 * m)));
-  }
-
   // ---- fused residual evaluation (see engine.cuh) ---------------------------
   __device__ __forceinline__ EvalOut evaluate(const V& x, const V& xbar,
                                               double sigma, double alpha, R* ri) {
     publish(x);
-    double tz = fr + Hz();
+    double hz;
+    const double atv = ATv_Hz<true>(&hz);
+    double tz = fr + hz;
     tz += GTl();
-    tz += ATv();
+    tz += atv;
     const double gz = Gz();
     const double tl = (lane < NL) ? hr - gz : 0.0;
     double si = 0.0, so = 0.0;
@@ -265,53 +316,93 @@ struct Warp {
     return e;
   }
 
-  // One segment of the Gauss-Jordan elimination of E: steps k0..k1-1, during
-  // which at most W trailing columns are still non-zero.  Every step the row
+  // Gauss-Jordan elimination, one segment: steps k0..k1-1, during which at most
+  // W trailing columns are still non-zero.  Lane `row` owns row `row` of the
+  // matrix in a[0..W] and NA augmented entries in g[]; every step the row
   // registers rotate left by one, so a[0] is always the entry in the pivot
-  // column and the loop body is the same for every k.  The loop is kept
-  // ROLLED on purpose: the CTA's warps run different instances at different
-  // program counters, and a fully unrolled elimination (10.5k SASS
-  // instructions) measured 43% of all stall samples on instruction fetch
-  // (profiles/r1_dense_small_unrolled_elimination.txt).  Lane k broadcasts its
-  // (already rotated) pivot row through shared memory.
-  template <int W>
-  __device__ __forceinline__ void eliminate(int k0, int k1) {
+  // column and the loop body is the same for every k.  The loop is kept ROLLED
+  // on purpose: the CTA's warps run different instances at different program
+  // counters, and a fully unrolled elimination measured 43% of all stall
+  // samples on instruction fetch (profiles/r1_dense_small_unrolled_elimination.txt).
+  //
+  // The pivot row travels through shared memory (two buffers, one __syncwarp
+  // per step).  It is the pivot row ITSELF, not the pivot column taken from
+  // the other lanes: after the 1e8-scale cancellations of A' Gamma A the (k,j)
+  // and (j,k) entries differ at the 1e-8 relative level, and mixing them ruins
+  // the accuracy of dz along the active-constraint normals.
+  //
+  // Round 2 (profiles/r2_dense_small_steps.txt): the owner of the NEXT pivot row
+  // stores it pair by pair as the update produces it -- predicated stores between
+  // the DFMAs -- instead of in a 21-store block at the top of the next step
+  // (210 + 66 cycles of store issue and drain on the critical path of every
+  // step); pairs (a[0],a[1]), (a[2],a[3]), ... are register-aligned, so each
+  // 16-byte store takes its operands in place (the (a[1],a[2]) pairing of round
+  // 1 cost three register moves per store); the row is loaded in chunks of four
+  // pairs, one chunk ahead of the update (the whole row in flight cost 84
+  // registers and pushed loop invariants out of the register file).  Same
+  // operations in the same order: results are bit-identical to round 1.
+  // Precondition: row k0 is already in buffer k0 & 1 (store_row / previous segment).
+  template <int W, int NA, int NG>
+  __device__ __forceinline__ void eliminate(int k0, int k1, int row, double (&a)[NZ],
+                                            double (&g)[NG], double* rpiv) {
+    static_assert(W & 1, "a[0..W] travels as (W + 1) / 2 aligned pairs");
+    constexpr int NP = (W + 1) / 2, NAP = (NA + 1) / 2, NCH = (NP + 3) / 4;
 #pragma unroll 1
     for (int k = k0; k < k1; k++) {
       const unsigned cb = sb + D(OFF_COL + COL_STRIDE * (k & 1));
-      if (lane == k) {
-        // the pivot row itself (NOT the pivot column taken from the other
-        // lanes: after the 1e8-scale cancellations of A' Gamma A the (k,j) and
-        // (j,k) entries differ at the 1e-8 relative level, and mixing them
-        // ruins the accuracy of dz along the active-constraint normals)
-        sts(cb + D(32), a[0]);
-#pragma unroll
-        for (int m = 1; m + 1 <= W; m += 2) sts2(cb + D(m - 1), a[m], a[m + 1]);
-        if (W & 1) sts(cb + D(W - 1), a[W]);
-#pragma unroll
-        for (int r = 0; r < NL + 1; r += 2)
-          sts2(cb + D(34 + r), g[r], (r + 1 < NL + 1) ? g[r + 1] : 0.0);
-      }
+      const unsigned nb = sb + D(OFF_COL + COL_STRIDE * ((k + 1) & 1));
       __syncwarp();
-      const double d = lds(cb + D(32));
+      double2 c[2][4], xr[NAP];
+#pragma unroll
+      for (int p = 0; p < 4; p++)
+        if (p < NP) c[0][p] = lds2(cb + D(2 * p));
+#pragma unroll
+      for (int r = 0; r < NAP; r++) xr[r] = lds2(cb + D(32 + 2 * r));
+      const double d = c[0][0].x;
       if (!(fabs(d) > 0.0)) ok = false;
       const double rd = 1.0 / d;
-      if (lane == k) dinv = rd;
-      const double lik = (lane != k) ? a[0] * rd : 0.0;
+      if (row == k) *rpiv = rd;
+      const double lik = (row != k) ? a[0] * rd : 0.0;
+      const bool nxt = (row == k + 1);
 #pragma unroll
-      for (int m = 1; m <= W; m += 2) {
-        const double2 c = lds2(cb + D(m - 1));
-        a[m - 1] = fma(-lik, c.x, a[m]);
-        if (m + 1 < NZ) a[m] = fma(-lik, c.y, a[m + 1]);
-      }
-      if (W < NZ - 1) a[W] = 0.0; else a[NZ - 1] = 0.0;
+      for (int q = 0; q < NCH; q++) {
 #pragma unroll
-      for (int r = 0; r < NL + 1; r += 2) {
-        const double2 xr = lds2(cb + D(34 + r));
-        g[r] = fma(-lik, xr.x, g[r]);
-        if (r + 1 < NL + 1) g[r + 1] = fma(-lik, xr.y, g[r + 1]);
+        for (int p = 0; p < 4; p++)
+          if (4 * (q + 1) + p < NP) c[(q + 1) & 1][p] = lds2(cb + D(8 * (q + 1) + 2 * p));
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          const int pg = 4 * q + p;  // pair (entries 2 pg, 2 pg + 1) of the pivot row
+          if (pg < NP) {
+            if (pg >= 1) {
+              a[2 * pg - 1] = fma(-lik, c[q & 1][p].x, a[2 * pg]);
+              sts2_if(nxt, nb + D(2 * pg - 2), a[2 * pg - 2], a[2 * pg - 1]);
+            }
+            a[2 * pg] = fma(-lik, c[q & 1][p].y, a[2 * pg + 1]);
+          }
+        }
       }
+      a[W] = 0.0;
+      sts2_if(nxt, nb + D(W - 1), a[W - 1], 0.0);
+#pragma unroll
+      for (int r = 0; r < NA; r++) {
+        const double xm = (r & 1) ? xr[r / 2].y : xr[r / 2].x;
+        g[r] = fma(-lik, xm, g[r]);
+        if (r & 1) sts2_if(nxt, nb + D(32 + r - 1), g[r - 1], g[r]);
+      }
+      if (NA & 1) sts2_if(nxt, nb + D(32 + NA - 1), g[NA - 1], 0.0);
     }
+  }
+  // Row `row` == k0 into pivot buffer k0 & 1 (before the first segment).
+  template <int W, int NA, int NG>
+  __device__ __forceinline__ void store_row(int k0, int row, const double (&a)[NZ],
+                                            const double (&g)[NG]) {
+    const unsigned cb = sb + D(OFF_COL + COL_STRIDE * (k0 & 1));
+    const bool own = (row == k0);
+#pragma unroll
+    for (int m = 0; m <= W; m += 2) sts2_if(own, cb + D(m), a[m], a[m + 1]);
+#pragma unroll
+    for (int r = 0; r < NA; r += 2)
+      sts2_if(own, cb + D(32 + r), g[r], (r + 1 < NA) ? g[r + 1] : 0.0);
   }
 
   // ---- Newton step: LinearSolver::Initialize + ::Solve fused -----------------
@@ -327,9 +418,10 @@ struct Warp {
 #pragma unroll
       for (int m = 0; m < NVR; m++) {
         const double ys = x.y[m] + sigma * (x.v[m] - xbar.v[m]);
-        pfb_barrier(ys, x.v[m], alpha, sigma, &gamma[m], &mus[m]);
-        Gam[m] = gamma[m] / mus[m];
-        r2[m] = (-ri.v[m]) / mus[m];
+        pfb_barrier_r(ys, x.v[m], alpha, sigma, &gamma[m], &mus[m]);
+        rmu[m] = 1.0 / mus[m];
+        Gam[m] = div_r(gamma[m], mus[m], rmu[m]);
+        r2[m] = div_r(-ri.v[m], mus[m], rmu[m]);
       }
       // r1z = -rz - A'(rv/mus) ; Gamma -> shared for the DMMA operand scaling
       __syncwarp();
@@ -340,7 +432,7 @@ struct Warp {
       }
       __syncwarp();
     }
-    g[NL] = (-ri.z) - ATv();
+    g[NL] = (-ri.z) - ATv_Hz<false>(nullptr);
 
     // E (lower 8x8 blocks) on the FP64 tensor cores
     {
@@ -353,16 +445,26 @@ struct Warp {
           C[I][J][0] = Hel(hr, hc) + ((I == J && r8 == 2 * c4) ? sigma : 0.0);
           C[I][J][1] = Hel(hr, hc + 1) + ((I == J && r8 == 2 * c4 + 1) ? sigma : 0.0);
         }
+      // operands of chunk kc + 1 are requested before the DMMAs of chunk kc issue
+      const unsigned ar0 = sb + D(OFF_A + LD * c4 + r8);
+      const unsigned gk0 = scr + D(c4);
+      double an[4], gn;
+      gn = lds(gk0);
+#pragma unroll
+      for (int X = 0; X < 4; X++) an[X] = lds(ar0 + D(8 * X));
 #pragma unroll 1
       for (int kc = 0; kc < NV / 4; kc++) {
-        const unsigned ar = sb + D(OFF_A + LD * (4 * kc + c4) + r8);
-        const double gk = lds(scr + D(4 * kc + c4));
         double af[4], bf[4];
 #pragma unroll
         for (int X = 0; X < 4; X++) {
-          af[X] = lds(ar + D(8 * X));
-          bf[X] = gk * af[X];
+          af[X] = an[X];
+          bf[X] = gn * an[X];
         }
+        // (the last trip re-reads chunk 0: no branch in the loop body)
+        const int kn = (kc + 1) & (NV / 4 - 1);
+        gn = lds(gk0 + D(4 * kn));
+#pragma unroll
+        for (int X = 0; X < 4; X++) an[X] = lds(ar0 + D(LD * 4 * kn + 8 * X));
 #pragma unroll
         for (int I = 0; I < 4; I++)
 #pragma unroll
@@ -399,10 +501,11 @@ struct Warp {
     // Gauss-Jordan elimination of the E block; the
     // pivot-row buffers alias the transposition scratch read just above
     __syncwarp();
-    eliminate<31>(0, 8);
-    eliminate<23>(8, 16);
-    eliminate<15>(16, 24);
-    eliminate<7>(24, 32);
+    store_row<31, NL + 1>(0, lane, a, g);
+    eliminate<31, NL + 1>(0, 8, lane, a, g, &dinv);
+    eliminate<23, NL + 1>(8, 16, lane, a, g, &dinv);
+    eliminate<15, NL + 1>(16, 24, lane, a, g, &dinv);
+    eliminate<7, NL + 1>(24, 32, lane, a, g, &dinv);
     // lane i now holds d_i * (E^-1 [G' a])(i,:) in g[0..8] and dinv = 1/d_i
 
     // Schur complement S = -sigma I - G Y, rhs c - G t  with [Y t] = E^-1 [G' a]
@@ -431,34 +534,25 @@ struct Warp {
     __syncwarp();
     double dl = 0.0;
     {
-      // 8x8 elimination by lanes 0..7 (lane r = row r)
+      // 8x8 Gauss-Jordan elimination with the same routine: lane r (and its three
+      // replicas r + 8, r + 16, r + 24) owns row r in a[0..7] -- the E rows are
+      // used up -- and the right-hand side rides along as the one augmented entry
       const int r = lane & 7;
-      double srow[NL];
 #pragma unroll
       for (int j = 0; j < NL; j += 2) {
         const double2 t = lds2(scr + D(320 + 8 * r + j));
-        srow[j] = -t.x - ((j == r) ? sigma : 0.0);
-        srow[j + 1] = -t.y - ((j + 1 == r) ? sigma : 0.0);
+        a[j] = -t.x - ((j == r) ? sigma : 0.0);
+        a[j + 1] = -t.y - ((j + 1 == r) ? sigma : 0.0);
       }
-      double rhs = ((lane < NL) ? ri.l : 0.0) - lds(scr + D(384 + r));
-      double dsi = 0.0;
-#pragma unroll
-      for (int k = 0; k < NL; k++) {
-        const double dk = bcast(srow[k], k);
-        if (!(fabs(dk) > 0.0)) ok = false;
-        const double rdk = 1.0 / dk;
-        if (r == k) dsi = rdk;
-        // Gauss-Jordan here as well: no back substitution
-        const double lrk = (r != k) ? srow[k] * rdk : 0.0;
-#pragma unroll
-        for (int j = k + 1; j < NL; j++) {
-          const double cj = bcast(srow[j], k);  // S(k,j): pivot row
-          srow[j] = fma(-lrk, cj, srow[j]);
-        }
-        const double rk = bcast(rhs, k);
-        rhs = fma(-lrk, rk, rhs);
-      }
-      dl = (lane < NL) ? rhs * dsi : 0.0;
+      double sg[2], dsi = 0.0;
+      sg[0] = ((lane < NL) ? ri.l : 0.0) - lds(scr + D(384 + r));
+      sg[1] = 0.0;
+      __syncwarp();  // every lane has read S and T: the pivot buffers may be reused
+      // (row index = lane: the replicas in lanes 8..31 never own a pivot row, so
+      // they never store; what they compute is not used)
+      store_row<NL - 1, 1>(0, lane, a, sg);
+      eliminate<NL - 1, 1>(0, NL, lane, a, sg, &dsi);
+      dl = (lane < NL) ? sg[0] * dsi : 0.0;
     }
     // dz = t - Y dl = (g[8] - sum_r g[r] dl_r) / d
     double acc = g[NL];
@@ -475,7 +569,7 @@ struct Warp {
     Az(adz);
 #pragma unroll
     for (int m = 0; m < NVR; m++) {
-      dx->v[m] = (gamma[m] * adz[m] + (-ri.v[m])) / mus[m];
+      dx->v[m] = div_r(gamma[m] * adz[m] + (-ri.v[m]), mus[m], rmu[m]);
       dx->y[m] = br[m] - adz[m];
     }
     return ok;
@@ -492,10 +586,12 @@ struct Warp {
       if (lane + 32 * m < nv) d1 = fmax(d1, adz[m]);
     const double gz = Gz();  // shuffles inside: every lane must call it
     const double d2 = (lane < NL) ? fabs(gz) : 0.0;
-    const double d3 = fabs(Hz());
+    double hz;
+    const double atv = ATv_Hz<true>(&hz);
+    const double d3 = fabs(hz);
     const double w = warp_max(fabs(dx.z));
     const double d4 = warp_sum(fr * dx.z);
-    const double p1 = warp_max(fabs(ATv() + GTl()));
+    const double p1 = warp_max(fabs(atv + GTl()));
     double p2 = (lane < NL) ? hr * dx.l : 0.0;
     double umax = fabs(dx.l);
 #pragma unroll
@@ -556,15 +652,56 @@ struct Warp {
       }
     }
   }
+  // Exact 32 / 8 / 64 shape (BASELINE config 2): compile-time index arithmetic
+  // (no integer division per element) and 16 loads in flight per lane.
+  __device__ __forceinline__ void load_exact(const Args& a_, int inst) {
+    const double* Asrc = a_.A + (size_t)inst * NV * NZ;
+    const double* Hsrc = a_.H + (size_t)inst * NZ * NZ;
+    const double* Gsrc = a_.G + (size_t)inst * NL * NZ;
+    // A(r, c) at r + 64 c -> As[c + LD r]; element e = lane + 32 u: c = u / 2, r = lane + 32 (u & 1)
+#pragma unroll 1
+    for (int u0 = 0; u0 < 2 * NZ; u0 += 16) {
+      double t[16];
+#pragma unroll
+      for (int u = 0; u < 16; u++) t[u] = __ldg(Asrc + lane + 32 * (u0 + u));
+      const unsigned base = sb + D(OFF_A + LD * lane + (u0 >> 1));
+#pragma unroll
+      for (int u = 0; u < 16; u++) sts(base + D(LD * 32 * (u & 1) + (u >> 1)), t[u]);
+    }
+    // H(r, c) at r + 32 c, lower triangle only -> Hp[r (r + 1) / 2 + c]; e = lane + 32 u: c = u, r = lane
+#pragma unroll 1
+    for (int u0 = 0; u0 < NZ; u0 += 16) {
+      double t[16];
+#pragma unroll
+      for (int u = 0; u < 16; u++)
+        t[u] = (lane >= u0 + u) ? __ldg(Hsrc + lane + 32 * (u0 + u)) : 0.0;
+      const unsigned base = sb + D(OFF_H + (lane * (lane + 1) >> 1) + u0);
+#pragma unroll
+      for (int u = 0; u < 16; u++)
+        if (lane >= u0 + u) sts(base + D(u), t[u]);
+    }
+    // G(r, c) at r + 8 c -> Gs[c + LD r]; e = lane + 32 u: c = lane / 8 + 4 u, r = lane % 8
+    {
+      double t[NZ / 4];
+#pragma unroll
+      for (int u = 0; u < NZ / 4; u++) t[u] = __ldg(Gsrc + lane + 32 * u);
+      const unsigned base = sb + D(OFF_G + LD * (lane & 7) + (lane >> 3));
+#pragma unroll
+      for (int u = 0; u < NZ / 4; u++) sts(base + D(4 * u), t[u]);
+    }
+  }
   __device__ __forceinline__ void load(const Args& a_, int inst) {
     __syncwarp();
-    if (nz < NZ || nl < NL || nv < NV) {  // zero padding of the unused part
+    if (nz == NZ && nl == NL && nv == NV) {
+      load_exact(a_, inst);
+    } else {
+      // zero padding of the unused part
       for (int e = 2 * lane; e < OFF_ZB; e += 64) sts2(sb + D(e), 0.0, 0.0);
       __syncwarp();
+      stage_lower(a_.H + (size_t)inst * nz * nz, nz);
+      stage_matrix(a_.A + (size_t)inst * nv * nz, nv, nz, OFF_A);
+      stage_matrix(a_.G + (size_t)inst * nl * nz, nl, nz, OFF_G);
     }
-    stage_lower(a_.H + (size_t)inst * nz * nz, nz);
-    stage_matrix(a_.A + (size_t)inst * nv * nz, nv, nz, OFF_A);
-    stage_matrix(a_.G + (size_t)inst * nl * nz, nl, nz, OFF_G);
     fr = (lane < nz) ? __ldg(a_.f + (size_t)inst * nz + lane) : 0.0;
     hr = (lane < nl) ? __ldg(a_.h + (size_t)inst * nl + lane) : 0.0;
 #pragma unroll

@@ -44,10 +44,18 @@
  *   iterates: z(nz) l(nl) v(nv) y(nv) per instance, instance-major.
  *
  * Every data/iterate pointer may be a HOST pointer or a DEVICE pointer on the
- * handle's device (checked per pointer).  Host buffers are staged through the
- * handle's device buffers inside the call; device buffers are used in place.
+ * handle's device (checked per pointer: a pointer that belongs to another
+ * device is FBSTAB_ERR_INVALID).  Host buffers are staged through the handle's
+ * device buffers inside the call; device buffers are used in place.
  * If every pointer is a device pointer the call only enqueues work on `stream`
  * (asynchronous); otherwise it returns after the results are in host memory.
+ *
+ * Streams and threads: a handle owns ONE instance counter and ONE set of
+ * workspaces, so its launches are serialised -- each call makes its stream wait
+ * (cudaStreamWaitEvent) for the handle's previous launch, whatever stream that
+ * ran on.  Calls on one handle must not be issued from two host threads at the
+ * same time (like the reference's solver objects, fbstab/components/
+ * dense_cholesky_solver.h:27); distinct handles are independent.
  *
  * There is NO CPU fallback: with no usable CUDA device every create/solve call
  * fails with FBSTAB_ERR_NOGPU / FBSTAB_ERR_CUDA.
@@ -67,6 +75,7 @@ extern "C" {
 #define FBSTAB_ERR_CUDA 2    /* a CUDA runtime call failed                    */
 #define FBSTAB_ERR_NOGPU 3   /* no CUDA device: the engine has no CPU path    */
 #define FBSTAB_ERR_ALLOC 4   /* device or host allocation failed              */
+#define FBSTAB_ERR_NCCL 5    /* NCCL missing or a NCCL call failed            */
 
 /* ---- ExitFlag, reference fbstab/fbstab_algorithm.h:17-24 ---------------- */
 #define FBSTAB_SUCCESS 0
@@ -228,6 +237,67 @@ int fbstab_mpc_batch_component(fbstab_mpc_batch* handle, int comp, int batch,
                                const double* E, const double* L,
                                const double* d, const double* x0,
                                const fbstab_component_io* io, void* stream);
+
+/* ---- multi-GPU: the batch shards by instance -----------------------------
+ * QP instances are independent (one reference Solve call each,
+ * fbstab/fbstab_dense.h:137-142), so a batch is cut into contiguous instance
+ * ranges, one per GPU, and the solve itself needs no collective.
+ *
+ * (1) One process per GPU (torchrun, MPI): rank 0 calls
+ * fbstab_multi_gpu_unique_id, the launcher's own channel broadcasts the 128
+ * bytes, every rank calls fbstab_multi_gpu_create and solves its shard
+ * [fbstab_multi_gpu_shard] with its own fbstab_*_batch handle on DEVICE result
+ * buffers.  fbstab_multi_gpu_gather is the only exchange: one grouped NCCL
+ * send/recv per result array moves each rank's rows straight from its result
+ * buffers into the root's global arrays (z: nz, l: nl, v and y: nv doubles and
+ * one fbstab_out per instance; Z..OUT are read on the root only), on `stream`.
+ * NCCL is resolved at run time (libnccl.so.2).                                */
+typedef struct fbstab_multi_gpu fbstab_multi_gpu;
+int fbstab_multi_gpu_unique_id(char id[128]);
+int fbstab_multi_gpu_create(int rank, int nranks, const char id[128], int device,
+                            fbstab_multi_gpu** handle);
+int fbstab_multi_gpu_destroy(fbstab_multi_gpu* handle);
+/* Contiguous range [first, first + count) of `global_batch` instances owned by
+ * `rank`: the first (global_batch % nranks) ranks take one instance more. */
+int fbstab_multi_gpu_shard(int nranks, int rank, long global_batch, long* first,
+                           long* count);
+int fbstab_multi_gpu_gather(fbstab_multi_gpu* handle, int root, long global_batch,
+                            int nz, int nl, int nv, const double* z,
+                            const double* l, const double* v, const double* y,
+                            const fbstab_out* out, double* Z, double* L, double* V,
+                            double* Y, fbstab_out* OUT, void* stream);
+
+/* (2) One process driving several GPUs with HOST buffers (what the C++ facade's
+ * SolveBatch(..., devices) calls): one batch handle and one host thread per
+ * device, each running the pipelined host-buffer solve on its shard; results
+ * land in the caller's arrays at the shard's offset.  Same argument meaning as
+ * fbstab_dense_batch_solve / fbstab_mpc_batch_solve. */
+typedef struct fbstab_dense_multi_gpu fbstab_dense_multi_gpu;
+typedef struct fbstab_mpc_multi_gpu fbstab_mpc_multi_gpu;
+int fbstab_dense_multi_gpu_create(int ndev, const int* devices, int nz, int nl,
+                                  int nv, long max_batch,
+                                  fbstab_dense_multi_gpu** handle);
+int fbstab_dense_multi_gpu_destroy(fbstab_dense_multi_gpu* handle);
+int fbstab_dense_multi_gpu_set_options(fbstab_dense_multi_gpu* handle,
+                                       const fbstab_options* o);
+int fbstab_dense_multi_gpu_solve(fbstab_dense_multi_gpu* handle, long batch,
+                                 const double* H, const double* f, const double* G,
+                                 const double* h, const double* A, const double* b,
+                                 double* z, double* l, double* v, double* y,
+                                 fbstab_out* out);
+int fbstab_mpc_multi_gpu_create(int ndev, const int* devices, int N, int nx, int nu,
+                                int nc, long max_batch,
+                                fbstab_mpc_multi_gpu** handle);
+int fbstab_mpc_multi_gpu_destroy(fbstab_mpc_multi_gpu* handle);
+int fbstab_mpc_multi_gpu_set_options(fbstab_mpc_multi_gpu* handle,
+                                     const fbstab_options* o);
+int fbstab_mpc_multi_gpu_solve(fbstab_mpc_multi_gpu* handle, long batch,
+                               const double* Q, const double* R, const double* S,
+                               const double* q, const double* r, const double* A,
+                               const double* B, const double* c, const double* E,
+                               const double* L, const double* d, const double* x0,
+                               double* z, double* l, double* v, double* y,
+                               fbstab_out* out);
 
 /* ---- synthetic problems (host code; mirrors fbstab/test/ocp_generator.h) - */
 #define FBSTAB_OCP_DOUBLE_INTEGRATOR 0 /* ocp_generator.cc:319-363 nx2 nu1 nc6  */

@@ -12,6 +12,12 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
+# Second build of the SAME restatement with FMA contraction allowed
+# (-ffp-contract=fast -mfma).  Not a second oracle: it exists to measure how far
+# two correctly rounded evaluations of the reference's arithmetic drift apart in
+# iteration counts (tests/test_oracle_fma_floor.py) -- the floor under any
+# "same trajectory" requirement on the GPU path.
+_FMA_LIB_PATH = os.path.join(_HERE, "liboracle_fma.so")
 
 EXIT_FLAGS = {0: "SUCCESS", 1: "DIVERGENCE", 2: "MAXITERATIONS",
               3: "PRIMAL_INFEASIBLE", 4: "DUAL_INFEASIBLE",
@@ -46,17 +52,35 @@ assert OUT_DTYPE.itemsize == C.sizeof(Out) == 48
 
 
 def build(force=False):
-    """Compile liboracle.so with the committed Makefile."""
-    if force or not os.path.exists(_LIB_PATH) or (
-            os.path.getmtime(_LIB_PATH) <
-            max(os.path.getmtime(os.path.join(_HERE, f))
-                for f in ("fbstab_oracle.cpp", "fbstab_oracle.h"))):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    """Compile liboracle.so (and the FMA-contracted build) with the committed Makefile."""
+    newest = max(os.path.getmtime(os.path.join(_HERE, f))
+                 for f in ("fbstab_oracle.cpp", "fbstab_oracle.h", "Makefile"))
+    if force or any(not os.path.exists(q) or os.path.getmtime(q) < newest
+                    for q in (_LIB_PATH, _FMA_LIB_PATH)):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 
 
 _lib = None
+_fma_lib = None
 _dp = C.POINTER(C.c_double)
+
+
+def fma_lib():
+    """The FMA-contracted build (batch solvers only; see _FMA_LIB_PATH)."""
+    global _fma_lib
+    if _fma_lib is None:
+        if not os.path.exists(_FMA_LIB_PATH):
+            build()
+        L = C.CDLL(_FMA_LIB_PATH)
+        L.oracle_dense_solve_batch.argtypes = (
+            [C.c_int] * 4 + [_dp] * 10 + [C.POINTER(Options), C.c_void_p,
+                                          C.c_int, C.c_int])
+        L.oracle_mpc_solve_batch.argtypes = (
+            [C.c_int] * 5 + [_dp] * 16 + [C.POINTER(Options), C.c_void_p,
+                                          C.c_int])
+        _fma_lib = L
+    return _fma_lib
 
 
 def lib():
@@ -254,7 +278,7 @@ class Problem:
 
 
 def dense_solve_batch(nz, nl, nv, H, f, G, h, A, b, opts=None, x0=None,
-                      variant=0, nthreads=1):
+                      variant=0, nthreads=1, fma=False):
     """Instance-major flat arrays.  Returns (out structured array, z,l,v,y)."""
     if opts is None:
         opts = default_options()
@@ -267,13 +291,13 @@ def dense_solve_batch(nz, nl, nv, H, f, G, h, A, b, opts=None, x0=None,
                    for t in x0]
     y = np.zeros(batch * nv)
     out = np.zeros(batch, dtype=OUT_DTYPE)
-    lib().oracle_dense_solve_batch(
+    (fma_lib() if fma else lib()).oracle_dense_solve_batch(
         nz, nl, nv, batch, _p(H), _p(f), _p(G), _p(h), _p(A), _p(b), _p(z),
         _p(l), _p(v), _p(y), C.byref(opts), out.ctypes.data, variant, nthreads)
     return out, z, l, v, y
 
 
-def mpc_solve_batch(N, nx, nu, nc, seqs, opts=None, x0=None, nthreads=1):
+def mpc_solve_batch(N, nx, nu, nc, seqs, opts=None, x0=None, nthreads=1, fma=False):
     """seqs = (Q,R,S,q,r,A,B,c,E,L,d,x0) instance-major flat arrays."""
     if opts is None:
         opts = default_options()
@@ -287,7 +311,7 @@ def mpc_solve_batch(N, nx, nu, nc, seqs, opts=None, x0=None, nthreads=1):
                    for t in x0]
     y = np.zeros(batch * nv)
     out = np.zeros(batch, dtype=OUT_DTYPE)
-    lib().oracle_mpc_solve_batch(
+    (fma_lib() if fma else lib()).oracle_mpc_solve_batch(
         N, nx, nu, nc, batch, *[_p(a) for a in seqs], _p(z), _p(l), _p(v),
         _p(y), C.byref(opts), out.ctypes.data, nthreads)
     return out, z, l, v, y

@@ -1,0 +1,48 @@
+"""The trajectory floor (CPU): two builds of the same oracle source -- without and
+with FMA contraction, both correctly rounded IEEE arithmetic -- do not always take
+the same number of Newton iterations (tests/golden/make_trajectory_floor.py).
+The committed measurement tests/golden/trajectory_floor.json is what the GPU
+parity tests take their "same trajectory" thresholds from; this test re-measures
+a subset on every CPU run so that the file cannot drift from the code."""
+import importlib.util
+import json
+import os
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location(
+    "make_trajectory_floor", os.path.join(HERE, "golden", "make_trajectory_floor.py"))
+floor = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(floor)
+
+with open(os.path.join(HERE, "golden", "trajectory_floor.json")) as fh:
+    COMMITTED = json.load(fh)["families"]
+
+
+def test_committed_file_covers_every_family():
+    assert set(COMMITTED) == set(floor.FAMILIES)
+    for name, rec in COMMITTED.items():
+        assert rec["same_flags"], name  # exit flags never depend on the rounding
+        assert rec["max_abs_newton_diff"] <= 2, name
+
+
+@pytest.mark.parametrize("name,count", [("servo_motor_N50", 512), ("dense_32_8_64", 512),
+                                        ("double_integrator_N50", 256)])
+def test_floor_remeasured(name, count):
+    got = floor.measure(name, threads=4, count=count)
+    want = COMMITTED[name]
+    assert got["same_flags"]
+    assert got["max_abs_newton_diff"] <= max(1, want["max_abs_newton_diff"])
+    # the subset is a prefix of the committed sample: same instances, so the
+    # fraction can only differ through the sample size
+    assert abs(got["same_trajectory_frac"] - want["same_trajectory_frac"]) <= 0.03, (got, want)
+    # same-trajectory instances agree to far better than the 1e-8 of north_star
+    assert got["max_rel_solution_diff_same_trajectory"] <= 1e-8
+
+
+def test_servo_floor_is_below_one():
+    """The point of the file: at sigma = 1e-8 the servo-motor problem is sensitive
+    to rounding, the dense 32/8/64 family is not."""
+    assert COMMITTED["servo_motor_N50"]["same_trajectory_frac"] < 0.995
+    assert COMMITTED["dense_32_8_64"]["same_trajectory_frac"] == 1.0
