@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FBSTAB_B200_LIB") or os.path.join(_HERE, "libfbstab_b200.so")
 
-OK, ERR_INVALID, ERR_CUDA, ERR_NOGPU, ERR_ALLOC = 0, 1, 2, 3, 4
+OK, ERR_INVALID, ERR_CUDA, ERR_NOGPU, ERR_ALLOC, ERR_NCCL = 0, 1, 2, 3, 4, 5
 EXIT_FLAGS = {0: "SUCCESS", 1: "DIVERGENCE", 2: "MAXITERATIONS",
               3: "PRIMAL_INFEASIBLE", 4: "DUAL_INFEASIBLE",
               5: "PRIMAL_DUAL_INFEASIBLE"}
@@ -31,6 +31,17 @@ SYMBOLS = [
     "fbstab_mpc_batch_set_options", "fbstab_mpc_batch_get_options",
     "fbstab_mpc_batch_solve", "fbstab_mpc_batch_last_launches",
     "fbstab_mpc_batch_path", "fbstab_mpc_batch_component",
+    "fbstab_mpc_batch_solve_shared", "fbstab_mpc_batch_solve_lti",
+    "fbstab_mpc_closed_loop_create", "fbstab_mpc_closed_loop_destroy",
+    "fbstab_mpc_closed_loop_set_options", "fbstab_mpc_closed_loop_reset",
+    "fbstab_mpc_closed_loop_step", "fbstab_mpc_closed_loop_run",
+    "fbstab_mpc_closed_loop_path",
+    "fbstab_multi_gpu_unique_id", "fbstab_multi_gpu_create", "fbstab_multi_gpu_destroy",
+    "fbstab_multi_gpu_shard", "fbstab_multi_gpu_gather",
+    "fbstab_dense_multi_gpu_create", "fbstab_dense_multi_gpu_destroy",
+    "fbstab_dense_multi_gpu_set_options", "fbstab_dense_multi_gpu_solve",
+    "fbstab_mpc_multi_gpu_create", "fbstab_mpc_multi_gpu_destroy",
+    "fbstab_mpc_multi_gpu_set_options", "fbstab_mpc_multi_gpu_solve",
     "fbstab_ocp_dims", "fbstab_ocp_generate", "fbstab_ocp_generate_batch",
     "fbstab_random_dense_qp", "fbstab_fp64_peak",
     "fbstab_fp64_peak_concurrent",
@@ -131,10 +142,12 @@ def ptr(a):
     if isinstance(a, int):
         return a
     if isinstance(a, np.ndarray):
-        assert a.flags["C_CONTIGUOUS"], "arrays must be contiguous"
+        if not a.flags["C_CONTIGUOUS"]:
+            raise RuntimeError("arrays must be contiguous")
         return a.ctypes.data
     if hasattr(a, "data_ptr"):  # torch tensor (host or cuda)
-        assert a.is_contiguous()
+        if not a.is_contiguous():
+            raise RuntimeError("tensors must be contiguous")
         return a.data_ptr()
     raise TypeError(type(a))
 

@@ -613,6 +613,9 @@ struct fbstab_mpc_batch : HandleBase {
   int lane_warps = 0;
   int lane_min = 0;
   char lane_name[320];
+  // fbstab_mpc_batch_solve_lti: pinned host copy of the horizon (one stage replicated)
+  double* lti_host = nullptr;
+  size_t lti_cap = 0;
 };
 
 namespace {
@@ -1075,6 +1078,7 @@ int fbstab_mpc_batch_destroy(fbstab_mpc_batch* h) {
   if (h->lane_sdata) cudaFree(h->lane_sdata);
   if (h->lane_mismatch) cudaFree(h->lane_mismatch);
   if (h->cta_mismatch) cudaFree(h->cta_mismatch);
+  if (h->lti_host) cudaFreeHost(h->lti_host);
   h->FreeAll();
   delete h;
   return FBSTAB_OK;
@@ -1094,8 +1098,10 @@ const char* fbstab_mpc_batch_path(const fbstab_mpc_batch* h) {
   return h ? h->path : "";
 }
 
+// shared: the 11 stage-data sequences are ONE copy for the whole batch (x0 stays per
+// instance).  Host copies of shared data are staged at once, ahead of the pipeline.
 static int MpcStageData(fbstab_mpc_batch* h, Stager* st, int batch,
-                        const double* const* user, fbs::MpcData* a) {
+                        const double* const* user, fbs::MpcData* a, bool shared = false) {
   const size_t N = h->N, nx = h->nx, nu = h->nu, nc = h->nc, K = N + 1,
                B = batch, D = sizeof(double);
   const size_t sizes[12] = {K * nx * nx, K * nu * nu, K * nu * nx, K * nx,
@@ -1104,19 +1110,23 @@ static int MpcStageData(fbstab_mpc_batch* h, Stager* st, int batch,
   const double** dst[12] = {&a->Q, &a->R, &a->S, &a->q, &a->r, &a->A,
                             &a->B, &a->c, &a->E, &a->L, &a->d, &a->x0};
   for (int k = 0; k < 12; k++) {
-    int rc = st->In(&h->in[k], user[k], B * sizes[k] * D, (const void**)dst[k]);
+    int rc;
+    if (shared && k < 11) {
+      const bool defer = st->defer;
+      st->defer = false;  // immediate copy on the caller's stream
+      rc = st->In(&h->in[k], user[k], sizes[k] * D, (const void**)dst[k]);
+      st->defer = defer;
+    } else {
+      rc = st->In(&h->in[k], user[k], B * sizes[k] * D, (const void**)dst[k]);
+    }
     if (rc) return rc;
   }
   return FBSTAB_OK;
 }
 
-int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
-                           const double* R, const double* S, const double* q,
-                           const double* r, const double* A, const double* B,
-                           const double* c, const double* E, const double* L,
-                           const double* d, const double* x0, double* z,
-                           double* l, double* v, double* y, fbstab_out* out,
-                           void* stream) {
+static int MpcSolveImpl(fbstab_mpc_batch* h, int batch, const double* const* user, bool shared,
+                        double* z, double* l, double* v, double* y, fbstab_out* out,
+                        void* stream) {
   if (!h) return Fail(FBSTAB_ERR_INVALID, "null handle");
   if (batch < 0 || batch > h->max_batch)
     return Fail(FBSTAB_ERR_INVALID, "batch exceeds the handle's max_batch");
@@ -1131,9 +1141,12 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
   st.defer = true;
   st.batch = batch;
   fbs::MpcData a;
-  const double* user[12] = {Q, R, S, q, r, A, B, c, E, L, d, x0};
-  int rc = MpcStageData(h, &st, batch, user, &a);
-  if (rc) return rc;
+  int rc;
+  if (shared && h->has_last) {
+    // the one-copy staging buffers may still be read by the previous call's kernels
+    CUDA_TRY(cudaStreamWaitEvent(st.stream, h->ev_last, 0));
+  }
+  if ((rc = MpcStageData(h, &st, batch, user, &a, shared))) return rc;
   const size_t nz = h->nz, nl = h->nl, nv = h->nv, Bn = batch, D = sizeof(double);
   double *dz, *dl, *dv, *dy;
   fbstab_out* dout;
@@ -1143,33 +1156,48 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
   if ((rc = st.InOut(&h->io[3], y, Bn * nv * D, false, (void**)&dy))) return rc;
   if ((rc = st.InOut(&h->out_buf, out, Bn * sizeof(fbstab_out), false, (void**)&dout)))
     return rc;
+  // shared stage data needs the kernels' common-data mode (a flag in device memory)
+  if (shared && !h->cta_mismatch)
+    return Fail(FBSTAB_ERR_INVALID, "shared stage data is disabled (FBSTAB_MPC_SHARED=0)");
   auto launch = [&](int lo, int n) -> int {
     const size_t N = h->N, nx = h->nx, nu = h->nu, nc = h->nc, K = N + 1, o = lo;
     fbs::MpcData c = a;
-    c.Q += o * K * nx * nx;
-    c.R += o * K * nu * nu;
-    c.S += o * K * nu * nx;
-    c.q += o * K * nx;
-    c.r += o * K * nu;
-    c.A += o * N * nx * nx;
-    c.B += o * N * nx * nu;
-    c.c += o * N * nx;
-    c.E += o * K * nc * nx;
-    c.L += o * K * nc * nu;
-    c.d += o * K * nc;
+    if (!shared) {
+      c.Q += o * K * nx * nx;
+      c.R += o * K * nu * nu;
+      c.S += o * K * nu * nx;
+      c.q += o * K * nx;
+      c.r += o * K * nu;
+      c.A += o * N * nx * nx;
+      c.B += o * N * nx * nu;
+      c.c += o * N * nx;
+      c.E += o * K * nc * nx;
+      c.L += o * K * nc * nu;
+      c.d += o * K * nc;
+    }
     c.x0 += o * nx;
-    const bool lane = h->lane_ws && n >= h->lane_min;
-    if (lane ? fbs::MpcLaneLaunch(h->N, h->nx, h->nu, h->nc, n, h->lane_warps, c, dz + o * nz,
-                                  dl + o * nl, dv + o * nv, dy + o * nv, dout + lo, h->opts,
-                                  h->lane_ws, h->counter, h->lane_mismatch, h->lane_sdata,
-                                  st.stream)
-             : ((h->cta_mismatch && n > 1 &&
-                 fbs::MpcSharedDetect(h->N, h->nx, h->nu, h->nc, n, c, h->cta_mismatch,
-                                      st.stream)) ||
-                fbs::MpcLaunch(h->plan, n, c, dz + o * nz, dl + o * nl, dv + o * nv,
-                               dy + o * nv, dout + lo, h->opts, -1, nullptr, h->counter,
-                               n > 1 ? h->cta_mismatch : nullptr, st.stream)))
-      return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
+    const bool lane = h->lane_ws && n >= h->lane_min && (!shared || h->lane_sdata);
+    int fail;
+    if (lane) {
+      fail = fbs::MpcLaneLaunch(h->N, h->nx, h->nu, h->nc, n, h->lane_warps, c, dz + o * nz,
+                                dl + o * nl, dv + o * nv, dy + o * nv, dout + lo, h->opts,
+                                h->lane_ws, h->counter, h->lane_mismatch, h->lane_sdata,
+                                st.stream, shared);
+    } else if (shared) {
+      // explicit common data: the flag is set without the detection pass
+      fail = cudaMemsetAsync(h->cta_mismatch, 0, sizeof(int), st.stream) != cudaSuccess ||
+             fbs::MpcLaunch(h->plan, n, c, dz + o * nz, dl + o * nl, dv + o * nv, dy + o * nv,
+                            dout + lo, h->opts, -1, nullptr, h->counter, h->cta_mismatch,
+                            st.stream);
+    } else {
+      fail = (h->cta_mismatch && n > 1 &&
+              fbs::MpcSharedDetect(h->N, h->nx, h->nu, h->nc, n, c, h->cta_mismatch,
+                                   st.stream)) ||
+             fbs::MpcLaunch(h->plan, n, c, dz + o * nz, dl + o * nl, dv + o * nv, dy + o * nv,
+                            dout + lo, h->opts, -1, nullptr, h->counter,
+                            n > 1 ? h->cta_mismatch : nullptr, st.stream);
+    }
+    if (fail) return Fail(FBSTAB_ERR_CUDA, "MPC kernel launch failed");
     CUDA_TRY(cudaGetLastError());
     return FBSTAB_OK;
   };
@@ -1182,6 +1210,84 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
     StampSolveTime(out, batch, sec);
   }
   return FBSTAB_OK;
+}
+
+int fbstab_mpc_batch_solve(fbstab_mpc_batch* h, int batch, const double* Q,
+                           const double* R, const double* S, const double* q,
+                           const double* r, const double* A, const double* B,
+                           const double* c, const double* E, const double* L,
+                           const double* d, const double* x0, double* z,
+                           double* l, double* v, double* y, fbstab_out* out,
+                           void* stream) {
+  const double* user[12] = {Q, R, S, q, r, A, B, c, E, L, d, x0};
+  return MpcSolveImpl(h, batch, user, false, z, l, v, y, out, stream);
+}
+
+int fbstab_mpc_batch_solve_shared(fbstab_mpc_batch* h, int batch, const double* Q,
+                                  const double* R, const double* S, const double* q,
+                                  const double* r, const double* A, const double* B,
+                                  const double* c, const double* E, const double* L,
+                                  const double* d, const double* x0, double* z, double* l,
+                                  double* v, double* y, fbstab_out* out, void* stream) {
+  const double* user[12] = {Q, R, S, q, r, A, B, c, E, L, d, x0};
+  return MpcSolveImpl(h, batch, user, true, z, l, v, y, out, stream);
+}
+
+// Time-invariant stage data: ONE stage of each sequence, replicated over the
+// horizon exactly like OcpGenerator::CopyOverHorizon (ocp_generator.cc:397-418:
+// the same Q,R,S,q,r,L,d at stages 0..N, A,B,c at stages 0..N-1, and E(0) = 0 --
+// no constraint on the measured state), then solved as shared stage data.
+int fbstab_mpc_batch_solve_lti(fbstab_mpc_batch* h, int batch, const double* Q,
+                               const double* R, const double* S, const double* q,
+                               const double* r, const double* A, const double* B,
+                               const double* c, const double* E, const double* L,
+                               const double* d, const double* x0, double* z, double* l,
+                               double* v, double* y, fbstab_out* out, void* stream) {
+  if (!h) return Fail(FBSTAB_ERR_INVALID, "null handle");
+  const size_t N = h->N, nx = h->nx, nu = h->nu, nc = h->nc, K = N + 1;
+  const size_t one[11] = {nx * nx, nu * nu, nu * nx, nx, nu, nx * nx, nx * nu, nx,
+                          nc * nx, nc * nu, nc};
+  const size_t len[11] = {K, K, K, K, K, N, N, N, K, K, K};
+  const double* src[11] = {Q, R, S, q, r, A, B, c, E, L, d};
+  size_t total = 0;
+  for (int k = 0; k < 11; k++) total += one[k] * len[k];
+  CUDA_TRY(cudaSetDevice(h->device));
+  // the horizon copy is 11 small sequences: built on the host (pinned, owned by the
+  // handle) and handed to the shared-data entry, which stages it with one copy each
+  if (h->lti_cap < total) {
+    if (h->lti_host) cudaFreeHost(h->lti_host);
+    h->lti_host = nullptr;
+    h->lti_cap = 0;
+    if (cudaMallocHost(&h->lti_host, total * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      return Fail(FBSTAB_ERR_ALLOC, "cudaMallocHost of the LTI horizon copy failed");
+    }
+    h->lti_cap = total;
+  }
+  // a previous LTI call's asynchronous staging copies must have left the buffer
+  if (h->has_last) CUDA_TRY(cudaEventSynchronize(h->ev_last));
+  std::vector<double> tmp;
+  const double* user[12];
+  double* w = h->lti_host;
+  for (int k = 0; k < 11; k++) {
+    if (!src[k]) return Fail(FBSTAB_ERR_INVALID, "null input pointer");
+    const double* s1 = src[k];
+    if (IsDevicePtr(s1)) {  // one stage from the device: a few hundred bytes
+      tmp.resize(one[k]);
+      CUDA_TRY(cudaMemcpy(tmp.data(), s1, one[k] * sizeof(double), cudaMemcpyDeviceToHost));
+      s1 = tmp.data();
+    }
+    for (size_t i = 0; i < len[k]; i++) {
+      if (k == 8 && i == 0)
+        memset(w + i * one[k], 0, one[k] * sizeof(double));  // E(0) = 0
+      else
+        memcpy(w + i * one[k], s1, one[k] * sizeof(double));
+    }
+    user[k] = w;
+    w += one[k] * len[k];
+  }
+  user[11] = x0;
+  return MpcSolveImpl(h, batch, user, true, z, l, v, y, out, stream);
 }
 
 int fbstab_mpc_batch_component(fbstab_mpc_batch* h, int comp, int batch,

@@ -196,7 +196,9 @@ struct Lane {
   }
 
   __device__ void bind(const LaneArgs& a, int inst) {
-    const size_t i = (size_t)inst, K = N + 1;
+    // SHARED: every instance carries instance 0's stage data -- and the caller may have
+    // passed exactly ONE copy (fbstab_mpc_batch_solve_shared); only x0 is per instance
+    const size_t i = SHARED ? 0 : (size_t)inst, K = N + 1;
     Q = a.data.Q + i * K * NX * NX;
     R = a.data.R + i * K * NU * NU;
     S = a.data.S + i * K * NU * NX;
@@ -208,7 +210,7 @@ struct Lane {
     E = a.data.E + i * K * NC * NX;
     L = a.data.L + i * K * NC * NU;
     d = a.data.d + i * K * NC;
-    x0 = a.data.x0 + i * NX;
+    x0 = a.data.x0 + (size_t)inst * NX;
   }
 
   // packed lower triangles <-> register matrices (t = FS-sized register copy)
@@ -1431,7 +1433,7 @@ size_t MpcLaneSharedDoubles(int N, int nx, int nu, int nc) {
 int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps, const MpcData& data,
                   double* z, double* l, double* v, double* y, fbstab_out* out,
                   const fbstab_options& opts, double* ws, int* counter, int* mismatch,
-                  double* sdata, cudaStream_t stream) {
+                  double* sdata, cudaStream_t stream, bool shared_known) {
   const LaneVariant* var = nullptr;
   for (const LaneVariant& c : kLaneVariants)
     if (c.nx == nx && c.nu == nu && c.nc == nc) var = &c;
@@ -1457,11 +1459,20 @@ int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps, const
   if (mismatch && sdata) {
     // common-stage-data detection: one pass over the inputs, then exactly one of
     // the two kernels below does the work (no host round trip)
-    if (MpcSharedDetect(N, nx, nu, nc, batch, data, mismatch, stream)) return 1;
+    // (shared_known: the caller passed ONE copy of the stage data -- no detection pass,
+    // and only the shared-data kernel is launched)
+    if (shared_known) {
+      if (cudaMemsetAsync(mismatch, 0, sizeof(int), stream) != cudaSuccess) return 1;
+    } else if (MpcSharedDetect(N, nx, nu, nc, batch, data, mismatch, stream)) {
+      return 1;
+    }
     var->build<<<32, 256, 0, stream>>>(data, N, mismatch, sdata);
     a.mismatch = mismatch;
     a.sdata = sdata;
     var->fn_shared<<<warps, 32, 0, stream>>>(a);
+    if (shared_known) return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  } else if (shared_known) {
+    return 1;  // the caller checks lane_sdata before asking for this path
   }
   var->fn<<<warps, 32, 0, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -29,6 +29,7 @@ int MpcSharedDetect(int N, int nx, int nu, int nc, int batch, const MpcData& dat
 int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps,
                   const MpcData& data, double* z, double* l, double* v, double* y,
                   fbstab_out* out, const fbstab_options& opts, double* ws, int* counter,
-                  int* mismatch, double* sdata, cudaStream_t stream);
+                  int* mismatch, double* sdata, cudaStream_t stream,
+                  bool shared_known = false);
 
 }  // namespace fbs

@@ -131,6 +131,16 @@ void RandomDenseQp(int config, long instance, int nz, int nl, int nv, int kind,
 struct Model {
   int nx = 0, nu = 0, nc = 0;
   std::vector<double> Q, R, S, q, r, A, B, c, E, L, d, x0;
+  // simulation side (OcpGenerator::GetSimulationInputs, ocp_generator.cc:56-71):
+  // output map y = C x (ny x nx, column-major; D = 0) and the number of steps T
+  int ny = 0, T = 0;
+  std::vector<double> C;
+  void Output(int ny_, int T_) {
+    ny = ny_;
+    T = T_;
+    C.assign((size_t)ny * nx, 0.0);
+  }
+  double& cm(int i, int j) { return C[(size_t)j * ny + i]; }
   void Alloc(int nx_, int nu_, int nc_) {
     nx = nx_;
     nu = nu_;
@@ -178,6 +188,9 @@ void DoubleIntegrator(Model* m) {
   m->l(5, 0) = 1;
   const double dd[6] = {0, 0, -2, -2, -1, -1};
   for (int i = 0; i < 6; i++) m->d[i] = dd[i];
+  m->Output(2, 40);  // ocp_generator.cc:357-362
+  m->cm(0, 0) = 1;
+  m->cm(1, 1) = 1;
 }
 
 // ocp_generator.cc:245-315
@@ -219,6 +232,9 @@ void ServoMotor(Model* m) {
   m->d[1] = -ymax;
   m->d[2] = -umax;
   m->d[3] = -umax;
+  m->Output(2, 40);  // ocp_generator.cc:271-272,309-314
+  m->cm(0, 0) = 1;
+  for (int j = 0; j < 4; j++) m->cm(1, j) = C1[j];
 }
 
 // ocp_generator.cc:171-244
@@ -308,6 +324,9 @@ void CopolymerizationReactor(Model* m) {
     m->l(5 + i, i) = -1.0;
   }
   for (int i = 0; i < 10; i++) m->d[i] = -umax;
+  m->Output(4, 200);  // ocp_generator.cc:130-138,163-168
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 18; j++) m->cm(i, j) = C[i][j];
 }
 
 bool BuildModel(int kind, Model* m) {

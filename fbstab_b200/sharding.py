@@ -1,38 +1,35 @@
-"""Multi-GPU sharding of a batch of independent QPs.
+"""Multi-GPU sharding of a batch of independent QPs: the Python
+mirror of the C-ABI's multi-GPU section (include/fbstab_b200.h, csrc/multi_gpu.cu).
 
 Every QP instance is an independent solve (reference fbstab_dense.h:136-142:
-one `Solve` = one problem), so a batch shards by instance with no collective
-on the data path: one process per GPU solves a contiguous index range, and the
-only exchange is the gather of the packed results to one rank over
-`torch.distributed` (NCCL on NVLink for CUDA tensors, gloo for the CPU tests).
-
-Packed record of one shard, as one byte buffer:
-    z (nz) | l (nl) | v (nv) | y (nv)   float64, instance-major
-    out                                   OUT_DTYPE records (48 bytes each)
-Shards are padded to the size of the largest one so that a plain `gather`
-works; rank 0 drops the padding and concatenates in rank order, which is the
-global instance order, so the result is byte-identical for every world size.
+one `Solve` = one problem), so a batch shards by contiguous instance ranges with
+no collective on the data path: one process per GPU solves its range with its
+own batch handle, and the only exchange is the result gather.  That gather is
+C++ host code in the library -- one grouped NCCL send/recv per result array,
+straight from each rank's result buffers into the root's global arrays over
+NVLink, no packing and no padding.  `torch.distributed` is used for exactly one
+thing: broadcasting the 128-byte NCCL unique id at start-up (the launcher's own
+channel).  The CPU tests run the same partition / ordering logic under gloo with
+host arrays (`gather_host`).
 """
+import ctypes as C
+
 import numpy as np
 
+from . import capi
 from .capi import OUT_DTYPE
 
 
 def shard_range(batch, world, rank):
-    """Contiguous index range [lo, hi) of `rank`: ceil(batch/world) instances
-    per rank, the last ranks possibly short or empty."""
-    per = -(-batch // world)
-    lo = min(batch, rank * per)
-    return lo, min(batch, lo + per)
+    """Contiguous index range [lo, hi) of `rank` (fbstab_multi_gpu_shard): the
+    first batch % world ranks own one instance more than the others."""
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
 
 
 def shard_sizes(batch, world):
     return [hi - lo for lo, hi in (shard_range(batch, world, r) for r in range(world))]
-
-
-def record_bytes(nz, nl, nv):
-    """Bytes of one instance in the packed result buffer."""
-    return 8 * (nz + nl + 2 * nv) + OUT_DTYPE.itemsize
 
 
 def slice_data(data, field_sizes, lo, hi):
@@ -40,76 +37,99 @@ def slice_data(data, field_sizes, lo, hi):
     return {k: a[lo * field_sizes[k]:hi * field_sizes[k]] for k, a in data.items()}
 
 
-def pack(torch, z, l, v, y, out, count, capacity, sizes):
-    """Packs `count` solved instances into a uint8 tensor with room for
-    `capacity` instances (same device as z).  `out` is a uint8 tensor (device
-    path) or a structured numpy array (host path)."""
-    nz, nl, nv = sizes
-    if isinstance(z, np.ndarray):
-        z, l, v, y = (torch.from_numpy(np.ascontiguousarray(a)) for a in (z, l, v, y))
-    if isinstance(out, np.ndarray):
-        out = torch.from_numpy(np.frombuffer(out.tobytes(), dtype=np.uint8).copy())
-    buf = torch.zeros(capacity * record_bytes(nz, nl, nv), dtype=torch.uint8, device=z.device)
-    off = 0
-    for t, n in ((z, nz), (l, nl), (v, nv), (y, nv)):
-        nb = 8 * n * count
-        if nb:
-            buf[off:off + nb].copy_(t[:n * count].contiguous().view(torch.uint8))
-        off += 8 * n * capacity
-    nb = OUT_DTYPE.itemsize * count
-    buf[off:off + nb].copy_(out[:nb])
-    return buf
+def _bind(L):
+    if getattr(L, "_fbstab_multi_gpu_bound", False):
+        return L
+    L.fbstab_multi_gpu_unique_id.argtypes = [C.c_char_p]
+    L.fbstab_multi_gpu_create.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                          C.POINTER(C.c_void_p)]
+    L.fbstab_multi_gpu_destroy.argtypes = [C.c_void_p]
+    L.fbstab_multi_gpu_shard.argtypes = [C.c_int, C.c_int, C.c_long, C.POINTER(C.c_long),
+                                         C.POINTER(C.c_long)]
+    L.fbstab_multi_gpu_gather.argtypes = ([C.c_void_p, C.c_int, C.c_long] + [C.c_int] * 3 +
+                                          [C.c_void_p] * 10 + [C.c_void_p])
+    L._fbstab_multi_gpu_bound = True
+    return L
 
 
-def unpack(buf, count, capacity, sizes):
-    """Inverse of pack(): numpy (z, l, v, y, out) of the first `count` instances."""
-    nz, nl, nv = sizes
-    raw = buf.cpu().numpy() if hasattr(buf, "cpu") else np.asarray(buf)
-    res, off = [], 0
-    for n in (nz, nl, nv, nv):
-        res.append(np.frombuffer(raw[off:off + 8 * n * count].tobytes(), dtype=np.float64))
-        off += 8 * n * capacity
-    out = np.frombuffer(raw[off:off + OUT_DTYPE.itemsize * count].tobytes(), dtype=OUT_DTYPE)
-    return (*res, out)
+def c_shard_range(batch, world, rank):
+    """The same range from the library (tests check it equals shard_range)."""
+    first, count = C.c_long(), C.c_long()
+    capi.check(_bind(capi.lib()).fbstab_multi_gpu_shard(world, rank, batch, C.byref(first),
+                                                        C.byref(count)))
+    return first.value, first.value + count.value
 
 
-def gather_results(torch, dist, packed, batch, sizes, dst=0, group=None):
-    """Gathers every rank's packed shard to `dst`.  Returns (z, l, v, y, out)
-    for the whole batch in global instance order on `dst`, None elsewhere."""
+class MultiGpu:
+    """One rank of a one-process-per-GPU job (fbstab_multi_gpu_*)."""
+
+    def __init__(self, rank, world, device, dist=None, torch=None):
+        self.rank, self.world, self.device = rank, world, device
+        self._h = C.c_void_p()
+        L = _bind(capi.lib())
+        ident = C.create_string_buffer(128)
+        if world > 1:
+            if rank == 0:
+                capi.check(L.fbstab_multi_gpu_unique_id(ident))
+            # the launcher's channel carries the id to the other ranks
+            dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else "cpu"
+            t = torch.frombuffer(bytearray(ident.raw), dtype=torch.uint8).to(dev)
+            dist.broadcast(t, src=0)
+            ident = C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+        capi.check(L.fbstab_multi_gpu_create(rank, world, ident, device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            capi.lib().fbstab_multi_gpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
+
+    def shard(self, global_batch):
+        return shard_range(global_batch, self.world, self.rank)
+
+    def gather(self, global_batch, sizes, shard, full=None, root=0, stream=None):
+        """shard = (z, l, v, y, out) device tensors of this rank's instances;
+        full = (Z, L, V, Y, OUT) device tensors of the whole batch on `root`
+        (None elsewhere).  Enqueues on `stream`; returns nothing."""
+        nz, nl, nv = sizes
+        full = full if full is not None else (None,) * 5
+        capi.check(capi.lib().fbstab_multi_gpu_gather(
+            self._h, root, global_batch, nz, nl, nv, *[capi.ptr(t) for t in shard],
+            *[capi.ptr(t) for t in full], stream))
+
+
+# ---- host-array path (gloo): the partition / ordering logic on CPU ---------------
+def gather_host(dist, parts, batch, dst=0, group=None):
+    """parts = (z, l, v, y, out) numpy arrays of this rank's shard.  Returns the
+    five arrays of the whole batch in global instance order on `dst`, None on the
+    other ranks.  Shards arrive in rank order, which IS the global order."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    counts = shard_sizes(batch, world)
-    cap = max(counts)
-    assert packed.numel() == cap * record_bytes(*sizes), "shards must be padded to capacity"
-    bufs = [torch.empty_like(packed) for _ in range(world)] if rank == dst else None
-    dist.gather(packed, bufs, dst=dst, group=group)
+    objs = [None] * world if rank == dst else None
+    dist.gather_object([np.ascontiguousarray(a) for a in parts], objs, dst=dst, group=group)
     if rank != dst:
         return None
-    parts = [unpack(b, c, cap, sizes) for b, c in zip(bufs, counts)]
-    return tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
+    counts = shard_sizes(batch, world)
+    assert [len(o[4]) for o in objs] == counts, "every rank must send exactly its range"
+    return tuple(np.concatenate([o[k] for o in objs]) for k in range(5))
 
 
-def solve_sharded(torch, dist, solve_shard, data, field_sizes, batch, sizes, group=None,
-                  device=None):
+def solve_sharded(dist, solve_shard, data, field_sizes, batch, group=None):
     """Shards `batch` instances over the ranks of `group`, calls
-    `solve_shard(data_shard, count) -> (z, l, v, y, out)` on this rank's range
-    and gathers the results to rank 0 (None on the other ranks).
-
-    `data` holds the WHOLE batch on every rank (instance-major numpy arrays or
-    tensors); a rank only touches its own rows.  `solve_shard` is normally
-    `lambda d, n: FBstabDense(...).solve_batch(...)`; the CPU tests pass a
-    stand-in so that the partition + pack + gather logic runs under gloo."""
+    `solve_shard(data_shard, count) -> (z, l, v, y, out)` (numpy) on this rank's
+    range and gathers the results to rank 0 (None on the other ranks).  `data`
+    holds the whole batch on every rank; a rank only touches its own rows."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     lo, hi = shard_range(batch, world, rank)
-    cap = max(shard_sizes(batch, world))
-    nz, nl, nv = sizes
     if hi > lo:
-        z, l, v, y, out = solve_shard(slice_data(data, field_sizes, lo, hi), hi - lo)
+        parts = solve_shard(slice_data(data, field_sizes, lo, hi), hi - lo)
     else:
         e = np.zeros(0)
-        z, l, v, y, out = e, e, e, e, np.zeros(0, dtype=OUT_DTYPE)
-    packed = pack(torch, z, l, v, y, out, hi - lo, cap, sizes)
-    if device is not None:
-        packed = packed.to(device)
-    return gather_results(torch, dist, packed, batch, sizes, group=group)
+        parts = (e, e, e, e, np.zeros(0, dtype=OUT_DTYPE))
+    return gather_host(dist, parts, batch, group=group)

@@ -18,18 +18,33 @@ def _is_host(a):
     return isinstance(a, np.ndarray)
 
 
-def _flat(a, n, name):
+def _flat(a, n, name, device=None, dtype_bytes=8):
+    """Checks one C-ABI argument before its raw pointer is handed over: element
+    count, float64 (or `dtype_bytes`-wide records), contiguity and -- for CUDA
+    tensors -- the device of the handle.  Raises RuntimeError (never assert: the
+    kernels would read past a mis-typed allocation)."""
     if a is None:
         if n == 0:
             return None
         raise RuntimeError(f"{name} is required")
-    size = a.size if isinstance(a, np.ndarray) else a.numel()
-    if size != n:
-        raise RuntimeError(
-            f"size mismatch for {name}: expected {n} elements, got {size}")
     if isinstance(a, np.ndarray):
-        if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+        if a.size != n:
+            raise RuntimeError(f"size mismatch for {name}: expected {n} elements, got {a.size}")
+        if a.dtype.itemsize != dtype_bytes or (dtype_bytes == 8 and a.dtype != np.float64) or \
+                not a.flags["C_CONTIGUOUS"]:
             raise RuntimeError(f"{name} must be contiguous float64")
+        return a
+    if not hasattr(a, "data_ptr"):
+        raise RuntimeError(f"{name}: expected a numpy array or a torch tensor, got {type(a)}")
+    if a.numel() * a.element_size() != n * dtype_bytes:
+        raise RuntimeError(f"size mismatch for {name}: expected {n * dtype_bytes} bytes, "
+                           f"got {a.numel() * a.element_size()}")
+    if dtype_bytes == 8 and str(a.dtype) != "torch.float64":
+        raise RuntimeError(f"{name} must be a float64 tensor, got {a.dtype}")
+    if not a.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if a.is_cuda and device is not None and a.device.index != device:
+        raise RuntimeError(f"{name} lives on cuda:{a.device.index}, the solver on cuda:{device}")
     return a
 
 
@@ -77,7 +92,7 @@ class _Base:
 
     def _data_ptrs(self, data, batch):
         sizes = self.field_sizes
-        return [capi.ptr(_flat(data[k], batch * sizes[k], k)) for k in self._fields]
+        return [capi.ptr(_flat(data[k], batch * sizes[k], k, self.device)) for k in self._fields]
 
     def solve_batch(self, data, z, l, v, y=None, out=None, stream=None):
         """Solve `batch` instances.  `data` maps field name -> flat array
@@ -86,9 +101,13 @@ class _Base:
         batch = (z.size if _is_host(z) else z.numel()) // self.nz
         if batch > self.max_batch:
             raise RuntimeError("batch exceeds max_batch")
-        _flat(z, batch * self.nz, "z")
-        _flat(l, batch * self.nl, "l")
-        _flat(v, batch * self.nv, "v")
+        _flat(z, batch * self.nz, "z", self.device)
+        _flat(l, batch * self.nl, "l", self.device)
+        _flat(v, batch * self.nv, "v", self.device)
+        if y is not None:
+            _flat(y, batch * self.nv, "y", self.device)
+        if out is not None:
+            _flat(out, batch, "out", self.device, dtype_bytes=OUT_DTYPE.itemsize)
         if y is None:
             y = np.zeros(batch * self.nv) if _is_host(z) else z.new_zeros(batch * self.nv)
         if out is None:
@@ -131,6 +150,7 @@ class FBstabDense(_Base):
             raise RuntimeError("In FBstabDense::FBstabDense: nz and nv must be "
                                "positive, nl nonnegative")
         self.nz, self.nl, self.nv, self.max_batch = nz, nl, nv, max_batch
+        self.device = device
         self.field_sizes = {"H": nz * nz, "f": nz, "G": nl * nz, "h": nl,
                             "A": nv * nz, "b": nv}
         capi.check(capi.lib().fbstab_dense_batch_create(
@@ -172,6 +192,7 @@ class FBstabMpc(_Base):
                 "In FBstabMpc::FBstabMpc: problem sizes must be positive.")
         self.N, self.nx, self.nu, self.nc = N, nx, nu, nc
         self.max_batch = max_batch
+        self.device = device
         K = N + 1
         self.nz, self.nl, self.nv = K * (nx + nu), K * nx, K * nc
         self.field_sizes = {"Q": K * nx * nx, "R": K * nu * nu, "S": K * nu * nx,
@@ -180,6 +201,44 @@ class FBstabMpc(_Base):
                             "L": K * nc * nu, "d": K * nc, "x0": nx}
         capi.check(capi.lib().fbstab_mpc_batch_create(
             N, nx, nu, nc, max_batch, device, C.byref(self._h)))
+
+    def _solve_one_copy(self, fn_name, sizes, data, z, l, v, y, out, stream):
+        batch = (z.size if _is_host(z) else z.numel()) // self.nz
+        if batch > self.max_batch:
+            raise RuntimeError("batch exceeds max_batch")
+        _flat(z, batch * self.nz, "z", self.device)
+        _flat(l, batch * self.nl, "l", self.device)
+        _flat(v, batch * self.nv, "v", self.device)
+        if y is None:
+            y = np.zeros(batch * self.nv) if _is_host(z) else z.new_zeros(batch * self.nv)
+        if out is None:
+            if _is_host(z):
+                out = np.zeros(batch, dtype=OUT_DTYPE)
+            else:
+                import torch
+                out = torch.zeros(batch * OUT_DTYPE.itemsize, dtype=torch.uint8, device=z.device)
+        ptrs = [capi.ptr(_flat(data[k], (batch if k == "x0" else 1) * sizes[k], k, self.device))
+                for k in self._fields]
+        fn = getattr(capi.lib(), fn_name)
+        fn.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 18
+        capi.check(fn(self._h, batch, *ptrs, capi.ptr(z), capi.ptr(l), capi.ptr(v), capi.ptr(y),
+                      capi.ptr(out), stream))
+        return out, y
+
+    def solve_batch_shared(self, data, z, l, v, y=None, out=None, stream=None):
+        """ONE copy of the 11 stage-data sequences for the whole batch; data["x0"]
+        holds the `batch` initial states (fbstab_mpc_batch_solve_shared)."""
+        return self._solve_one_copy("fbstab_mpc_batch_solve_shared", self.field_sizes, data,
+                                    z, l, v, y, out, stream)
+
+    def solve_batch_lti(self, data, z, l, v, y=None, out=None, stream=None):
+        """ONE STAGE of each sequence (time-invariant problem), replicated over the
+        horizon like OcpGenerator::CopyOverHorizon (fbstab_mpc_batch_solve_lti)."""
+        nx, nu, nc = self.nx, self.nu, self.nc
+        one = {"Q": nx * nx, "R": nu * nu, "S": nu * nx, "q": nx, "r": nu, "A": nx * nx,
+               "B": nx * nu, "c": nx, "E": nc * nx, "L": nc * nu, "d": nc, "x0": nx}
+        return self._solve_one_copy("fbstab_mpc_batch_solve_lti", one, data, z, l, v, y, out,
+                                    stream)
 
     def solve(self, data, x0=None):
         """One instance; `data` as produced by problems.ocp_batch(count=1)."""

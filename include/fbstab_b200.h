@@ -181,6 +181,70 @@ int fbstab_mpc_batch_solve(fbstab_mpc_batch* handle, int batch, const double* Q,
 int fbstab_mpc_batch_last_launches(const fbstab_mpc_batch* handle);
 const char* fbstab_mpc_batch_path(const fbstab_mpc_batch* handle);
 
+/* Shared stage data: ONE copy of the 11 sequences for the whole batch, x0 (and
+ * the iterates) per instance -- one plant solved from `batch` initial states,
+ * which is the MPC use case and exactly what the reference's wire format cannot
+ * say: FBstabMpc::ProblemDataRef (fbstab/fbstab_mpc.h:90-120) points at one
+ * MapMatrixSequence per field (tools/matrix_sequence.h:88-164), so a batch in
+ * that format repeats the same matrices `batch` times.  Ships 1/batch of the
+ * bytes and skips the device-side common-data detection of
+ * fbstab_mpc_batch_solve; results are bit-identical to passing the replicated
+ * data. */
+int fbstab_mpc_batch_solve_shared(fbstab_mpc_batch* handle, int batch,
+                                  const double* Q, const double* R, const double* S,
+                                  const double* q, const double* r, const double* A,
+                                  const double* B, const double* c, const double* E,
+                                  const double* L, const double* d, const double* x0,
+                                  double* z, double* l, double* v, double* y,
+                                  fbstab_out* out, void* stream);
+/* Time-invariant (LTI) problem: ONE STAGE of each sequence (Q nx*nx, R nu*nu,
+ * S nu*nx, q nx, r nu, A nx*nx, B nx*nu, c nx, E nc*nx, L nc*nu, d nc),
+ * replicated over the horizon as OcpGenerator::CopyOverHorizon does
+ * (fbstab/test/ocp_generator.cc:397-418): stages 0..N (A, B, c: 0..N-1), with
+ * E(0) = 0 -- no constraint on the measured state. */
+int fbstab_mpc_batch_solve_lti(fbstab_mpc_batch* handle, int batch, const double* Q,
+                               const double* R, const double* S, const double* q,
+                               const double* r, const double* A, const double* B,
+                               const double* c, const double* E, const double* L,
+                               const double* d, const double* x0, double* z,
+                               double* l, double* v, double* y, fbstab_out* out,
+                               void* stream);
+
+/* ---- receding-horizon (closed-loop) MPC ----------------------------------
+ * What OcpGenerator::GetSimulationInputs exists for (fbstab/test/
+ * ocp_generator.h:31-38,69; ocp_generator.cc:56-71) and what the reference's
+ * README calls "can be easily warmstarted" (README.md:20): `batch` plants are
+ * simulated for T control steps.  One step, for every plant at once and entirely
+ * on the device: shift the previous solution by one stage (warm start), solve
+ * the OCP from the current state, apply the first input to the plant
+ * x+ = Asim x + Bsim u (Asim = NULL: stage 0 of the plant's own OCP,
+ * x+ = A(0) x + B(0) u + c(0)), log x and u.  The handle owns the data, the
+ * iterates and the logs; a step only enqueues kernels on `stream`.
+ * shared_data != 0: the 11 sequences are one copy for all plants.  A plant
+ * whose solve ends infeasible / failed holds its previous input and restarts
+ * cold.  run(): T steps from x_init, then X (batch x (T+1) x nx), U (batch x T
+ * x nu) and out (T x batch) are copied to the caller (host or device, any may
+ * be NULL). */
+typedef struct fbstab_mpc_closed_loop fbstab_mpc_closed_loop;
+int fbstab_mpc_closed_loop_create(int N, int nx, int nu, int nc, int batch, int device,
+                                  int shared_data, const double* Q, const double* R,
+                                  const double* S, const double* q, const double* r,
+                                  const double* A, const double* B, const double* c,
+                                  const double* E, const double* L, const double* d,
+                                  const double* x_init, const double* Asim,
+                                  const double* Bsim, int max_steps,
+                                  fbstab_mpc_closed_loop** handle);
+int fbstab_mpc_closed_loop_destroy(fbstab_mpc_closed_loop* handle);
+int fbstab_mpc_closed_loop_set_options(fbstab_mpc_closed_loop* handle,
+                                       const fbstab_options* o);
+int fbstab_mpc_closed_loop_reset(fbstab_mpc_closed_loop* handle, void* stream);
+int fbstab_mpc_closed_loop_step(fbstab_mpc_closed_loop* handle, int warm_start,
+                                void* stream);
+int fbstab_mpc_closed_loop_run(fbstab_mpc_closed_loop* handle, int steps,
+                               int warm_start, double* X, double* U, fbstab_out* out,
+                               void* stream);
+const char* fbstab_mpc_closed_loop_path(const fbstab_mpc_closed_loop* handle);
+
 /* ---- component stages (for per-kernel parity tests) ----------------------
  * One CTA per instance runs ONE stage of the engine on caller-supplied
  * iterates.  All pointers host or device as above; unused ones may be NULL.

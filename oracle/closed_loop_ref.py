@@ -18,6 +18,7 @@ def closed_loop_reference(dims, data, T, solve, warm_start=True, shift=True):
     x = d["x0"].reshape(B, nx)
     X, U = np.zeros((B, T + 1, nx)), np.zeros((B, T, nu))
     X[:, 0] = x
+    u_prev = np.zeros((B, nu))
     flags, newton = np.zeros((T, B), dtype=np.int32), np.zeros((T, B), dtype=np.int32)
     for t in range(T):
         if not warm_start:
@@ -28,7 +29,13 @@ def closed_loop_reference(dims, data, T, solve, warm_start=True, shift=True):
                 a[:, :-1] = a[:, 1:].copy()
         out, z, l, v = solve(dims, d, (z, l, v))
         flags[t], newton[t] = out["eflag"], out["newton_iters"]
-        u0 = z.reshape(B, K, nx + nu)[:, 0, nx:]
+        # csrc/closed_loop.cu: a plant whose solve ends infeasible / failed holds its
+        # previous input and restarts cold (the iterate holds a certificate, not a control)
+        good = (out["status"] == 0) & ((out["eflag"] == 0) | (out["eflag"] == 2))
+        u_prev[good] = z.reshape(B, K, nx + nu)[good, 0, nx:]
+        for arr, w in ((z, nx + nu), (l, nx), (v, nc)):
+            arr.reshape(B, K * w)[~good] = 0.0
+        u0 = u_prev
         U[:, t] = u0
         x[:] = np.einsum("bij,bj->bi", A, x) + np.einsum("bij,bj->bi", Bm, u0) + c
         X[:, t + 1] = x

@@ -19,7 +19,11 @@ CASES = [("servo_motor", 50, 16384, 40, 0.02), ("double_integrator", 50, 16384, 
 
 def run(kind, N, B, T, rho, cpu_sample=256):
     dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=rho)
-    cl = fb.ClosedLoopMpc(dims, d)
+    # ONE copy of the plant's OCP data, B initial states (the C-ABI's shared-data mode)
+    s = fb.FBstabMpc(*dims, max_batch=1)
+    one = {k: (a if k == "x0" else a[:s.field_sizes[k]].copy()) for k, a in d.items()}
+    del s
+    cl = fb.ClosedLoopMpc(dims, one, shared=True, max_steps=T)
     cl.run(2)  # warm-up
     warm = cl.run(T)
     cold = cl.run(T, warm_start=False)

@@ -28,7 +28,7 @@ FAMILIES = {
     "dense_512_128_1024": ("dense", (512, 128, 1024), 16, 5, None),
     "servo_motor_N50": ("mpc", ("servo_motor", 50), 2048, 3, 0.02),
     "double_integrator_N50": ("mpc", ("double_integrator", 50), 2048, 3, -0.1),
-    "spacecraft_N40": ("mpc", ("spacecraft", 40), 64, 4, 0.05),
+    "spacecraft_N40": ("mpc", ("spacecraft", 40), 256, 4, 0.01),
     "copolymerization_N100": ("mpc", ("copolymerization", 100), 256, 4, 0.05),
 }
 

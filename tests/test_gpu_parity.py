@@ -7,16 +7,19 @@ relative in FP64.  The FP64 arithmetic of the two sides differs only in
 summation order and FMA contraction, which leaves the trajectory unchanged on
 well-conditioned instances; where sigma = 1e-8 makes the Newton system so
 ill-conditioned that rounding alone moves an instance across a convergence
-threshold (documented in DESIGN.md: two builds of the *oracle itself*, with and
-without FMA, differ by +-1 iteration on ~4% of servo-motor instances), the
-tests bound the fraction of such instances and check them at the solver's own
-tolerance instead of hiding them.
+threshold, the tests take their threshold from a MEASURED floor: two builds of
+the oracle itself, without and with FMA contraction, on the same instances
+(tests/golden/trajectory_floor.json, tests/test_oracle_fma_floor.py: 100% of the
+dense 32/8/64 and double-integrator families, 97.6% of servo-motor instances).
+`required_same_frac` is that floor minus the sampling margin; off-trajectory
+instances must still agree to 1e-5 (the two oracle builds differ by up to
+3.6e-6 there) and by at most 2 Newton iterations.
 """
 import numpy as np
 import pytest
 
-from util import (DENSE_CASES, DI2_L, DI2_V, DI2_Z, MPC_CASES, colmajor,
-                  component_ocp, dense_case, rel_err)
+from util import (DENSE_CASES, DI2_L, DI2_V, DI2_Z, FAMILY_OF_OCP, MPC_CASES, colmajor,
+                  component_ocp, dense_case, rel_err, required_same_frac)
 
 pytestmark = pytest.mark.gpu
 
@@ -252,7 +255,8 @@ def test_dense_batch_parity(fb, oracle, sizes, B):
     assert (out["eflag"] == oo["eflag"]).all()
     assert (out["eflag"] == 0).all() and (out["status"] == 0).all()
     same = _same_traj(out, oo)
-    assert same.mean() >= 0.98, f"trajectory differs on {(~same).sum()} of {B}"
+    assert same.mean() >= required_same_frac("dense_32_8_64", B), \
+        f"trajectory differs on {(~same).sum()} of {B}"
     Z, OZ = z.reshape(B, nz), oz.reshape(B, nz)
     V, OV = v.reshape(B, nv), ov.reshape(B, nv)
     for i in range(B):
@@ -347,12 +351,13 @@ def test_mpc_batch_parity(fb, oracle, kind, N, B, rho):
     assert (out["eflag"] == oo["eflag"]).all(), (out["eflag"], oo["eflag"])
     same = _same_traj(out, oo)
     # see the module docstring: rounding-level trajectory sensitivity at sigma=1e-8
-    assert same.mean() >= 0.85, f"trajectory differs on {(~same).sum()} of {B}"
-    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 3
+    assert same.mean() >= required_same_frac(FAMILY_OF_OCP[kind], B), \
+        f"trajectory differs on {(~same).sum()} of {B}"
+    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 2
     Z, OZ = z.reshape(B, -1), oz.reshape(B, -1)
     ok = out["eflag"] == 0
     for i in np.nonzero(ok)[0]:
-        tol = SOL_TOL if same[i] else 1e-4
+        tol = SOL_TOL if same[i] else 1e-5
         assert rel_err(Z[i], OZ[i]) <= tol, (i, rel_err(Z[i], OZ[i]), same[i])
 
 
@@ -375,12 +380,13 @@ def test_mpc_lane_path_parity(fb, oracle, monkeypatch, kind, N, B, rho):
     assert (out["status"] == 0).all()
     assert (out["eflag"] == oo["eflag"]).all(), (out["eflag"], oo["eflag"])
     same = _same_traj(out, oo)
-    assert same.mean() >= 0.85, f"trajectory differs on {(~same).sum()} of {B}"
-    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 3
+    assert same.mean() >= required_same_frac(FAMILY_OF_OCP[kind], B), \
+        f"trajectory differs on {(~same).sum()} of {B}"
+    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 2
     Z, OZ = z.reshape(B, -1), oz.reshape(B, -1)
     Y, OY = y.reshape(B, -1), oy.reshape(B, -1)
     for i in np.nonzero(out["eflag"] == 0)[0]:
-        tol = SOL_TOL if same[i] else 1e-4
+        tol = SOL_TOL if same[i] else 1e-5
         assert rel_err(Z[i], OZ[i]) <= tol, (i, rel_err(Z[i], OZ[i]), same[i])
         assert rel_err(Y[i], OY[i]) <= tol * 10
     # a small batch of the same problem runs the CTA kernel: same answers
@@ -443,12 +449,17 @@ def test_mpc_time_varying_data(fb, oracle, monkeypatch, shape, N, B):
     assert (out["eflag"] == oo["eflag"]).all(), (out["eflag"], oo["eflag"])
     assert (oo["eflag"] == 0).mean() >= 0.9, "the generator should produce solvable OCPs"
     same = _same_traj(out, oo)
-    assert same.mean() >= 0.85, f"trajectory differs on {(~same).sum()} of {B}"
+    # random data has no committed floor: measure it here, oracle (no FMA) vs oracle (FMA)
+    of = oracle.mpc_solve_batch(*dims, [d[k] for k in fb.problems.MPC_FIELDS], nthreads=8,
+                                fma=True)[0]
+    floor_here = _same_traj(of, oo).mean()
+    need = floor_here - max(0.05, 3.0 * (floor_here * (1 - floor_here) / B) ** 0.5)
+    assert same.mean() >= need, f"trajectory differs on {(~same).sum()} of {B} (floor {floor_here})"
     assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 3
     Z, OZ = z.reshape(B, -1), oz.reshape(B, -1)
     V, OV = v.reshape(B, -1), ov.reshape(B, -1)
     for i in np.nonzero(out["eflag"] == 0)[0]:
-        tol = SOL_TOL if same[i] else 1e-4
+        tol = SOL_TOL if same[i] else 1e-5
         assert rel_err(Z[i], OZ[i]) <= tol, (i, rel_err(Z[i], OZ[i]), same[i])
         assert rel_err(V[i], OV[i]) <= tol * 100, (i, rel_err(V[i], OV[i]))
 
@@ -504,6 +515,74 @@ def test_closed_loop_mpc_parity(fb, oracle, monkeypatch, kind, N, B, T, rho):
     cold = cl.run(T, warm_start=False)
     assert got["newton_iters"][1:].sum() < cold["newton_iters"][1:].sum()
     assert rel_err(cold["U"][ok], ref["U"][ok]) <= 1e-5
+
+
+@pytest.mark.parametrize("kind,N,B,rho,lane", [("servo_motor", 20, 384, 0.02, True),
+                                              ("double_integrator", 15, 300, 0.6, True),
+                                              ("copolymerization", 12, 24, 0.05, False),
+                                              ("spacecraft", 10, 40, 0.05, False),
+                                              ("servo_motor", 20, 64, 0.02, False)])
+def test_mpc_shared_and_lti_entries_are_bit_identical(fb, monkeypatch, kind, N, B, rho, lane):
+    """fbstab_mpc_batch_solve_shared (ONE copy of the stage data) and
+    fbstab_mpc_batch_solve_lti (ONE STAGE, replicated like CopyOverHorizon) return the
+    bytes of the wire-format call that ships every instance's matrices -- on the lane
+    kernel and on the CTA kernel, with host and with device buffers."""
+    import torch
+    monkeypatch.setenv("FBSTAB_MPC_LANE_MIN", "256")
+    dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=rho)
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    assert s.path.startswith("mpc-lane") == lane, s.path
+    new = lambda: (np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv))
+    z, l, v = new()
+    out, y = s.solve_batch(d, z, l, v)
+    ref = (z, l, v, y, out["eflag"].copy(), out["newton_iters"].copy(), out["residual"].copy())
+    # one copy of every sequence = the first instance's rows
+    one = {k: (a if k == "x0" else a[:s.field_sizes[k]].copy()) for k, a in d.items()}
+    z, l, v = new()
+    out, y = s.solve_batch_shared(one, z, l, v)
+    got = (z, l, v, y, out["eflag"].copy(), out["newton_iters"].copy(), out["residual"].copy())
+    for a, b_ in zip(ref, got):
+        assert np.array_equal(a, b_)
+    # one stage: the OCP fixtures are time-invariant with E(0) = 0; stage 1 carries E
+    N_, nx, nu, nc = dims
+    st = {"Q": nx * nx, "R": nu * nu, "S": nu * nx, "q": nx, "r": nu, "A": nx * nx,
+          "B": nx * nu, "c": nx, "E": nc * nx, "L": nc * nu, "d": nc}
+    lti = {k: d[k][st[k]:2 * st[k]].copy() for k in st}
+    lti["x0"] = d["x0"]
+    z, l, v = new()
+    out, y = s.solve_batch_lti(lti, z, l, v)
+    got = (z, l, v, y, out["eflag"].copy(), out["newton_iters"].copy(), out["residual"].copy())
+    for a, b_ in zip(ref, got):
+        assert np.array_equal(a, b_)
+    # device pointers: asynchronous, in place
+    dev = torch.device("cuda:0")
+    dd = {k: torch.from_numpy(a).to(dev) for k, a in one.items()}
+    zt, lt, vt = (torch.zeros(n, dtype=torch.float64, device=dev) for n in (B * s.nz, B * s.nl, B * s.nv))
+    o_dev, y_dev = s.solve_batch_shared(dd, zt, lt, vt)
+    torch.cuda.synchronize()
+    assert np.array_equal(zt.cpu().numpy(), ref[0]) and np.array_equal(y_dev.cpu().numpy(), ref[3])
+
+
+def test_closed_loop_entry_shared_data_and_explicit_plant(fb):
+    """fbstab_mpc_closed_loop_* with ONE copy of the OCP data equals the per-plant-data
+    loop bit for bit, and an explicit plant model (GetSimulationInputs' A, B) that
+    equals stage 0 of the OCP gives the same trajectory."""
+    kind, N, B, T = "double_integrator", 10, 64, 6
+    dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=0.3)
+    a = fb.ClosedLoopMpc(dims, d, max_steps=T).run(T)
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    one = {k: (x if k == "x0" else x[:s.field_sizes[k]].copy()) for k, x in d.items()}
+    b = fb.ClosedLoopMpc(dims, one, shared=True, max_steps=T).run(T)
+    for k in ("X", "U", "eflag", "newton_iters"):
+        assert np.array_equal(a[k], b[k]), k
+    nx, nu = dims[1], dims[2]
+    A0 = d["A"][:nx * nx].reshape(nx, nx).T  # column-major block -> matrix
+    B0 = d["B"][:nx * nu].reshape(nu, nx).T
+    assert not d["c"].any()  # the double integrator has no offset: A x + B u is the plant
+    c_ = fb.ClosedLoopMpc(dims, one, shared=True, Asim=A0, Bsim=B0, max_steps=T).run(T)
+    for k in ("X", "U", "eflag"):
+        assert np.array_equal(a[k], c_[k]), k
+    assert a["X"].shape == (B, T + 1, nx) and np.abs(a["U"]).max() > 0
 
 
 @pytest.mark.parametrize("kind,N,B,rho", [("servo_motor", 20, 384, 0.02),
@@ -619,22 +698,46 @@ def test_dense_config2_full_size(fb):
 
 
 def test_dense_config5_sample(fb, oracle):
-    """BASELINE config 5 shape (nz=512 nl=128 nv=1024), a small batch vs the
-    oracle plus the independent KKT check."""
-    nz, nl, nv, B = 512, 128, 1024, 3
+    """BASELINE config 5 shape (nz=512 nl=128 nv=1024): EVERY instance of a small batch
+    against the oracle (flags, trajectory up to the measured floor, solutions to 1e-8)
+    plus the independent KKT check."""
+    nz, nl, nv, B = 512, 128, 1024, 6
     d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=5)
     s = fb.FBstabDense(nz, nl, nv, max_batch=B)
     z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
     out, y = s.solve_batch(d, z, l, v)
     assert (out["eflag"] == 0).all()
     assert _kkt_check_dense(d, nz, nl, nv, z, l, v, y, range(B)) <= 2e-6
-    oo, oz, *_ = oracle.dense_solve_batch(
-        nz, nl, nv, *[d[k][:sz] for k, sz in
-                      zip(fb.problems.DENSE_FIELDS,
-                          (nz * nz, nz, nl * nz, nl, nv * nz, nv))], variant=2)
-    assert out["newton_iters"][0] == oo["newton_iters"][0]
-    assert out["prox_iters"][0] == oo["prox_iters"][0]
-    assert rel_err(z[:nz], oz) <= SOL_TOL
+    oo, oz, *_ = oracle.dense_solve_batch(nz, nl, nv, *[d[k] for k in fb.problems.DENSE_FIELDS],
+                                          variant=2, nthreads=6)
+    assert (out["eflag"] == oo["eflag"]).all()
+    assert np.abs(out["newton_iters"] - oo["newton_iters"]).max() <= 2
+    same = _same_traj(out, oo)
+    # the oracle's own FMA / no-FMA builds agree on 15 of 16 such instances
+    # (tests/golden/trajectory_floor.json): at most one of six may differ
+    assert same.sum() >= B - 1, (out["newton_iters"], oo["newton_iters"])
+    for i in range(B):
+        assert rel_err(z[i * nz:(i + 1) * nz], oz[i * nz:(i + 1) * nz]) <= SOL_TOL, i
+
+
+def test_mpc_config4b_copolymerization_full_horizon(fb, oracle):
+    """BASELINE config 4b at its full horizon (copolymerisation reactor, N=100: nz=2323,
+    892 KB of stage data per instance): every instance of a small batch against the
+    oracle."""
+    B = 12
+    dims, d = fb.problems.ocp_batch("copolymerization", 100, count=B, config=4, rho=0.05)
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    z, l, v = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, oz, ol, ov, oy = oracle.mpc_solve_batch(*dims, [d[k] for k in fb.problems.MPC_FIELDS],
+                                                nthreads=8)
+    assert (out["status"] == 0).all() and (out["eflag"] == oo["eflag"]).all()
+    assert (out["eflag"] == 0).all()
+    assert _same_traj(out, oo).all(), (out["newton_iters"], oo["newton_iters"])
+    Z, OZ = z.reshape(B, -1), oz.reshape(B, -1)
+    for i in range(B):
+        assert rel_err(Z[i], OZ[i]) <= SOL_TOL, (i, rel_err(Z[i], OZ[i]))
+    np.testing.assert_allclose(out["residual"], oo["residual"], rtol=1e-5, atol=1e-11)
 
 
 @pytest.mark.parametrize("sizes,B", [((136, 24, 200), 6), ((200, 70, 130), 4),

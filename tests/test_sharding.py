@@ -1,7 +1,10 @@
 """Multi-rank path on CPU: world_size-2 and -3 `gloo` process groups run the
-partition -> solve -> pack -> gather logic of fbstab_b200.sharding with the CPU
-oracle standing in for the GPU solve, and rank 0 must receive exactly the bytes
-a single process produces (identical bytes for every G)."""
+partition -> solve -> gather logic of fbstab_b200.sharding with the CPU oracle
+standing in for the GPU solve, and rank 0 must receive exactly the bytes a single
+process produces (identical bytes for every G).  The NCCL gather
+of the C-ABI itself (fbstab_multi_gpu_gather) needs GPUs: tests/multi_gpu_check.py
+runs it under torchrun and compares the gathered bytes with a single-GPU solve;
+here the library's shard arithmetic and argument checks are covered."""
 import os
 import socket
 import sys
@@ -41,8 +44,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         sizes = {"H": NZ * NZ, "f": NZ, "G": NL * NZ, "h": NL, "A": NV * NZ, "b": NV}
-        res = fb.sharding.solve_sharded(torch, dist, _oracle_solve, _problem(), sizes,
-                                        BATCH, (NZ, NL, NV))
+        res = fb.sharding.solve_sharded(dist, _oracle_solve, _problem(), sizes, BATCH)
         if rank == 0:
             q.put([a.tobytes() for a in res])
         else:
@@ -59,25 +61,29 @@ def test_shard_ranges_cover_the_batch():
             assert r[0][0] == 0 and r[-1][1] == batch
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             assert sum(sharding.shard_sizes(batch, world)) == batch
-            assert max(sharding.shard_sizes(batch, world)) == -(-batch // world)
+            sizes = sharding.shard_sizes(batch, world)
+            assert max(sizes) == -(-batch // world) and max(sizes) - min(sizes) <= 1
+            # the C-ABI's fbstab_multi_gpu_shard is the same arithmetic
+            for k in range(world):
+                assert sharding.c_shard_range(batch, world, k) == r[k]
 
 
-def test_pack_unpack_round_trip():
-    import torch
-    from fbstab_b200 import sharding
-    from fbstab_b200.capi import OUT_DTYPE
-    rng = np.random.default_rng(3)
-    count, cap = 3, 5
-    z, l = rng.normal(size=count * NZ), rng.normal(size=count * NL)
-    v, y = rng.normal(size=count * NV), rng.normal(size=count * NV)
-    out = np.zeros(count, dtype=OUT_DTYPE)
-    out["eflag"] = [0, 3, 4]
-    out["residual"] = rng.normal(size=count)
-    buf = sharding.pack(torch, z, l, v, y, out, count, cap, (NZ, NL, NV))
-    assert buf.numel() == cap * sharding.record_bytes(NZ, NL, NV)
-    z2, l2, v2, y2, out2 = sharding.unpack(buf, count, cap, (NZ, NL, NV))
-    for a, b in ((z, z2), (l, l2), (v, v2), (y, y2), (out, out2)):
-        assert a.tobytes() == b.tobytes()
+def test_multi_gpu_entry_points_reject_bad_arguments():
+    """No GPU here: argument checks and the no-GPU error of the multi-GPU C-ABI."""
+    import ctypes as C
+    from fbstab_b200 import capi, sharding
+    L = sharding._bind(capi.lib())
+    first, count = C.c_long(), C.c_long()
+    assert L.fbstab_multi_gpu_shard(0, 0, 10, C.byref(first), C.byref(count)) == capi.ERR_INVALID
+    assert L.fbstab_multi_gpu_shard(2, 2, 10, C.byref(first), C.byref(count)) == capi.ERR_INVALID
+    h = C.c_void_p()
+    rc = L.fbstab_multi_gpu_create(0, 1, None, 0, C.byref(h))
+    if capi.device_count() == 0:
+        assert rc == capi.ERR_NOGPU and b"no CPU path" in L.fbstab_last_error()
+    else:
+        assert rc == capi.OK
+        L.fbstab_multi_gpu_destroy(h)
+    assert L.fbstab_multi_gpu_create(3, 2, None, 0, C.byref(h)) == capi.ERR_INVALID
 
 
 @pytest.mark.parametrize("world", [2, 3])

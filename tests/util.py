@@ -65,3 +65,33 @@ def component_ocp(fb):
     N, nx, nu, nc = dims
     d["E"][:nc * nx] = d["E"][nc * nx:2 * nc * nx]
     return dims, d
+
+
+# ---- "same trajectory" thresholds from the measured floor -------------------------
+_FLOOR = None
+
+
+def trajectory_floor(family):
+    """Committed oracle-vs-oracle (FMA off / on) same-trajectory fraction of a
+    problem family (tests/golden/trajectory_floor.json)."""
+    global _FLOOR
+    if _FLOOR is None:
+        import json
+        import os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                               "trajectory_floor.json")) as fh:
+            _FLOOR = json.load(fh)["families"]
+    return _FLOOR[family]["same_trajectory_frac"]
+
+
+def required_same_frac(family, batch):
+    """What a GPU parity test demands: the floor minus a margin for the finite sample
+    (three binomial standard deviations, at least 2%) -- 0.999 where the floor is 1."""
+    f = trajectory_floor(family)
+    if f >= 1.0:
+        return 0.999 if batch >= 1000 else 1.0 - 1.5 / batch
+    return f - max(0.02, 3.0 * (f * (1.0 - f) / batch) ** 0.5)
+
+
+FAMILY_OF_OCP = {"servo_motor": "servo_motor_N50", "double_integrator": "double_integrator_N50",
+                 "spacecraft": "spacecraft_N40", "copolymerization": "copolymerization_N100"}
