@@ -43,6 +43,7 @@ SYMBOLS = [
     "fbstab_mpc_multi_gpu_create", "fbstab_mpc_multi_gpu_destroy",
     "fbstab_mpc_multi_gpu_set_options", "fbstab_mpc_multi_gpu_solve",
     "fbstab_ocp_dims", "fbstab_ocp_generate", "fbstab_ocp_generate_batch",
+    "fbstab_ocp_simulation",
     "fbstab_random_dense_qp", "fbstab_fp64_peak",
     "fbstab_fp64_peak_concurrent",
 ]
@@ -55,7 +56,8 @@ class Options(C.Structure):
         "inner_tol_max", "inner_tol_min")] + [(n, C.c_int32) for n in (
             "max_newton_iters", "max_prox_iters", "max_inner_iters",
             "max_linesearch_iters", "check_feasibility",
-            "nonmonotone_linesearch", "display_level")]
+            "nonmonotone_linesearch", "display_level", "refine_steps",
+            "regularize_retries")]
 
 
 OUT_DTYPE = np.dtype([("eflag", "i4"), ("newton_iters", "i4"),

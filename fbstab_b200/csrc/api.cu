@@ -723,6 +723,8 @@ void fbstab_default_options(fbstab_options* o) {
   o->check_feasibility = 1;
   o->nonmonotone_linesearch = 1;
   o->display_level = 1;  // Display::FINAL
+  o->refine_steps = 0;
+  o->regularize_retries = 0;
 }
 
 void fbstab_reliable_options(fbstab_options* o) {
@@ -761,6 +763,8 @@ int fbstab_validate_options(fbstab_options* o) {
   o->max_prox_iters = std::max(o->max_prox_iters, 1);
   o->max_inner_iters = std::max(o->max_inner_iters, 1);
   o->max_linesearch_iters = std::max(o->max_linesearch_iters, 1);
+  o->refine_steps = std::min(std::max(o->refine_steps, 0), 1);
+  o->regularize_retries = std::min(std::max(o->regularize_retries, 0), 8);
   if (!ok) return Fail(FBSTAB_ERR_INVALID, "saturate(): lower bound above upper bound");
   return FBSTAB_OK;
 }
@@ -902,9 +906,13 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
   if ((rc = st.InOut(&h->out_buf, out, B * sizeof(fbstab_out), false,
                      (void**)&a.c.out)))
     return rc;
+  // refinement / regularise-and-retry re-use stored factors: the team kernels have them,
+  // the warp kernel eliminates with the right-hand side riding along and keeps none
+  const bool use_small =
+      h->small.enabled && h->opts.refine_steps == 0 && h->opts.regularize_retries == 0;
   // TMA operand staging of the large path: one tensor map over A of the whole batch
   CUtensorMap tmA;
-  const bool use_tma = h->large && !h->small.enabled && EnvInt("FBSTAB_DENSE_LARGE_TMA", 1) &&
+  const bool use_tma = h->large && !use_small && EnvInt("FBSTAB_DENSE_LARGE_TMA", 1) &&
                        EncodeTensorMapA(&tmA, a.A, h->nv, h->nz, batch);
   auto launch = [&](int lo, int n) -> int {
     DenseArgs c = a;
@@ -920,7 +928,7 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
     c.c.y += (size_t)lo * nv;
     c.c.out += lo;
     c.c.batch = n;
-    if (h->small.enabled) {
+    if (use_small) {
       if (fbs::DenseSmallLaunch(h->small, n, c.H, c.f, c.G, c.h, c.A, c.b, c.c.z, c.c.l,
                                 c.c.v, c.c.y, c.c.out, h->opts, -1, nullptr, st.stream))
         return Fail(FBSTAB_ERR_CUDA, "dense small-path launch failed");
@@ -946,7 +954,7 @@ int fbstab_dense_batch_solve(fbstab_dense_batch* h, int batch, const double* H,
     CUDA_TRY(cudaGetLastError());
     return FBSTAB_OK;
   };
-  const int capacity = h->small.enabled ? h->small.grid * fbs::DenseSmallWarpsPerCta() : h->grid_max;
+  const int capacity = use_small ? h->small.grid * fbs::DenseSmallWarpsPerCta() : h->grid_max;
   if ((rc = RunPipelined(h, &st, batch, 4 * capacity, launch))) return rc;
   if (st.any_host && !IsDevicePtr(out)) {
     const double sec =
@@ -1176,7 +1184,8 @@ static int MpcSolveImpl(fbstab_mpc_batch* h, int batch, const double* const* use
       c.d += o * K * nc;
     }
     c.x0 += o * nx;
-    const bool lane = h->lane_ws && n >= h->lane_min && (!shared || h->lane_sdata);
+    const bool lane = h->lane_ws && n >= h->lane_min && (!shared || h->lane_sdata) &&
+                      h->opts.refine_steps == 0 && h->opts.regularize_retries == 0;
     int fail;
     if (lane) {
       fail = fbs::MpcLaneLaunch(h->N, h->nx, h->nu, h->nc, n, h->lane_warps, c, dz + o * nz,

@@ -31,6 +31,8 @@ struct DenseProblem {
   double* tz;     // nz  scratch (feasibility)
 
   __device__ __forceinline__ double b(int i) const { return bvec[i]; }
+  __device__ __forceinline__ double fvec(int i) const { return f[i]; }
+  __device__ __forceinline__ double hvec(int i) const { return h[i]; }
 
   // dense_data.h:72-73
   __device__ double forcing_norm(const Team& t) const {

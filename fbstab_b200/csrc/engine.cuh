@@ -14,6 +14,8 @@
 //   bool factor(team, x, xbar, sigma, alpha)        LinearSolver::Initialize
 //   void solve(team, rz, rl, rv, dx)                LinearSolver::Solve on -r
 //   int  feasibility(team, dx, tol)                 CheckFeasibility
+//   double fvec(i), hvec(i); double* gamma, mus     f, h and the barrier terms of the
+//                                                   last factor() (iterative refinement)
 //
 // Work the reference does twice is done once (results are bit-identical):
 //  * InnerResidual and PenalizedNaturalResidual share f+Hz+G'l+A'v and h-Gz
@@ -124,6 +126,41 @@ struct Buffers {
   Resid ri;
 };
 
+// One step of iterative refinement of the Newton system V dx = -r just solved
+// (abstract_components.h:335-337 lists it as a TODO; off by default).  On entry
+// `keep` (the trial-point buffer, free at this time) holds r in z, l, v -- saved
+// before the solve, which may overwrite its argument -- and dx the solution with
+// dx.y = b - A dz.  rho = -r - V dx with
+//   V = [H + sigma I, G', A'; -G, sigma I, 0; -gamma A, 0, mu]
+// (reference components/dense_cholesky_solver.h:49-62); the same factors solve
+// V ddx = rho and dx += ddx.  The MPC policy parks scratch in the dx buffer while
+// it solves, so the correction is solved INTO dx after dx has moved to `keep`.
+template <class P>
+__device__ __forceinline__ void refine_step(const Team& t, P& p, double sigma, const Resid& ri,
+                                            const Vars& keep, const Vars& dx) {
+  // ri <- (f + H dz + G' dl + A' dv, h - G dz)
+  p.kkt(t, dx, ri.z, ri.l);
+  // ri <- r + V dx: solve() returns the solution for MINUS its argument, i.e. ddx
+  for (int i = t.rank(); i < p.nz; i += t.size())
+    ri.z[i] = keep.z[i] + ((ri.z[i] - p.fvec(i)) + sigma * dx.z[i]);
+  for (int i = t.rank(); i < p.nl; i += t.size())
+    ri.l[i] = keep.l[i] + (sigma * dx.l[i] + (ri.l[i] - p.hvec(i)));
+  for (int i = t.rank(); i < p.nv; i += t.size()) {
+    const double adz = p.b(i) - dx.y[i];
+    ri.v[i] = keep.v[i] + (p.mus[i] * dx.v[i] - p.gamma[i] * adz);
+  }
+  t.sync();
+  vars_copy(t, p, dx, keep);           // r is used up: keep <- dx
+  p.solve(t, ri.z, ri.l, ri.v, dx);    // dx <- ddx
+  for (int i = t.rank(); i < p.nz; i += t.size()) dx.z[i] = keep.z[i] + dx.z[i];
+  for (int i = t.rank(); i < p.nl; i += t.size()) dx.l[i] = keep.l[i] + dx.l[i];
+  for (int i = t.rank(); i < p.nv; i += t.size()) {
+    dx.v[i] = keep.v[i] + dx.v[i];
+    dx.y[i] = (keep.y[i] + dx.y[i]) - p.b(i);  // b - A (dz + ddz)
+  }
+  t.sync();
+}
+
 // Solves one instance.  (z0,l0,v0): warm start in global memory, overwritten
 // with the result together with y0.  Returns through *out.
 template <class P>
@@ -205,12 +242,31 @@ __device__ void solve_instance(const Team& t, P& p, const fbstab_options& o,
       if ((Ei <= inner_tol && Eo < Ek) || (Ei <= o.inner_tol_min)) break;  // impl:250
       if (newton >= o.max_newton_iters) break;                              // impl:258
 
-      if (!p.factor(t, xi, xk, sigma, alpha)) {  // impl:263-267
-        status = FBSTAB_STATUS_FACTOR_FAILED;
-        done = true;
-        break;
+      double sigma_ls = sigma;
+      {
+        bool ok = p.factor(t, xi, xk, sigma, alpha);  // impl:263-267
+        // regularise and retry (riccati_linear_solver.cc:129-130 lists it as a TODO):
+        // sigma x 100 per attempt, in the linear solver only; default 0 attempts
+        for (int j = 0; !ok && j < o.regularize_retries; j++) {
+          sigma_ls *= 100.0;
+          ok = p.factor(t, xi, xk, sigma_ls, alpha);
+        }
+        if (!ok) {
+          status = FBSTAB_STATUS_FACTOR_FAILED;
+          done = true;
+          break;
+        }
+      }
+      if (o.refine_steps > 0) {
+        // the policies may overwrite r while solving: keep it (xp is free until the
+        // line search builds the first trial point)
+        for (int i = t.rank(); i < p.nz; i += t.size()) xp.z[i] = ri.z[i];
+        for (int i = t.rank(); i < p.nl; i += t.size()) xp.l[i] = ri.l[i];
+        for (int i = t.rank(); i < p.nv; i += t.size()) xp.v[i] = ri.v[i];
+        t.sync();
       }
       p.solve(t, ri.z, ri.l, ri.v, dx);  // solves V dx = -r, impl:268-274
+      if (o.refine_steps > 0) refine_step(t, p, sigma_ls, ri, xp, dx);
       newton++;
 
       const double current_merit = 0.5 * Ei * Ei;  // impl:278

@@ -241,6 +241,16 @@ struct MpcProblem {
   __device__ __forceinline__ unsigned fbar(int s) const { return bar0 + 8u * (unsigned)(kRing + s); }
   __device__ __forceinline__ int ns() const { FBS_MPC_DIMS return nx + nu; }
   __device__ __forceinline__ double b(int i) const { return -d[i]; }
+  // entries of the stacked f = [q(i); r(i)] and h = -[x0; c(0); ...; c(N-1)]
+  __device__ __forceinline__ double fvec(int e) const {
+    const int nsv = ns(), i = e / nsv;
+    return f_entry(i, e - i * nsv);
+  }
+  __device__ __forceinline__ double hvec(int k) const {
+    FBS_MPC_DIMS
+    const int i = k / nx;
+    return h_entry(i, k - i * nx);
+  }
   __device__ __forceinline__ const double* Qi(int i) const { FBS_MPC_DIMS return Q + (size_t)i * nx * nx; }
   __device__ __forceinline__ const double* Ri(int i) const { FBS_MPC_DIMS return R + (size_t)i * nu * nu; }
   __device__ __forceinline__ const double* Si(int i) const { FBS_MPC_DIMS return S + (size_t)i * nu * nx; }

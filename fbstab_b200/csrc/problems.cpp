@@ -377,6 +377,27 @@ int fbstab_ocp_dims(int kind, int* nx, int* nu, int* nc) {
   return FBSTAB_OK;
 }
 
+// OcpGenerator::GetSimulationInputs (ocp_generator.cc:56-71): the plant x+ = A x + B u,
+// y = C x (+ D u, D = 0 in all four fixtures) and the number of steps T.  A, B, C are
+// written column-major when non-null (nx*nx, nx*nu, ny*nx doubles); x0 likewise.
+int fbstab_ocp_simulation(int kind, double* A, double* B, double* C, double* x0,
+                          int* ny, int* T) {
+  Model m;
+  if (!BuildModel(kind, &m)) return FBSTAB_ERR_INVALID;
+  if (m.ny == 0) {
+    // SpacecraftRelativeMotion: C = I(6), T = 100 (ocp_generator.cc:195,238-243)
+    m.Output(m.nx, 100);
+    for (int i = 0; i < m.nx; i++) m.cm(i, i) = 1.0;
+  }
+  if (A) std::memcpy(A, m.A.data(), m.A.size() * sizeof(double));
+  if (B) std::memcpy(B, m.B.data(), m.B.size() * sizeof(double));
+  if (C) std::memcpy(C, m.C.data(), m.C.size() * sizeof(double));
+  if (x0) std::memcpy(x0, m.x0.data(), m.x0.size() * sizeof(double));
+  if (ny) *ny = m.ny;
+  if (T) *T = m.T;
+  return FBSTAB_OK;
+}
+
 int fbstab_ocp_generate(int kind, int N, double* Q, double* R, double* S,
                         double* q, double* r, double* A, double* B, double* c,
                         double* E, double* L, double* d, double* x0) {

@@ -75,6 +75,14 @@ struct AlgorithmParameters {
   bool nonmonotone_linesearch = true;
   Display display_level = Display::FINAL;
 
+  // Engine extensions, both off by default (= the reference's behaviour): one
+  // step of iterative refinement per Newton system and regularise-and-retry
+  // attempts after a failed factorisation -- the two TODOs the reference leaves
+  // in its linear solvers (components/abstract_components.h:335-337,
+  // components/riccati_linear_solver.cc:129-130); see fbstab_options.
+  int refine_steps = 0;
+  int regularize_retries = 0;
+
   // Checks validity of fields and overwrites if necessary
   // (fbstab_algorithm-impl.h:7-31); throws std::runtime_error where the
   // reference's saturate() throws.
@@ -120,6 +128,8 @@ struct AlgorithmParameters {
     o.check_feasibility = check_feasibility ? 1 : 0;
     o.nonmonotone_linesearch = nonmonotone_linesearch ? 1 : 0;
     o.display_level = static_cast<int>(display_level);
+    o.refine_steps = refine_steps;
+    o.regularize_retries = regularize_retries;
     return o;
   }
   void FromC(const fbstab_options& o) {
@@ -144,6 +154,8 @@ struct AlgorithmParameters {
     check_feasibility = o.check_feasibility != 0;
     nonmonotone_linesearch = o.nonmonotone_linesearch != 0;
     display_level = static_cast<Display>(o.display_level);
+    refine_steps = o.refine_steps;
+    regularize_retries = o.regularize_retries;
   }
 };
 

@@ -129,7 +129,9 @@ class FBstabDense {
   SolverOut Solve(const InputData& qp, InputVariable* x, const OutStream& os) {
     ValidateData(qp.H.rows(), qp.H.cols(), qp.f.size(), qp.G.rows(), qp.G.cols(),
                  qp.h.size(), qp.A.rows(), qp.A.cols(), qp.b.size());
-    if (nz_ != x->z.size() || x->l.size() != nl_ || nv_ != x->v.size())
+    // (y is out-only, but the engine writes nv doubles through x->y.data(): a
+    // short y must be an error here, as in FBstabMpc, not a heap overflow)
+    if (nz_ != x->z.size() || x->l.size() != nl_ || nv_ != x->v.size() || nv_ != x->y.size())
       throw std::runtime_error(
           "In FBstabDense::Solve: mismatch between *this and initial guess dimensions.");
     fbstab_out out;
@@ -171,6 +173,39 @@ class FBstabDense {
     return res;
   }
 
+  /**
+   * The same batch on several GPUs of this box: the instances are cut into
+   * contiguous ranges, one per device, and solved concurrently (one host thread
+   * and one engine handle per device: fbstab_dense_multi_gpu_solve).  HOST
+   * pointers only; results land in the caller's arrays, identical byte for byte
+   * to the single-GPU call.  `devices`: CUDA ordinals, no duplicates.
+   */
+  std::vector<SolverOut> SolveBatch(int batch, const double* H, const double* f,
+                                    const double* G, const double* h, const double* A,
+                                    const double* b, double* z, double* l, double* v,
+                                    double* y, const std::vector<int>& devices) {
+    if (!multi_ || multi_devices_ != devices || multi_cap_ < batch) {
+      fbstab_dense_multi_gpu* m = nullptr;
+      detail::Check(fbstab_dense_multi_gpu_create((int)devices.size(), devices.data(), nz_, nl_,
+                                                  nv_, batch > max_batch_ ? batch : max_batch_,
+                                                  &m),
+                    "FBstabDense::SolveBatch");
+      multi_.reset(m);
+      multi_devices_ = devices;
+      multi_cap_ = batch > max_batch_ ? batch : max_batch_;
+      fbstab_options o = opts_.ToC();
+      detail::Check(fbstab_dense_multi_gpu_set_options(m, &o), "FBstabDense::SolveBatch");
+    }
+    std::vector<fbstab_out> out((size_t)(batch > 0 ? batch : 0));
+    detail::Check(fbstab_dense_multi_gpu_solve(multi_.get(), batch, H, f, G, h, A, b, z, l, v,
+                                               y, out.data()),
+                  "FBstabDense::SolveBatch");
+    std::vector<SolverOut> res;
+    res.reserve(out.size());
+    for (const fbstab_out& o : out) res.push_back(detail::FromC(o));
+    return res;
+  }
+
   /** Batched solve over arrays of the single-instance structs. */
   template <class InputData, class InputVariable>
   std::vector<SolverOut> SolveBatch(const std::vector<InputData>& qps,
@@ -186,7 +221,7 @@ class FBstabDense {
       ValidateData(q.H.rows(), q.H.cols(), q.f.size(), q.G.rows(), q.G.cols(), q.h.size(),
                    q.A.rows(), q.A.cols(), q.b.size());
       const InputVariable& x = (*xs)[i];
-      if (nz_ != x.z.size() || x.l.size() != nl_ || nv_ != x.v.size())
+      if (nz_ != x.z.size() || x.l.size() != nl_ || nv_ != x.v.size() || nv_ != x.y.size())
         throw std::runtime_error(
             "In FBstabDense::Solve: mismatch between *this and initial guess dimensions.");
       Copy(q.H.data(), &H[i * nz * nz], nz * nz);
@@ -221,6 +256,9 @@ class FBstabDense {
     detail::Check(fbstab_dense_batch_get_options(handle_.get(), &o),
                   "FBstabDense::UpdateOptions");
     opts_.FromC(o);
+    if (multi_)
+      detail::Check(fbstab_dense_multi_gpu_set_options(multi_.get(), &o),
+                    "FBstabDense::UpdateOptions");
   }
 
   static Options DefaultOptions() {
@@ -241,6 +279,9 @@ class FBstabDense {
  private:
   struct Destroy {
     void operator()(fbstab_dense_batch* h) const { fbstab_dense_batch_destroy(h); }
+  };
+  struct DestroyMulti {
+    void operator()(fbstab_dense_multi_gpu* h) const { fbstab_dense_multi_gpu_destroy(h); }
   };
   static void Copy(const double* src, double* dst, size_t n) {
     for (size_t i = 0; i < n; i++) dst[i] = src[i];
@@ -265,6 +306,10 @@ class FBstabDense {
   int nz_ = 0, nl_ = 0, nv_ = 0, max_batch_ = 1;
   Options opts_;
   std::unique_ptr<fbstab_dense_batch, Destroy> handle_;
+  // SolveBatch(..., devices): created on first use
+  std::unique_ptr<fbstab_dense_multi_gpu, DestroyMulti> multi_;
+  std::vector<int> multi_devices_;
+  int multi_cap_ = 0;
 };
 
 }  // namespace fbstab

@@ -176,6 +176,76 @@ class FBstabMpc {
     return res;
   }
 
+  /**
+   * One plant, `batch` initial states: `qp` is ONE problem (its x0 is ignored),
+   * x0 holds batch * nx doubles, instance-major.  The stage data crosses the
+   * boundary once instead of `batch` times (fbstab_mpc_batch_solve_shared) and
+   * the results equal SolveBatch on the replicated data bit for bit.
+   */
+  template <class InputData>
+  std::vector<SolverOut> SolveBatchShared(const InputData& qp, int batch, const double* x0,
+                                          double* z, double* l, double* v, double* y,
+                                          void* stream = nullptr) {
+    ValidateData(qp);
+    std::vector<fbstab_out> out((size_t)(batch > 0 ? batch : 0));
+    detail::Check(
+        fbstab_mpc_batch_solve_shared(handle_.get(), batch, qp.Q.data(), qp.R.data(), qp.S.data(),
+                                      qp.q.data(), qp.r.data(), qp.A.data(), qp.B.data(),
+                                      qp.c.data(), qp.E.data(), qp.L.data(), qp.d.data(), x0, z,
+                                      l, v, y, out.data(), stream),
+        "FBstabMpc::SolveBatchShared");
+    std::vector<SolverOut> res;
+    res.reserve(out.size());
+    for (const fbstab_out& o : out) res.push_back(detail::FromC(o));
+    return res;
+  }
+
+  /**
+   * Time-invariant problem from ONE stage of each matrix (column-major: Q nx*nx,
+   * R nu*nu, S nu*nx, q nx, r nu, A nx*nx, B nx*nu, c nx, E nc*nx, L nc*nu, d nc),
+   * replicated over the horizon like the reference's OcpGenerator::CopyOverHorizon
+   * (E(0) = 0), for `batch` initial states (fbstab_mpc_batch_solve_lti).
+   */
+  std::vector<SolverOut> SolveBatchLti(int batch, const double* Q, const double* R,
+                                       const double* S, const double* q, const double* r,
+                                       const double* A, const double* B, const double* c,
+                                       const double* E, const double* L, const double* d,
+                                       const double* x0, double* z, double* l, double* v,
+                                       double* y, void* stream = nullptr) {
+    std::vector<fbstab_out> out((size_t)(batch > 0 ? batch : 0));
+    detail::Check(fbstab_mpc_batch_solve_lti(handle_.get(), batch, Q, R, S, q, r, A, B, c, E, L,
+                                             d, x0, z, l, v, y, out.data(), stream),
+                  "FBstabMpc::SolveBatchLti");
+    std::vector<SolverOut> res;
+    res.reserve(out.size());
+    for (const fbstab_out& o : out) res.push_back(detail::FromC(o));
+    return res;
+  }
+
+  /** The wire-format batch on several GPUs (HOST pointers; see FBstabDense). */
+  std::vector<SolverOut> SolveBatch(int batch, const double* Q, const double* R,
+                                    const double* S, const double* q, const double* r,
+                                    const double* A, const double* B, const double* c,
+                                    const double* E, const double* L, const double* d,
+                                    const double* x0, double* z, double* l, double* v,
+                                    double* y, const std::vector<int>& devices) {
+    fbstab_mpc_multi_gpu* m = nullptr;
+    detail::Check(fbstab_mpc_multi_gpu_create((int)devices.size(), devices.data(), N_, nx_, nu_,
+                                              nc_, batch > 0 ? batch : 1, &m),
+                  "FBstabMpc::SolveBatch");
+    std::unique_ptr<fbstab_mpc_multi_gpu, DestroyMulti> guard(m);
+    fbstab_options o = opts_.ToC();
+    detail::Check(fbstab_mpc_multi_gpu_set_options(m, &o), "FBstabMpc::SolveBatch");
+    std::vector<fbstab_out> out((size_t)(batch > 0 ? batch : 0));
+    detail::Check(fbstab_mpc_multi_gpu_solve(m, batch, Q, R, S, q, r, A, B, c, E, L, d, x0, z, l,
+                                             v, y, out.data()),
+                  "FBstabMpc::SolveBatch");
+    std::vector<SolverOut> res;
+    res.reserve(out.size());
+    for (const fbstab_out& oo : out) res.push_back(detail::FromC(oo));
+    return res;
+  }
+
   /** Batched solve over arrays of the single-instance structs. */
   template <class InputData, class InputVariable>
   std::vector<SolverOut> SolveBatch(const std::vector<InputData>& qps,
@@ -242,6 +312,9 @@ class FBstabMpc {
  private:
   struct Destroy {
     void operator()(fbstab_mpc_batch* h) const { fbstab_mpc_batch_destroy(h); }
+  };
+  struct DestroyMulti {
+    void operator()(fbstab_mpc_multi_gpu* h) const { fbstab_mpc_multi_gpu_destroy(h); }
   };
   static void Copy(const double* src, double* dst, size_t n) {
     for (size_t i = 0; i < n; i++) dst[i] = src[i];

@@ -38,6 +38,41 @@ class OcpGenerator {
                                      &data_.x0);
   }
 
+  /**
+   * Inputs for a closed-loop simulation (reference ocp_generator.h:31-38,69):
+   *     x(i+1) = A x(i) + B u(i),   y(i) = C x(i) + D u(i)
+   * for T steps from x(0) = x0.  Feed them to fbstab::ClosedLoopMpc
+   * (include/fbstab/closed_loop.h) to run the loop on the GPU.
+   */
+  struct SimulationInputs {
+    Eigen::VectorXd x0;
+    Eigen::MatrixXd A;
+    Eigen::MatrixXd B;
+    Eigen::MatrixXd C;
+    Eigen::MatrixXd D;
+    int T = 0;
+  };
+  SimulationInputs GetSimulationInputs() const {
+    if (!initialized_)
+      throw std::runtime_error(
+          "In OcpGenerator::GetSimulationInputs: Call a problem creator method first.");
+    SimulationInputs out;
+    int ny = 0;
+    if (fbstab_ocp_simulation(kind_, nullptr, nullptr, nullptr, nullptr, &ny, &out.T) !=
+        FBSTAB_OK)
+      throw std::runtime_error(fbstab_last_error());
+    out.x0 = Eigen::VectorXd(nx_);
+    out.A = Eigen::MatrixXd(nx_, nx_);
+    out.B = Eigen::MatrixXd(nx_, nu_);
+    out.C = Eigen::MatrixXd(ny, nx_);
+    out.D = Eigen::MatrixXd(ny, nu_);
+    for (int i = 0; i < ny * nu_; i++) out.D.data()[i] = 0.0;
+    if (fbstab_ocp_simulation(kind_, out.A.data(), out.B.data(), out.C.data(), out.x0.data(),
+                              nullptr, nullptr) != FBSTAB_OK)
+      throw std::runtime_error(fbstab_last_error());
+    return out;
+  }
+
   /** (N, nx, nu, nc) */
   Eigen::Vector4d ProblemSize() const {
     Eigen::Vector4d s;
@@ -63,6 +98,7 @@ class OcpGenerator {
     if (fbstab_ocp_dims(kind, &nx_, &nu_, &nc_) != FBSTAB_OK)
       throw std::runtime_error(fbstab_last_error());
     N_ = N;
+    kind_ = kind;
     data_.Q = MatrixSequence(N + 1, nx_, nx_);
     data_.R = MatrixSequence(N + 1, nu_, nu_);
     data_.S = MatrixSequence(N + 1, nu_, nx_);
@@ -84,7 +120,7 @@ class OcpGenerator {
   }
 
   FBstabMpc::ProblemData data_;
-  int N_ = 0, nx_ = 0, nu_ = 0, nc_ = 0;
+  int N_ = 0, nx_ = 0, nu_ = 0, nc_ = 0, kind_ = 0;
   bool initialized_ = false;
 };
 

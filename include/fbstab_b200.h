@@ -101,6 +101,20 @@ typedef struct fbstab_options {
   int32_t max_newton_iters, max_prox_iters, max_inner_iters,
       max_linesearch_iters;
   int32_t check_feasibility, nonmonotone_linesearch, display_level;
+  /* Linear-solver extensions the reference lists as missing; both default to 0,
+   * which is the reference's behaviour (fbstab_default_options):
+   *  refine_steps        0 or 1: one step of iterative refinement of every Newton
+   *                      system V dx = -R: rho = -R - V dx, V ddx = rho with the
+   *                      same factors, dx += ddx ("TODO: implement iterative
+   *                      refinement", components/abstract_components.h:335-337)
+   *  regularize_retries  a failed factorisation is repeated up to this many times
+   *                      with sigma x 100 per attempt inside the linear solver
+   *                      ("TODO: regularize and retry",
+   *                      components/riccati_linear_solver.cc:129-130) before the
+   *                      instance is given FBSTAB_STATUS_FACTOR_FAILED.
+   * Either option selects the team-per-instance kernels (the warp / lane kernels
+   * keep no factors to re-use). */
+  int32_t refine_steps, regularize_retries;
 } fbstab_options;
 
 /* SolverOut, reference fbstab/fbstab_algorithm.h:30-37, plus the trajectory
@@ -374,6 +388,12 @@ int fbstab_ocp_dims(int kind, int* nx, int* nu, int* nc);
 int fbstab_ocp_generate(int kind, int N, double* Q, double* R, double* S,
                         double* q, double* r, double* A, double* B, double* c,
                         double* E, double* L, double* d, double* x0);
+/* OcpGenerator::GetSimulationInputs (ocp_generator.cc:56-71): the plant
+ * x+ = A x + B u, y = C x (D = 0 in all four fixtures), initial state and number
+ * of steps T.  A (nx*nx), B (nx*nu), C (ny*nx), x0 (nx): column-major, written
+ * where non-NULL; ny <= nx. */
+int fbstab_ocp_simulation(int kind, double* A, double* B, double* C, double* x0,
+                          int* ny, int* T);
 /* `count` instances first..first+count-1 of benchmark config `config`:
  * identical stage data, x0 = nominal + rho*U(-1,1)^nx (instance 0 unperturbed);
  * rho < 0 perturbs one-sidedly, x0 = nominal + |rho|*U(0,1)^nx. */

@@ -32,7 +32,8 @@ class Options(C.Structure):
         "inner_tol_max", "inner_tol_min")] + [(n, C.c_int) for n in (
             "max_newton_iters", "max_prox_iters", "max_inner_iters",
             "max_linesearch_iters", "check_feasibility",
-            "nonmonotone_linesearch", "display_level")]
+            "nonmonotone_linesearch", "display_level", "refine_steps",
+            "regularize_retries")]
 
 
 class Out(C.Structure):

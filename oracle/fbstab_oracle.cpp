@@ -1190,6 +1190,8 @@ void DefaultParameters(oracle_options* o) {
   o->check_feasibility = 1;
   o->nonmonotone_linesearch = 1;
   o->display_level = 1;
+  o->refine_steps = 0;
+  o->regularize_retries = 0;
 }
 
 struct TrajSink {
@@ -1246,6 +1248,41 @@ struct Algorithm {
     return 5;                 // PRIMAL_DUAL_INFEASIBLE
   }
 
+  // One step of iterative refinement of the Newton system just solved: ri holds the
+  // right-hand side, dx the solution, ls the factors.  A dz is read off dx.y = b - A dz.
+  double sigma_ls = 0.0;
+  bool Refine(double sigma) {
+    const int nz = data->nz, nl = data->nl, nv = data->nv;
+    Residual rr(data);
+    Variable ddx(data);
+    // (V dx)_z = H dz + G' dl + A' dv + sigma dz
+    Vec t(nz, 0.0);
+    data->gemvH(dx.z.data(), 1.0, 0.0, t.data());
+    data->gemvGT(dx.l.data(), 1.0, 1.0, t.data());
+    data->gemvAT(dx.v.data(), 1.0, 1.0, t.data());
+    for (int i = 0; i < nz; i++) rr.z[i] = ri.z[i] - (t[i] + sigma * dx.z[i]);
+    // (V dx)_l = -G dz + sigma dl
+    Vec g(nl, 0.0);
+    data->gemvG(dx.z.data(), 1.0, 0.0, g.data());
+    for (int i = 0; i < nl; i++) rr.l[i] = ri.l[i] - (sigma * dx.l[i] - g[i]);
+    // (V dx)_v = -gamma .* (A dz) + mu .* dv,  A dz = b - dx.y
+    Vec adz(nv, 0.0);
+    data->axpyb(1.0, adz.data());
+    for (int i = 0; i < nv; i++) {
+      adz[i] -= dx.y[i];
+      rr.v[i] = ri.v[i] - (ls->mus[i] * dx.v[i] - ls->gamma[i] * adz[i]);
+    }
+    if (!ls->Solve(rr, &ddx)) return false;
+    for (int i = 0; i < nz; i++) dx.z[i] += ddx.z[i];
+    for (int i = 0; i < nl; i++) dx.l[i] += ddx.l[i];
+    for (int i = 0; i < nv; i++) dx.v[i] += ddx.v[i];
+    // dy = b - A (dz + ddz) = dx.y + ddx.y - b
+    Vec bb(nv, 0.0);
+    data->axpyb(1.0, bb.data());
+    for (int i = 0; i < nv; i++) dx.y[i] = (dx.y[i] + ddx.y[i]) - bb[i];
+    return true;
+  }
+
   // impl:229-304
   double SolveProximalSubproblem(Variable* x, Variable* xbar, double tol,
                                  double sigma, double current_outer_residual) {
@@ -1263,14 +1300,35 @@ struct Algorithm {
       }
       if (newton_iters >= opts.max_newton_iters) break;
 
-      if (!ls->Initialize(*x, *xbar, sigma)) {
-        status = 1;
-        throw status;
+      {
+        // "TODO: regularize and retry" (riccati_linear_solver.cc:129-130): with
+        // regularize_retries > 0 a failed factorisation is repeated with sigma x 100
+        // per attempt in the linear solver only (default 0: throw like the reference)
+        bool ok = ls->Initialize(*x, *xbar, sigma);
+        double sig_r = sigma;
+        for (int j = 0; !ok && j < opts.regularize_retries; j++) {
+          sig_r *= 100.0;
+          ok = ls->Initialize(*x, *xbar, sig_r);
+        }
+        if (!ok) {
+          status = 1;
+          throw status;
+        }
+        sigma_ls = sig_r;
       }
       ri.Negate();
       if (!ls->Solve(ri, &dx)) {
         status = 3;
         throw status;
+      }
+      // "TODO: implement iterative refinement" (abstract_components.h:335-337):
+      // rho = rhs - V dx with V = [H + sigma I, G', A'; -G, sigma I, 0; -gamma A, 0, mu]
+      // (dense_cholesky_solver.h:49-62: "the matrix V(x,xbar,sigma)"), one more solve with the same factors, dx += ddx.
+      for (int it = 0; it < std::min(opts.refine_steps, 1); it++) {
+        if (!Refine(sigma_ls)) {
+          status = 3;
+          throw status;
+        }
       }
       newton_iters++;
 
@@ -1439,6 +1497,8 @@ int oracle_validate_options(oracle_options* o) {
     o->max_prox_iters = std::max(o->max_prox_iters, 1);
     o->max_inner_iters = std::max(o->max_inner_iters, 1);
     o->max_linesearch_iters = std::max(o->max_linesearch_iters, 1);
+    o->refine_steps = std::min(std::max(o->refine_steps, 0), 1);
+    o->regularize_retries = std::min(std::max(o->regularize_retries, 0), 8);
   } catch (SaturateError&) {
     return 2;
   }

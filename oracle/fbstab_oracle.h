@@ -26,6 +26,11 @@ typedef struct oracle_options {
   double inner_tol_max, inner_tol_min;
   int max_newton_iters, max_prox_iters, max_inner_iters, max_linesearch_iters;
   int check_feasibility, nonmonotone_linesearch, display_level;
+  /* Linear-solver extensions the reference lists as missing (both default 0 = the
+   * reference's behaviour): steps of iterative refinement of every Newton system
+   * (abstract_components.h:335-337) and regularise-and-retry attempts when a
+   * factorisation fails (riccati_linear_solver.cc:129-130). */
+  int refine_steps, regularize_retries;
 } oracle_options;
 
 /* Mirrors SolverOut (fbstab_algorithm.h:30-37) + trajectory counters. */

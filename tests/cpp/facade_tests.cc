@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "fbstab/closed_loop.h"
 #include "fbstab/fbstab_dense.h"
 #include "fbstab/fbstab_mpc.h"
 #include "fbstab/ocp_generator.h"
@@ -345,6 +346,114 @@ TEST(FBstabMpc, SolveBatchOfStructs, true) {
   }
 }
 
+// One plant from many initial states: the shared-data and LTI entries return the bytes
+// of the wire-format batch, which repeats the stage data per instance.
+TEST(FBstabMpc, SharedAndLtiEqualTheWireFormat, true) {
+  OcpGenerator ocp;
+  ocp.DoubleIntegrator(8);
+  const int B = 5, nx = ocp.nx(), nu = ocp.nu(), nc = ocp.nc();
+  FBstabMpc::ProblemData one = ocp.GetFBstabInput();
+  std::vector<FBstabMpc::ProblemData> qps(B, one);
+  std::vector<double> x0(B * nx);
+  for (int i = 0; i < B; i++) {
+    for (int k = 0; k < nx; k++) {
+      qps[i].x0(k) += 0.05 * (i + 1) * (k + 1);
+      x0[i * nx + k] = qps[i].x0(k);
+    }
+  }
+  std::vector<FBstabMpc::Variable> xs(B, FBstabMpc::Variable(ocp.ProblemSize()));
+  FBstabMpc solver(ocp.N(), nx, nu, nc, /*max_batch=*/B);
+  FBstabMpc::Options opts = FBstabMpc::DefaultOptions();
+  opts.display_level = Display::OFF;
+  solver.UpdateOptions(opts);
+  std::vector<SolverOut> ref = solver.SolveBatch(qps, &xs);
+  const int nz = ocp.nz(), nl = ocp.nl(), nv = ocp.nv();
+  std::vector<double> z(B * nz, 0.0), l(B * nl, 0.0), v(B * nv, 0.0), y(B * nv, 0.0);
+  std::vector<SolverOut> got =
+      solver.SolveBatchShared(one, B, x0.data(), z.data(), l.data(), v.data(), y.data());
+  for (int i = 0; i < B; i++) {
+    ASSERT_EQ(got[i].eflag, ref[i].eflag);
+    ASSERT_EQ(got[i].newton_iters, ref[i].newton_iters);
+    for (int k = 0; k < nz; k++) EXPECT_NEAR(z[i * nz + k], xs[i].z(k), 0.0);
+    for (int k = 0; k < nv; k++) EXPECT_NEAR(y[i * nv + k], xs[i].y(k), 0.0);
+  }
+  // one stage of each matrix: stage 1 carries E (the generator zeroes E(0))
+  std::fill(z.begin(), z.end(), 0.0);
+  std::fill(l.begin(), l.end(), 0.0);
+  std::fill(v.begin(), v.end(), 0.0);
+  got = solver.SolveBatchLti(B, one.Q(1).data(), one.R(1).data(), one.S(1).data(),
+                             one.q(1).data(), one.r(1).data(), one.A(0).data(),
+                             one.B(0).data(), one.c(0).data(), one.E(1).data(),
+                             one.L(1).data(), one.d(1).data(), x0.data(), z.data(), l.data(),
+                             v.data(), y.data());
+  for (int i = 0; i < B; i++) {
+    ASSERT_EQ(got[i].newton_iters, ref[i].newton_iters);
+    for (int k = 0; k < nz; k++) EXPECT_NEAR(z[i * nz + k], xs[i].z(k), 0.0);
+  }
+}
+
+// SolveBatch(..., devices): every visible GPU, host buffers, same bytes as one GPU.
+TEST(FBstabDense, SolveBatchOnAllDevices, true) {
+  const int nz = 6, nl = 2, nv = 9, B = 11;
+  std::vector<double> H(B * nz * nz), f(B * nz), G(B * nl * nz), h(B * nl), A(B * nv * nz),
+      b(B * nv);
+  ASSERT_EQ(fbstab_random_dense_qp(21, 0, B, nz, nl, nv, 0, H.data(), f.data(), G.data(),
+                                   h.data(), A.data(), b.data(), 2),
+            FBSTAB_OK);
+  FBstabDense solver(nz, nl, nv, B);
+  std::vector<double> z(B * nz, 0.0), l(B * nl, 0.0), v(B * nv, 0.0), y(B * nv, 0.0);
+  std::vector<SolverOut> one = solver.SolveBatch(B, H.data(), f.data(), G.data(), h.data(),
+                                                 A.data(), b.data(), z.data(), l.data(),
+                                                 v.data(), y.data());
+  std::vector<int> devices;
+  for (int d = 0; d < fbstab_device_count(); d++) devices.push_back(d);
+  std::vector<double> z2(B * nz, 0.0), l2(B * nl, 0.0), v2(B * nv, 0.0), y2(B * nv, 0.0);
+  std::vector<SolverOut> all = solver.SolveBatch(B, H.data(), f.data(), G.data(), h.data(),
+                                                 A.data(), b.data(), z2.data(), l2.data(),
+                                                 v2.data(), y2.data(), devices);
+  for (int i = 0; i < B; i++) {
+    ASSERT_EQ(all[i].eflag, one[i].eflag);
+    ASSERT_EQ(all[i].newton_iters, one[i].newton_iters);
+  }
+  EXPECT_TRUE(z == z2 && l == l2 && v == v2 && y == y2);
+  std::vector<int> dup(2, 0);
+  EXPECT_THROW(solver.SolveBatch(B, H.data(), f.data(), G.data(), h.data(), A.data(), b.data(),
+                                 z2.data(), l2.data(), v2.data(), y2.data(), dup),
+               "duplicate device");
+}
+
+// OcpGenerator::GetSimulationInputs + the closed loop on the device: the servo motor is
+// steered to its 30 degree target (ocp_generator.cc:286-288) within T = 40 steps, and
+// warm starts cost fewer Newton iterations than cold starts.
+TEST(ClosedLoop, ServoMotorReachesItsTarget, true) {
+  OcpGenerator ocp;
+  ocp.ServoMotor(20);
+  OcpGenerator::SimulationInputs sim = ocp.GetSimulationInputs();
+  ASSERT_EQ(sim.T, 40);
+  ASSERT_EQ(sim.C.rows(), 2);
+  const int B = 4, nx = ocp.nx();
+  std::vector<double> x0(B * nx, 0.0);
+  for (int i = 0; i < B; i++) x0[i * nx] = 0.01 * i;  // slightly different starting angles
+  FBstabMpc::ProblemData qp = ocp.GetFBstabInput();
+  ClosedLoopMpc loop(qp, B, x0.data(), sim.A.data(), sim.B.data(), sim.T);
+  ClosedLoopMpc::Trajectory warm = loop.Run(sim.T, true);
+  ClosedLoopMpc::Trajectory cold = loop.Run(sim.T, false);
+  const double target = 30 * 3.1415926535897 / 180;
+  long nw = 0, ncold = 0;
+  for (int i = 0; i < B; i++) {
+    EXPECT_NEAR(warm.x(i, 0)[0], 0.01 * i, 0.0);
+    EXPECT_NEAR(warm.x(i, sim.T)[0], target, 2e-2);
+    EXPECT_NEAR(cold.x(i, sim.T)[0], warm.x(i, sim.T)[0], 1e-6);
+  }
+  for (int t = 1; t < sim.T; t++)
+    for (int i = 0; i < B; i++) {
+      ASSERT_EQ(warm.out[(size_t)t * B + i].eflag, ExitFlag::SUCCESS);
+      nw += warm.out[(size_t)t * B + i].newton_iters;
+      ncold += cold.out[(size_t)t * B + i].newton_iters;
+    }
+  EXPECT_TRUE(nw < ncold);
+}
+
 // ---- host-only: types, validation, error behaviour ----------------------------
 TEST(Host, OptionsDefaultsAndClamps, false) {
   // DefaultParameters, fbstab_algorithm-impl.h:33-59
@@ -433,11 +542,42 @@ TEST(Host, NoSilentCpuFallback, false) {
   EXPECT_THROW(FBstabMpc s(2, 2, 1, 1), "no CUDA device");
 }
 
+TEST(Host, SimulationInputs, false) {
+  OcpGenerator ocp;
+  EXPECT_THROW(ocp.GetSimulationInputs(), "problem creator");
+  ocp.DoubleIntegrator(4);
+  OcpGenerator::SimulationInputs s = ocp.GetSimulationInputs();
+  ASSERT_EQ(s.T, 40);
+  ASSERT_EQ(s.A.rows(), 2);
+  ASSERT_EQ(s.B.cols(), 1);
+  EXPECT_NEAR(s.A(0, 1), 1.0, 0.0);  // [1 1; 0 1], ocp_generator.cc:325-326
+  EXPECT_NEAR(s.A(1, 0), 0.0, 0.0);
+  EXPECT_NEAR(s.B(1, 0), 1.0, 0.0);
+  EXPECT_NEAR(s.C(1, 1), 1.0, 0.0);
+  EXPECT_NEAR(s.D.norm(), 0.0, 0.0);
+  ocp.CopolymerizationReactor(3);
+  s = ocp.GetSimulationInputs();
+  ASSERT_EQ(s.T, 200);
+  ASSERT_EQ(s.C.rows(), 4);
+  ASSERT_EQ(s.C.cols(), 18);
+  EXPECT_NEAR(s.C(3, 17), 1.8214, 0.0);
+  ocp.SpacecraftRelativeMotion(3);
+  s = ocp.GetSimulationInputs();
+  ASSERT_EQ(s.T, 100);
+  ASSERT_EQ(s.C.rows(), 6);
+}
+
 TEST(FBstabDense, SizeMismatchThrows, true) {
   FBstabDense solver(2, 0, 2);
   FBstabDense::ProblemData bad(3, 0, 2);
   FBstabDense::Variable x(2, 0, 2);
   EXPECT_THROW(solver.Solve(bad, &x), "mismatch between *this and data");
+  {  // a short y is an error, not a heap overflow (the engine writes nv doubles into it)
+    FBstabDense::ProblemData ok(2, 0, 2);
+    FBstabDense::Variable xy(2, 0, 2);
+    xy.y = VectorXd(1);
+    EXPECT_THROW(solver.Solve(ok, &xy), "initial guess");
+  }
   FBstabDense::ProblemData good(2, 0, 2);
   FBstabDense::Variable xb(2, 1, 2);
   EXPECT_THROW(solver.Solve(good, &xb), "initial guess");
