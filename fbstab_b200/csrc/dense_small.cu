@@ -30,6 +30,7 @@
 // Follows the same reference code as engine.cuh / dense_problem.cuh
 // (fbstab_algorithm-impl.h:113-304, dense_cholesky_solver.cc:32-148,
 // full_residual.cc:49-118, full_feasibility.cc:25-88).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -111,6 +112,11 @@ __device__ __forceinline__ void sts2_if(bool p, unsigned a, double x, double y) 
       "{\n .reg .pred q;\n setp.ne.s32 q, %3, 0;\n @q st.shared.v2.f64 [%0], {%1,%2};\n}"
       ::"r"(a), "d"(x), "d"(y), "r"((int)p)
       : "memory");
+}
+__device__ __forceinline__ void sts_if(bool p, unsigned a, double x) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}" ::"r"(a),
+               "d"(x), "r"((int)p)
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -202,6 +208,42 @@ struct Warp {
     const unsigned zb = sb + D(OFF_ZB);
     const unsigned hrow = sb + D(OFF_H + (lane * (lane + 1) >> 1));  // H(lane, 0..lane)
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, h0 = 0.0, h1 = 0.0;
+#ifdef FBSTAB_DS_PIPE_MATVEC
+    // software pipelined: the operands of trip t + 1 are requested before the FMAs of
+    // trip t issue (the last trip re-reads trip 0: no branch in the body)
+    double2 v0, v1, zz = {0.0, 0.0};
+    double a0, a1, a2, a3, e0 = 0.0, e1 = 0.0;
+    auto fetch = [&](int t) {
+      const int k = 4 * t, j = 2 * t;
+      v0 = lds2(vb + D(k));
+      v1 = lds2(vb + D(k + 2));
+      a0 = lds(ac + D(LD * k));
+      a1 = lds(ac + D(LD * (k + 1)));
+      a2 = lds(ac + D(LD * (k + 2)));
+      a3 = lds(ac + D(LD * (k + 3)));
+      if (WITH_H) {
+        zz = lds2(zb + D(j));
+        e0 = lds(j <= lane ? hrow + D(j) : sb + D(OFF_H + (j * (j + 1) >> 1) + lane));
+        e1 = lds(j + 1 <= lane ? hrow + D(j + 1)
+                               : sb + D(OFF_H + ((j + 1) * (j + 2) >> 1) + lane));
+      }
+    };
+    fetch(0);
+#pragma unroll 2
+    for (int t = 0; t < NV / 4; t++) {
+      const double2 cv0 = v0, cv1 = v1, czz = zz;
+      const double c0 = a0, c1 = a1, c2 = a2, c3 = a3, ce0 = e0, ce1 = e1;
+      fetch((t + 1) & (NV / 4 - 1));
+      if (WITH_H) {
+        h0 = fma(ce0, czz.x, h0);
+        h1 = fma(ce1, czz.y, h1);
+      }
+      s0 = fma(c0, cv0.x, s0);
+      s1 = fma(c1, cv0.y, s1);
+      s2 = fma(c2, cv1.x, s2);
+      s3 = fma(c3, cv1.y, s3);
+    }
+#else
 #pragma unroll 2
     for (int t = 0; t < NV / 4; t++) {
       const int k = 4 * t, j = 2 * t;
@@ -223,6 +265,7 @@ struct Warp {
       s2 = fma(a2, v1.x, s2);
       s3 = fma(a3, v1.y, s3);
     }
+#endif
     if (WITH_H) *hz = h0 + h1;
     return (s0 + s1) + (s2 + s3);
   }
@@ -357,7 +400,13 @@ struct Warp {
     for (int r = 0; r < NAP; r++) xr[r] = lds2(cb + D(32 + 2 * r));
     const double d = c[0][0].x;
     if (!(fabs(d) > 0.0)) ok = false;
+#ifdef FBSTAB_DS_LOOKAHEAD_RCP
+    // the pivot's reciprocal was computed one step ahead by the row's owner, off the
+    // store -> barrier -> load -> reciprocal -> multiply chain of a step
+    const double rd = lds(cb + D(42));
+#else
     const double rd = 1.0 / d;
+#endif
     if (row == k) *rpiv = rd;
     const double lik = (row != k) ? a[0] * rd : 0.0;
     const bool nxt = (row == k + 1);
@@ -380,6 +429,11 @@ struct Warp {
     }
     a[W] = 0.0;
     sts2_if(nxt, nb + D(W - 1), a[W - 1], 0.0);
+#ifdef FBSTAB_DS_LOOKAHEAD_RCP
+    // a[0] is final since the first FMA of the update: the division overlaps the rest
+    // (other lanes divide 1 by 1: the fast path, whatever their entry is)
+    sts_if(nxt, nb + D(42), 1.0 / (nxt ? a[0] : 1.0));
+#endif
 #pragma unroll
     for (int r = 0; r < NA; r++) {
       const double xm = (r & 1) ? xr[r / 2].y : xr[r / 2].x;
@@ -412,6 +466,9 @@ struct Warp {
 #pragma unroll
     for (int r = 0; r < NA; r += 2)
       sts2_if(own, cb + D(32 + r), g[r], (r + 1 < NA) ? g[r + 1] : 0.0);
+#ifdef FBSTAB_DS_LOOKAHEAD_RCP
+    sts_if(own, cb + D(42), 1.0 / (own ? a[0] : 1.0));
+#endif
   }
 
   // ---- Newton step: LinearSolver::Initialize + ::Solve fused -----------------
@@ -1130,6 +1187,15 @@ int DenseSmallInit(DenseSmallPlan* p, int nz, int nl, int nv, int sm_count,
   p->grid = sm_count * occ;
   p->enabled = true;
   p->name = "dense-small-warp (smem-resident data, DMMA SYRK, register LDL')";
+  {
+    const char* e = getenv("FBSTAB_DENSE_SMALL_TEAM");
+    const int want = e ? atoi(e) : 1;
+    if (want == 2 && DenseSmall2Init(p) == 0) {
+      p->team2 = 1;
+      p->name = "dense-small-team2 (two warps per instance, smem-resident data, DMMA SYRK, "
+                "column-split register Gauss-Jordan)";
+    }
+  }
   return 0;
 }
 
@@ -1139,6 +1205,8 @@ int DenseSmallLaunch(const DenseSmallPlan& p, int batch, const double* H,
                      double* v, double* y, fbstab_out* out,
                      const fbstab_options& opts, int comp,
                      const fbstab_component_io* io, cudaStream_t stream) {
+  if (p.team2)
+    return DenseSmall2Launch(p, batch, H, f, G, h, A, b, z, l, v, y, out, opts, comp, io, stream);
   small::Args a;
   a.comp = comp;
   if (io)

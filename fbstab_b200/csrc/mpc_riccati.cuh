@@ -424,20 +424,12 @@ struct MpcProblem {
     const DataOff dof = data_off();
     const int off[7] = {dof.Q, dof.R, dof.S, dof.A, dof.B, dof.E, dof.L};
     const int cnt[7] = {nxx, nuu, nux, i < N ? nxx : 0, i < N ? nux : 0, ncx, ncu};
-    bool ragged = false;
     unsigned bytes = 0;
 #pragma unroll
-    for (int k = 0; k < 7; k++) {
-      const int par = (int)(((uintptr_t)src[k] >> 3) & 1);
-      bytes += tma::copy_run(base + off[k] + par, src[k], cnt[k], bar, false, &ragged);
-    }
-    if (ragged) tma::cp_async_mbar_arrive(bar);
+    for (int k = 0; k < 7; k++) bytes += tma::copy_run(base + off[k], src[k], cnt[k], bar, false);
     tma::mbar_arrive_expect_tx(bar, bytes);
 #pragma unroll
-    for (int k = 0; k < 7; k++) {
-      const int par = (int)(((uintptr_t)src[k] >> 3) & 1);
-      tma::copy_run(base + off[k] + par, src[k], cnt[k], bar, true, &ragged);
-    }
+    for (int k = 0; k < 7; k++) tma::copy_run(base + off[k], src[k], cnt[k], bar, true);
   }
   __device__ __forceinline__ StageData stage_data(int i) {
     StageData sd;
@@ -450,13 +442,15 @@ struct MpcProblem {
     tma::mbar_wait(dbar(s), (dphase >> s) & 1u);
     dphase ^= 1u << s;
     const double* base = dslot(s);
-    auto at = [&](const double* src, int off) {
-      return base + off + (int)(((uintptr_t)src >> 3) & 1);
+    // a run the TMA engine could not take whole is read in place (tma.cuh)
+    auto at = [&](const double* src, int off, int n) {
+      return tma::bulk_able(src, n) ? base + off : src;
     };
     const DataOff dof = data_off();
-    sd.Q = at(Qi(i), dof.Q); sd.R = at(Ri(i), dof.R); sd.S = at(Si(i), dof.S);
-    sd.A = at(Ai(i), dof.A); sd.B = at(Bi(i), dof.B); sd.E = at(Ei(i), dof.E);
-    sd.L = at(Lci(i), dof.L);
+    const int nxx = nx * nx, nuu = nu * nu, nux = nu * nx, ncx = nc * nx, ncu = nc * nu;
+    sd.Q = at(Qi(i), dof.Q, nxx); sd.R = at(Ri(i), dof.R, nuu); sd.S = at(Si(i), dof.S, nux);
+    sd.A = at(Ai(i), dof.A, nxx); sd.B = at(Bi(i), dof.B, nux); sd.E = at(Ei(i), dof.E, ncx);
+    sd.L = at(Lci(i), dof.L, ncu);
     return sd;
   }
   // Factor ring (streaming mode): block i lives in slot i % kRing.

@@ -3,9 +3,8 @@
 //
 // Used to stream per-stage matrix blocks global -> shared ahead of the Riccati
 // sweep (mpc_riccati.cu) and factor blocks shared -> global behind it.
-// cp.async.bulk moves 16-byte aligned runs; the at most one leading and one
-// trailing double of a run that is only 8-byte aligned travel as 8-byte
-// cp.async (LDGSTS) operations tracked by the same mbarrier.
+// cp.async.bulk moves 16-byte aligned runs of whole 16-byte units; a run that is
+// not (odd-sized blocks) is read in place instead of being staged.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -82,42 +81,33 @@ __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// one double, global -> shared, asynchronous (LDGSTS)
-__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+// A run of n doubles can go through the TMA engine as ONE bulk copy iff it is
+// 16-byte aligned and a whole number of 16-byte units.  Runs that are not (in the
+// four OCP shapes of the BASELINE configs: only the nu x nu block R, nu odd, whose
+// stage-i copy starts at an odd double for every other i) are NOT staged: the
+// consumer reads them in place and the issuing thread prefetches their lines.
+// (Round 1 moved the ragged first / last double as 8-byte cp.async tracked on the
+// TMA mbarrier; compute-sanitizer's racecheck and synccheck do not model that
+// protocol and reported it -- profiles/r2_sanitizer.txt.  With whole runs either
+// bulk or in place there is no non-bulk asynchronous copy left on the barrier.)
+__device__ __forceinline__ bool bulk_able(const double* src, int n) {
+  return n > 0 && (((uintptr_t)src >> 3) & 1) == 0 && (n & 1) == 0;
 }
-// `bar` receives one arrival when all cp.async of this thread so far are done
-// (the pending count is raised by one now and lowered on completion)
-__device__ __forceinline__ void cp_async_mbar_arrive(unsigned bar) {
-  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
-
-// Copies n doubles src -> dst (shared) asynchronously; dst must have the same
-// 16-byte phase as src.  Returns the bytes that will be reported to the
-// mbarrier as a transaction count (the bulk part); *ragged is set when 8-byte
-// cp.async pieces were issued.  Call order for one stage: every copy_run with
-// issue_bulk = false first (ragged ends only, sums the bulk bytes), then
-// cp_async_mbar_arrive if *ragged, then mbar_arrive_expect_tx(bytes), then
-// every copy_run again with issue_bulk = true.
+// Bytes the run contributes to the stage's transaction count (pass 1, issue = false)
+// or issues its bulk copy (pass 2); runs that are not bulk-able are prefetched.
 __device__ __forceinline__ unsigned copy_run(double* dst, const double* src, int n,
-                                             unsigned bar, bool issue_bulk, bool* ragged) {
+                                             unsigned bar, bool issue) {
   if (n <= 0) return 0;
-  const int head = (int)(((uintptr_t)src >> 3) & 1);
-  const int interior = (n - head) & ~1;
-  const int tail = n - head - interior;
-  if (!issue_bulk) {
-    if (head) {
-      cp_async8(smem_addr(dst), src);
-      *ragged = true;
-    }
-    if (tail) {
-      cp_async8(smem_addr(dst + head + interior), src + head + interior);
-      *ragged = true;
-    }
-  } else if (interior) {
-    bulk_g2s(smem_addr(dst + head), src + head, (unsigned)interior * 8u, bar);
+  if (!bulk_able(src, n)) {
+    if (issue)
+      for (int o = 0; o < n; o += 16) prefetch_l1(src + o);
+    return 0;
   }
-  return (unsigned)interior * 8u;
+  if (issue) bulk_g2s(smem_addr(dst), src, (unsigned)n * 8u, bar);
+  return (unsigned)n * 8u;
 }
 
 }  // namespace tma

@@ -2,7 +2,8 @@
 kernel from an ncu capture with source (--import-source on).
 Usage: ncu -i X.ncu-rep --page source --csv > sass.csv
        ncu -i X.ncu-rep --page source --csv --print-source cuda,sass > src.csv
-       python tools/ncu_phases.py sass.csv src.csv <kernel ms> <newton steps in the capture>"""
+       python tools/ncu_phases.py sass.csv src.csv <kernel ms> <newton steps in the capture> [dense_small.cu of that build]
+The source file must be the one the capture was built from (line numbers)."""
 import collections
 import csv
 import os
@@ -29,7 +30,8 @@ hdr = s[1]
 ix = {h: i for i, h in enumerate(hdr)}
 data = s[2:]
 here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = open(os.path.join(here, "fbstab_b200", "csrc", "dense_small.cu")).read().split("\n")
+src_path = sys.argv[5] if len(sys.argv) > 5 else os.path.join(here, "fbstab_b200", "csrc", "dense_small.cu")
+src = open(src_path).read().split("\n")
 
 
 def find(st):
