@@ -120,6 +120,21 @@ __device__ __forceinline__ double pnr(double y, double v, double alpha) {
   return alpha * fmin(y, v) + (1.0 - alpha) * fmax(0.0, y) * fmax(0.0, v);
 }
 
+// a / b from rb = RN(1 / b): one product and Markstein's exact-remainder
+// correction give the correctly rounded quotient -- what `a / b` returns -- but
+// quotients can share a reciprocal and, unlike the compiler's inline division, a
+// zero or tiny quotient (v = 0 on every inactive constraint) does not leave the
+// fast path for the out-of-line IEEE routine.  Where every thread or lane handles
+// a different constraint that call was taken on practically every division
+// (profiles/r1_dense_small_ncu_full_8warps.txt: eight calls per Newton step;
+// the lane kernel: 10% of all stall samples on division lines).
+__device__ __forceinline__ double div_r(double a, double b, double rb) {
+  const double q = a * rb;
+  const double rem = fma(-b, q, a);
+  return fma(rem, rb, q);
+}
+__device__ __forceinline__ double div_nr(double a, double b) { return div_r(a, b, 1.0 / b); }
+
 // Generalised gradient of the PFB function -> (gamma, mu):
 // dense_cholesky_solver.cc:54-60,129-148 == riccati_linear_solver.cc:91-99,346-365.
 __device__ __forceinline__ void pfb_barrier(double ys, double v, double alpha,
@@ -131,12 +146,16 @@ __device__ __forceinline__ void pfb_barrier(double ys, double v, double alpha,
     const double d = 0.70710678118654752440;  // 1/sqrt(2)
     ga = alpha * (1.0 - d);
     gb = ga;
-  } else if (ys > 0.0 && v > 0.0) {
-    ga = alpha * (1.0 - ys / r) + (1.0 - alpha) * v;
-    gb = alpha * (1.0 - v / r) + (1.0 - alpha) * ys;
   } else {
-    ga = alpha * (1.0 - ys / r);
-    gb = alpha * (1.0 - v / r);
+    const double rr = 1.0 / r;
+    const double qa = div_r(ys, r, rr), qb = div_r(v, r, rr);  // ys / r, v / r
+    if (ys > 0.0 && v > 0.0) {
+      ga = alpha * (1.0 - qa) + (1.0 - alpha) * v;
+      gb = alpha * (1.0 - qb) + (1.0 - alpha) * ys;
+    } else {
+      ga = alpha * (1.0 - qa);
+      gb = alpha * (1.0 - qb);
+    }
   }
   *gamma = ga;
   *mu = gb + sigma * ga;

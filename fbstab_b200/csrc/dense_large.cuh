@@ -551,7 +551,7 @@ struct DenseLargeProblem : DenseProblem {
       pfb_barrier(ys, x.v[i], alpha, sigma, &ga, &mu);
       gamma[i] = ga;
       mus[i] = mu;
-      Gam[i] = ga / mu;
+      Gam[i] = div_nr(ga, mu);
     }
     __syncthreads();
     // E = (H + sigma I) + A' (Gamma A), lower tiles -> K(0:nz, 0:nz)   (:52,62-63)
@@ -749,7 +749,7 @@ struct DenseLargeProblem : DenseProblem {
       __syncthreads();
     };
     FBS_LAP(15);
-    for (int i = tid; i < nv; i += dl::kThreads) r2[i] = (-rv[i]) / mus[i];
+    for (int i = tid; i < nv; i += dl::kThreads) r2[i] = div_nr(-rv[i], mus[i]);
     for (int i = tid; i < nl; i += dl::kThreads) r1[nz + i] = rl[i];
     __syncthreads();
     for (int i = warp; i < nz; i += nw) {
@@ -843,7 +843,7 @@ struct DenseLargeProblem : DenseProblem {
     // dv = (rv + gamma .* (A dz)) ./ mus ; dy = b - A dz
     for (int i = tid; i < nv; i += dl::kThreads) {
       const double s = dl::dot_stream(A + i, (size_t)nv, dx.z, 1, nz, 0.0);
-      dx.v[i] = (gamma[i] * s + (-rv[i])) / mus[i];
+      dx.v[i] = div_nr(gamma[i] * s + (-rv[i]), mus[i]);
       dx.y[i] = bvec[i] - s;
     }
     __syncthreads();

@@ -95,7 +95,7 @@ struct DenseProblem {
       pfb_barrier(ys, x.v[i], alpha, sigma, &ga, &mu);
       gamma[i] = ga;
       mus[i] = mu;
-      Gam[i] = ga / mu;
+      Gam[i] = div_nr(ga, mu);
     }
     t.sync();
     // E = (H + sigma I) + A' (Gamma A), lower triangle -> K(0:nz,0:nz)
@@ -143,7 +143,7 @@ struct DenseProblem {
   // LinearSolver::Solve with r = -(rz,rl,rv), dense_cholesky_solver.cc:81-127
   __device__ void solve(const Team& t, const double* rz, const double* rl,
                         const double* rv, const Vars& dx) {
-    for (int i = t.rank(); i < nv; i += t.size()) r2[i] = (-rv[i]) / mus[i];
+    for (int i = t.rank(); i < nv; i += t.size()) r2[i] = div_nr(-rv[i], mus[i]);
     for (int i = t.rank(); i < nl; i += t.size()) r1[nz + i] = -(-rl[i]);
     t.sync();
     for (int i = t.warp(); i < nz; i += t.nwarps()) {
@@ -181,7 +181,7 @@ struct DenseProblem {
     for (int i = t.rank(); i < nv; i += t.size()) {
       double s = 0.0;
       for (int j = 0; j < nz; j++) s = fma(A[i + (size_t)j * nv], dx.z[j], s);
-      dx.v[i] = (gamma[i] * s + (-rv[i])) / mus[i];
+      dx.v[i] = div_nr(gamma[i] * s + (-rv[i]), mus[i]);
       dx.y[i] = bvec[i] - s;
     }
     t.sync();

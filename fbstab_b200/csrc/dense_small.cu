@@ -27,10 +27,18 @@
 // and prefetches that instance's data into L2 while it is still solving the
 // current one.
 //
+// Round 2 measured and rejected (profiles/r2_dense_small_steps.txt,
+// profiles/r2_dense_small_team2_ncu.txt): two warps per instance on the same
+// slab (commit 783f97a, dense_small2.cu: parity-green, 1.47x SLOWER -- the
+// dependent chain of one instance got longer, and there are two instances per
+// scheduler either way), an (even, odd) pair of elimination steps per loop trip
+// (-2.5%), the pivot reciprocal computed one step ahead (-4.7%, the switch
+// FBSTAB_DS_LOOKAHEAD_RCP is kept for re-measurement), software-pipelined
+// mat-vec loops (+0.4%, FBSTAB_DS_PIPE_MATVEC).
+//
 // Follows the same reference code as engine.cuh / dense_problem.cuh
 // (fbstab_algorithm-impl.h:113-304, dense_cholesky_solver.cc:32-148,
 // full_residual.cc:49-118, full_feasibility.cc:25-88).
-#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -132,42 +140,6 @@ __device__ __forceinline__ double bcast(double v, int src) {
 }
 // byte address of double index i in a slab at shared address sb
 __device__ __forceinline__ constexpr unsigned D(int i) { return 8u * (unsigned)i; }
-// a / b from rb = RN(1 / b): one product and Markstein's exact-remainder
-// correction give the correctly rounded quotient (what `a / b` returns), but
-// several quotients share one reciprocal and -- unlike the compiler's inline
-// division -- a zero or tiny quotient (v = 0 on every inactive constraint)
-// does not leave the fast path for the out-of-line IEEE routine: that call
-// was taken eight times per Newton step (profiles/r1_dense_small_ncu_full_8warps.txt).
-__device__ __forceinline__ double div_r(double a, double b, double rb) {
-  const double q = a * rb;
-  const double rem = fma(-b, q, a);
-  return fma(rem, rb, q);
-}
-// PFB gradient -> (gamma, mu), common.cuh::pfb_barrier with the two quotients
-// on one reciprocal.
-__device__ __forceinline__ void pfb_barrier_r(double ys, double v, double alpha,
-                                              double sigma, double* gamma,
-                                              double* mu) {
-  const double r = sqrt(ys * ys + v * v);
-  double ga, gb;
-  if (r < 1e-13) {  // zero_tolerance_
-    const double d = 0.70710678118654752440;  // 1/sqrt(2)
-    ga = alpha * (1.0 - d);
-    gb = ga;
-  } else {
-    const double rr = 1.0 / r;
-    const double qa = div_r(ys, r, rr), qb = div_r(v, r, rr);
-    if (ys > 0.0 && v > 0.0) {
-      ga = alpha * (1.0 - qa) + (1.0 - alpha) * v;
-      gb = alpha * (1.0 - qb) + (1.0 - alpha) * ys;
-    } else {
-      ga = alpha * (1.0 - qa);
-      gb = alpha * (1.0 - qb);
-    }
-  }
-  *gamma = ga;
-  *mu = gb + sigma * ga;
-}
 
 struct Warp {
   unsigned sb;  // shared-space byte address of this warp's slab
@@ -484,7 +456,7 @@ struct Warp {
 #pragma unroll
       for (int m = 0; m < NVR; m++) {
         const double ys = x.y[m] + sigma * (x.v[m] - xbar.v[m]);
-        pfb_barrier_r(ys, x.v[m], alpha, sigma, &gamma[m], &mus[m]);
+        pfb_barrier(ys, x.v[m], alpha, sigma, &gamma[m], &mus[m]);
         rmu[m] = 1.0 / mus[m];
         Gam[m] = div_r(gamma[m], mus[m], rmu[m]);
         r2[m] = div_r(-ri.v[m], mus[m], rmu[m]);
@@ -1187,15 +1159,6 @@ int DenseSmallInit(DenseSmallPlan* p, int nz, int nl, int nv, int sm_count,
   p->grid = sm_count * occ;
   p->enabled = true;
   p->name = "dense-small-warp (smem-resident data, DMMA SYRK, register LDL')";
-  {
-    const char* e = getenv("FBSTAB_DENSE_SMALL_TEAM");
-    const int want = e ? atoi(e) : 1;
-    if (want == 2 && DenseSmall2Init(p) == 0) {
-      p->team2 = 1;
-      p->name = "dense-small-team2 (two warps per instance, smem-resident data, DMMA SYRK, "
-                "column-split register Gauss-Jordan)";
-    }
-  }
   return 0;
 }
 
@@ -1205,8 +1168,6 @@ int DenseSmallLaunch(const DenseSmallPlan& p, int batch, const double* H,
                      double* v, double* y, fbstab_out* out,
                      const fbstab_options& opts, int comp,
                      const fbstab_component_io* io, cudaStream_t stream) {
-  if (p.team2)
-    return DenseSmall2Launch(p, batch, H, f, G, h, A, b, z, l, v, y, out, opts, comp, io, stream);
   small::Args a;
   a.comp = comp;
   if (io)

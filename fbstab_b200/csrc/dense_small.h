@@ -14,20 +14,7 @@ struct DenseSmallPlan {
   int grid = 0;
   int* counter = nullptr;
   size_t smem = 0;
-  // two warps per instance (dense_small2.cu) instead of one
-  int team2 = 0;
-  size_t smem2 = 0;
 };
-
-// dense_small2.cu
-int DenseSmall2TeamsPerCta();
-int DenseSmall2Init(DenseSmallPlan* p);  // 0 when the two-warp kernel can run
-int DenseSmall2Launch(const DenseSmallPlan& p, int batch, const double* H,
-                      const double* f, const double* G, const double* h,
-                      const double* A, const double* b, double* z, double* l,
-                      double* v, double* y, fbstab_out* out,
-                      const fbstab_options& opts, int comp,
-                      const fbstab_component_io* io, cudaStream_t stream);
 
 // Instances in flight per CTA of the warp kernel.
 int DenseSmallWarpsPerCta();

@@ -552,7 +552,7 @@ struct Lane {
         pfb_barrier(ys, vv[k], alpha, sigma, &ga, &mu);
         st(i, O_GM + k, ga);
         st(i, O_GM + NC + k, mu);
-        Gam[k] = ga / mu;
+        Gam[k] = div_nr(ga, mu);
       }
       const double* Qm = dat(i, D_Q);
       const double* Rm = dat(i, D_R);
@@ -711,7 +711,7 @@ struct Lane {
 #pragma unroll
     for (int k = 0; k < NC; k++) {
       const double sv = Az_entry(dz, i, k);
-      st(i, O_DX + V_V + k, ((-rv[k]) + ga[k] * sv) / mu[k]);
+      st(i, O_DX + V_V + k, div_nr((-rv[k]) + ga[k] * sv, mu[k]));
       st(i, O_DX + V_Y + k, (-sv) + (-dat(i, D_d)[k * DS]));
     }
   }
@@ -745,7 +745,7 @@ struct Lane {
 #pragma unroll
       for (int k = 0; k < NC; k++) {
         rvv[k] = rr_[R_V + k];
-        tv[k] = (-rvv[k]) / mu[k];
+        tv[k] = div_nr(-rvv[k], mu[k]);
       }
       {
         const double* Em = dat(i, D_E);

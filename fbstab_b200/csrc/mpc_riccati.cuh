@@ -481,7 +481,7 @@ struct MpcProblem {
       pfb_barrier(ys, x.v[i], alpha, sigma, &ga, &mu);
       gamma[i] = ga;
       mus[i] = mu;
-      Gam[i] = ga / mu;
+      Gam[i] = div_nr(ga, mu);
     }
     const int nxx = nx * nx, nuu = nu * nu, nux = nu * nx;
     const FacOff fo = fac_off();
@@ -696,7 +696,7 @@ struct MpcProblem {
       issue_factor_block(0);
       if (N >= 1) issue_factor_block(1);
     }
-    for (int i = t.rank(); i < nv; i += T) tv[i] = (-rv[i]) / mus[i];
+    for (int i = t.rank(); i < nv; i += T) tv[i] = div_nr(-rv[i], mus[i]);
     t.sync();
     for (int e = t.rank(); e < nz; e += T) {
       const int i = e / nsv, rr = e - i * nsv;
@@ -805,7 +805,7 @@ struct MpcProblem {
     for (int e = t.rank(); e < nv; e += T) {
       const int i = e / nc, k = e - i * nc;
       const double s = Az_entry(dx.z, i, k);
-      dx.v[e] = ((-rv[e]) + gamma[e] * s) / mus[e];
+      dx.v[e] = div_nr((-rv[e]) + gamma[e] * s, mus[e]);
       dx.y[e] = (-s) + (-d[e]);
     }
     t.sync();

@@ -8,6 +8,6 @@ name=$1; src=$2; shift 2
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC \
   -Iinclude -Ifbstab_b200/csrc "$@" -c "$src" -o build/variants/$name.o
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$name.so \
-  build/variants/$name.o build/api.cu.o build/dense_small2.cu.o build/mpc_riccati.cu.o build/mpc_lane.cu.o \
+  build/variants/$name.o build/api.cu.o build/mpc_riccati.cu.o build/mpc_lane.cu.o \
   build/microbench.cu.o build/multi_gpu.cu.o build/closed_loop.cu.o build/problems.cpp.o -ldl
 echo built build/variants/$name.so

@@ -14,7 +14,6 @@ run() {  # name, tool, env..., script
 for tool in memcheck racecheck synccheck; do
   SCRIPT=tools/sanitize_mpc.py run "mpc CTA kernel (TMA rings)" $tool X=1
   SCRIPT=tools/sanitize_dense_small.py run "dense small, warp kernel" $tool X=1
-  SCRIPT=tools/sanitize_dense_small.py run "dense small, two-warp team kernel" $tool FBSTAB_DENSE_SMALL_TEAM=2
 done
 SCRIPT=tools/sanitize_mpc.py run "mpc lane kernel" memcheck SANITIZE_LANE=1 FBSTAB_MPC_LANE_MIN=256
 SCRIPT=tools/sanitize_mpc.py run "mpc lane kernel" racecheck SANITIZE_LANE=1 FBSTAB_MPC_LANE_MIN=256
