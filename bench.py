@@ -522,6 +522,22 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
         assert (oh["eflag"] == o["eflag"]).all(), "host and device paths disagree"
         res["e2e"] = {"value": global_batch * Ke / float(te.item()), "unit": UNIT,
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        # the host-side ceiling of e2e: all ranks copy their pinned inputs to their GPUs at
+        # the same time, nothing else running (aggregate GB/s over the box's PCIe / host
+        # memory system); e2e cannot exceed global_batch / (h2d bytes / this rate)
+        big = max(d_host, key=lambda k_: d_host[k_].nbytes)
+        src_t = torch.from_numpy(d_host[big])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            d_dev[big].copy_(src_t, non_blocking=True)
+        barrier()
+        tb = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        agg = world * 2 * d_host[big].nbytes / float(tb.item()) / 1e9
+        res["e2e"]["host_h2d_aggregate_gbs"] = agg
+        res["e2e"]["host_ceiling"] = global_batch / (h2d / (agg / world * 1e9))
         if wl.kind == "mpc":
             # the same solve with ONE copy of the stage data (fbstab_mpc_batch_solve_shared):
             # what a caller who knows its plants are identical ships over PCIe

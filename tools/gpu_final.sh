@@ -1,10 +1,15 @@
+# The end-of-round measurement sequence on ONE GPU (GPU tests, smoke, the full bench line,
+# the reference arm, the ncu launch list of the bench command and the full capture of the
+# headline kernel, DRAM traffic of every config).  Multi-GPU: tools/gpu_final_multi.sh.
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-for c in 2 3a 3b 4a 4b 5; do timeout 600 python bench.py --config $c --steps 3 --warmup 3 > gpurun_out/final_$c.json 2> gpurun_out/final_$c.err; done
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final_ref.json 2>/dev/null
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_cfg2.csv python bench.py --steps 2 --warmup 1 > gpurun_out/launches_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:dense_small -s 1 -c 1 -o gpurun_out/dense_small8 python tools/prof_dense_small.py 16384 > gpurun_out/ncu_ds8.log 2>&1
-ls -la gpurun_out | tail -20
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest_final.log
+tail -3 gpurun_out/r2_pytest_final.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -2 gpurun_out/r2_smoke.log
+bash tools/capture_traffic.sh > gpurun_out/r2_traffic.log 2>&1; tail -5 gpurun_out/r2_traffic.log
+( time timeout 1500 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err ) 2>&1 | tail -3
+tail -9 gpurun_out/r2_bench_final.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2_bench_ref.json 2>/dev/null
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 2 --warmup 3 --per-config 3a,4b --no-cpu > gpurun_out/r2_launches_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:dense_small -s 1 -c 1 -o gpurun_out/r2_dense_small_final python tools/prof_dense_small.py 16384 > gpurun_out/r2_ncu_final.log 2>&1
+ls -la gpurun_out | tail -12
