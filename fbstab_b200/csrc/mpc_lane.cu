@@ -45,6 +45,12 @@
 #ifndef PREFETCH_DIST
 #define PREFETCH_DIST 1
 #endif
+#ifndef FBSTAB_LANE_WS_POLICY
+#define FBSTAB_LANE_WS_POLICY 1
+#endif
+#ifndef FBSTAB_LANE_SDATA_SMEM
+#define FBSTAB_LANE_SDATA_SMEM 0
+#endif
 
 namespace fbs {
 namespace {
@@ -64,6 +70,7 @@ struct LaneArgs {
   // carries the stage data of instance 0, which `sdata` then holds stage-major
   const int* mismatch;
   const double* sdata;
+  int sdata_smem;  // the launch carries (N+1)*DSZ doubles of dynamic shared memory
 };
 
 enum { PH_TOP = 0, PH_TRIAL = 1, PH_REEVAL = 2, PH_FINAL = 3 };
@@ -171,11 +178,26 @@ struct Lane {
   const double* sdata;  // SHARED: [stage][DSZ] common stage data
 
   // element `o` of stage i's block
+  // FBSTAB_LANE_WS_POLICY (A/B switch): 1 = the streamed workspace bypasses L1
+  // (ld.global.cg / st.global.cg), which then keeps the common stage data and the
+  // local-memory spills; 2 = evict-first streaming hints (.cs)
   __device__ __forceinline__ double ld(int i, int o) const {
+#if FBSTAB_LANE_WS_POLICY == 1
+    return __ldcg(ws + ((size_t)i * SB + o) * 32);
+#elif FBSTAB_LANE_WS_POLICY == 2
+    return __ldcs(ws + ((size_t)i * SB + o) * 32);
+#else
     return ws[((size_t)i * SB + o) * 32];
+#endif
   }
   __device__ __forceinline__ void st(int i, int o, double v) const {
+#if FBSTAB_LANE_WS_POLICY == 1
+    __stcg(ws + ((size_t)i * SB + o) * 32, v);
+#elif FBSTAB_LANE_WS_POLICY == 2
+    __stcs(ws + ((size_t)i * SB + o) * 32, v);
+#else
     ws[((size_t)i * SB + o) * 32] = v;
+#endif
   }
   // address of element `o` of stage i's block (stride 32 doubles between elements)
   __device__ __forceinline__ const double* dat(int i, int o) const {
@@ -1166,6 +1188,16 @@ __global__ void __launch_bounds__(32, 8) mpc_lane_kernel(const __grid_constant__
   p.nv = (a.N + 1) * NC;
   p.ws = a.ws + (size_t)blockIdx.x * a.ws_stride + lane;
   p.sdata = a.sdata;
+#if FBSTAB_LANE_SDATA_SMEM
+  // the common stage data ((N+1) x DSZ doubles) in the warp's shared memory
+  extern __shared__ double lane_smem[];
+  if (SHARED && a.sdata_smem) {
+    const int total = (a.N + 1) * LN::DSZ;
+    for (int e = lane; e < total; e += 32) lane_smem[e] = a.sdata[e];
+    __syncwarp();
+    p.sdata = lane_smem;
+  }
+#endif
 
   // per-lane solver state (fbstab_algorithm-impl.h:113-304 as a phase machine)
   bool active = false, exhausted = false;
@@ -1455,6 +1487,12 @@ int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps, const
   memset(&a.io, 0, sizeof(a.io));
   a.mismatch = nullptr;
   a.sdata = nullptr;
+  a.sdata_smem = 0;
+  size_t smem = 0;
+#if FBSTAB_LANE_SDATA_SMEM
+  smem = MpcLaneSharedDoubles(N, nx, nu, nc) * 8;
+  if (smem <= 48 * 1024) a.sdata_smem = 1; else smem = 0;
+#endif
   const int warps = std::min(max_warps, (batch + 31) / 32);
   if (mismatch && sdata) {
     // common-stage-data detection: one pass over the inputs, then exactly one of
@@ -1469,7 +1507,7 @@ int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps, const
     var->build<<<32, 256, 0, stream>>>(data, N, mismatch, sdata);
     a.mismatch = mismatch;
     a.sdata = sdata;
-    var->fn_shared<<<warps, 32, 0, stream>>>(a);
+    var->fn_shared<<<warps, 32, smem, stream>>>(a);
     if (shared_known) return cudaGetLastError() == cudaSuccess ? 0 : 1;
   } else if (shared_known) {
     return 1;  // the caller checks lane_sdata before asking for this path

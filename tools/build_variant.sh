@@ -1,13 +1,19 @@
 #!/bin/bash
-# tools/build_variant.sh NAME SRC [nvcc flags...]: links a copy of the library whose
-# dense_small.cu object is built from SRC with the given flags (A/B timing of kernel
-# variants in one GPU call: FBSTAB_B200_LIB=build/variants/NAME.so).
+# tools/build_variant.sh NAME SRC [nvcc flags...]: links a copy of the library in which the
+# object of SRC (a file of fbstab_b200/csrc, e.g. fbstab_b200/csrc/mpc_lane.cu) is rebuilt
+# with the given flags (A/B timing of kernel variants in one GPU call:
+# FBSTAB_B200_LIB=build/variants/NAME.so).  The other objects come from build/ (run
+# __graft_entry__.build() first).
 set -e
 cd "$(dirname "$0")/.."
 name=$1; src=$2; shift 2
+mkdir -p build/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC \
   -Iinclude -Ifbstab_b200/csrc "$@" -c "$src" -o build/variants/$name.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$name.so \
-  build/variants/$name.o build/api.cu.o build/mpc_riccati.cu.o build/mpc_lane.cu.o \
-  build/microbench.cu.o build/multi_gpu.cu.o build/closed_loop.cu.o build/problems.cpp.o -ldl
+base=$(basename "$src")
+objs=""
+for o in api.cu dense_small.cu mpc_riccati.cu mpc_lane.cu microbench.cu multi_gpu.cu closed_loop.cu problems.cpp; do
+  if [ "$o" == "$base" ]; then objs="$objs build/variants/$name.o"; else objs="$objs build/$o.o"; fi
+done
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$name.so $objs -ldl
 echo built build/variants/$name.so
