@@ -1047,8 +1047,9 @@ int fbstab_mpc_batch_create(int N, int nx, int nu, int nc, int max_batch,
                        std::max(256, (int)(fbs::MpcLaneCrossover(nx, nu, nc) * 16 * h->sm_count)));
   if (fbs::MpcLaneSupported(nx, nu, nc) && EnvInt("FBSTAB_MPC_LANE", 1) &&
       max_batch >= h->lane_min) {
-    const int warps = std::min((max_batch + 31) / 32,
-                               h->sm_count * EnvInt("FBSTAB_MPC_LANE_WARPS_PER_SM", 8));
+    int warps = fbs::MpcLaneWarps(N, nx, nu, nc, max_batch, h->sm_count, nullptr);
+    if (EnvInt("FBSTAB_MPC_LANE_WARPS_PER_SM", 0) > 0)
+      warps = std::min(warps, h->sm_count * EnvInt("FBSTAB_MPC_LANE_WARPS_PER_SM", 0));
     const size_t bytes = (size_t)warps * fbs::MpcLaneWsDoublesPerWarp(N, nx, nu, nc) * 8;
     if (cudaMalloc(&h->lane_ws, bytes) == cudaSuccess) {
       h->lane_warps = warps;

@@ -36,6 +36,7 @@
 #include "common.cuh"
 #include "engine.cuh"
 #include "mpc_lane.h"
+#include "tma.cuh"
 
 #ifdef PREFETCH_L1
 #define PREFETCH_OP "prefetch.global.L1"
@@ -49,7 +50,10 @@
 #define FBSTAB_LANE_WS_POLICY 1
 #endif
 #ifndef FBSTAB_LANE_SDATA_SMEM
-#define FBSTAB_LANE_SDATA_SMEM 0
+#define FBSTAB_LANE_SDATA_SMEM 1
+#endif
+#ifndef FBSTAB_LANE_SLOTS
+#define FBSTAB_LANE_SLOTS 2
 #endif
 
 namespace fbs {
@@ -71,7 +75,9 @@ struct LaneArgs {
   const int* mismatch;
   const double* sdata;
   int sdata_smem;  // the launch carries (N+1)*DSZ doubles of dynamic shared memory
+  int warps;       // warps that have a workspace (the last CTA may be partly idle)
 };
+constexpr int kLaneWarpsPerCta = 4;
 
 enum { PH_TOP = 0, PH_TRIAL = 1, PH_REEVAL = 2, PH_FINAL = 3 };
 
@@ -178,9 +184,9 @@ struct Lane {
   const double* sdata;  // SHARED: [stage][DSZ] common stage data
 
   // element `o` of stage i's block
-  // FBSTAB_LANE_WS_POLICY (A/B switch): 1 = the streamed workspace bypasses L1
-  // (ld.global.cg / st.global.cg), which then keeps the common stage data and the
-  // local-memory spills; 2 = evict-first streaming hints (.cs)
+  // The streamed workspace bypasses L1 (ld.global.cg / st.global.cg), which then keeps
+  // the common stage data and the local-memory spill slots (FBSTAB_LANE_WS_POLICY=0:
+  // default caching, 2: evict-first hints -- A/B switches).
   __device__ __forceinline__ double ld(int i, int o) const {
 #if FBSTAB_LANE_WS_POLICY == 1
     return __ldcg(ws + ((size_t)i * SB + o) * 32);
@@ -190,7 +196,10 @@ struct Lane {
     return ws[((size_t)i * SB + o) * 32];
 #endif
   }
+  // stores of a sweep that the whole warp executes are predicated on `on` (the lanes
+  // the sweep is for)
   __device__ __forceinline__ void st(int i, int o, double v) const {
+    if (!on) return;
 #if FBSTAB_LANE_WS_POLICY == 1
     __stcg(ws + ((size_t)i * SB + o) * 32, v);
 #elif FBSTAB_LANE_WS_POLICY == 2
@@ -199,6 +208,63 @@ struct Lane {
     ws[((size_t)i * SB + o) * 32] = v;
 #endif
   }
+
+  // ---- stage-block ring --------------------------------------------------------
+  // The four sweeps of a Newton round (evaluate, factor, forward and backward
+  // substitution) read their stage blocks from a 2-slot ring in shared memory that the
+  // TMA engine fills ONE STAGE AHEAD: a stage's block is contiguous in the
+  // lane-interleaved workspace, so lane 0 issues one cp.async.bulk for the elements
+  // [o0, o1) of the stage (plus up to two short runs, e.g. the next stage's
+  // multipliers) and the slot's mbarrier counts the bytes.  The warp waits on shared
+  // memory (~30 cycles) instead of on one L2 / DRAM round trip per batch of loads the
+  // compiler could not hoist (59 % of all stall samples before,
+  // profiles/r2_mpc_lane_ring.txt).  Stores go straight to global memory.
+  static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+  static constexpr int RING_E =
+      cmax(cmax(3 * VSZ + 3 * NX, (O_FAC + FS - O_RI) + NX), (O_FAC + FS - (O_RI + R_V)) + NS + NX);
+  static constexpr int SLOTS = FBSTAB_LANE_SLOTS;  // ring depth: SLOTS - 1 stages in flight
+  double* ring;        // this lane's column of slot 0 (element e of slot s: ring[(s*RING_E+e)*32])
+  unsigned bar0;       // shared address of the SLOTS slot mbarriers
+  unsigned par;        // bit s: the parity the next wait on slot s expects
+  bool on;             // this lane takes part in the current sweep (stores enabled)
+
+  // sweep start: the stores of earlier sweeps become visible to the TMA engine
+  __device__ __forceinline__ void ring_begin() const {
+    tma::fence_proxy_async_all();
+    __syncwarp();
+  }
+  // stage i's elements [o0, o1) and up to three runs of xn elements of stage ix, starting
+  // at x0o, x1o, x2o (a negative offset: no run) -> slot s, back to back
+  __device__ __forceinline__ void ring_issue(int s, int i, int o0, int o1, int ix = -1,
+                                             int xn = 0, int x0o = -1, int x1o = -1,
+                                             int x2o = -1) const {
+    if ((threadIdx.x & 31) == 0) {
+      const bool hx = ix >= 0 && ix <= N && xn > 0;
+      const int xo[3] = {x0o, x1o, x2o};
+      int runs = 0;
+#pragma unroll
+      for (int m = 0; m < 3; m++) runs += (hx && xo[m] >= 0) ? 1 : 0;
+      const unsigned bar = bar0 + 8u * s;
+      unsigned dst = tma::smem_addr(ring) + (unsigned)s * RING_E * 256u;
+      const char* base = (const char*)ws;
+      tma::mbar_arrive_expect_tx(bar, (unsigned)(o1 - o0 + runs * xn) * 256u);
+      tma::bulk_g2s(dst, base + ((size_t)i * SB + o0) * 256, (unsigned)(o1 - o0) * 256u, bar);
+      dst += (unsigned)(o1 - o0) * 256u;
+#pragma unroll
+      for (int m = 0; m < 3; m++)
+        if (hx && xo[m] >= 0) {
+          tma::bulk_g2s(dst, base + ((size_t)ix * SB + xo[m]) * 256, (unsigned)xn * 256u, bar);
+          dst += (unsigned)xn * 256u;
+        }
+    }
+  }
+  // waits for slot s; returns this lane's column of it
+  __device__ __forceinline__ const double* ring_wait(int s) {
+    tma::mbar_wait(bar0 + 8u * s, (par >> s) & 1u);
+    par ^= 1u << s;
+    return ring + (size_t)s * RING_E * 32;
+  }
+
   // address of element `o` of stage i's block (stride 32 doubles between elements)
   __device__ __forceinline__ const double* dat(int i, int o) const {
     if (SHARED) return sdata + (size_t)i * DSZ + (o - O_DAT);
@@ -356,33 +422,47 @@ struct Lane {
     double s[6] = {0, 0, 0, 0, 0, 0};
     double zp[NS], lc[NX], ln[NX];  // z(i-1), l(i), l(i+1)
 #pragma unroll
-    for (int k = 0; k < NX; k++) {
-      const double a0 = ld(0, base + V_L + k), b0 = ld(0, O_DX + V_L + k);
-      lc[k] = trial ? fma(t, b0, a0) : a0;
-      ln[k] = 0.0;
-    }
+    for (int k = 0; k < NX; k++) lc[k] = ln[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < NS; k++) zp[k] = 0.0;
+    // ring: [ xk | xi | dx ] of the stage, then l of the next stage in xk, xi and dx
+    constexpr int E0 = 3 * VSZ;
+    const int lsel = (base == O_XK) ? 0 : NX;
+    ring_begin();
+    for (int j = 0; j < SLOTS - 1 && j <= N; j++)
+      ring_issue(j, j, 0, E0, j + 1, NX, O_XK + V_L, O_XI + V_L, O_DX + V_L);
     for (int i = 0; i <= N; i++) {
-      prefetch(i + PREFETCH_DIST, 0, O_RI);
       prefetch(i + PREFETCH_DIST, O_DAT, SBF);
+      __syncwarp();
+      {
+        const int j = i + SLOTS - 1;
+        if (j <= N) ring_issue(j % SLOTS, j, 0, E0, j + 1, NX, O_XK + V_L, O_XI + V_L, O_DX + V_L);
+      }
+      const double* sl = ring_wait(i % SLOTS);
+      if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+          const double a0 = sl[(base + V_L + k) * 32], b0 = sl[(O_DX + V_L + k) * 32];
+          lc[k] = trial ? fma(t, b0, a0) : a0;
+        }
+      }
       double xb[VSZ], xd[VSZ], zk[NS], lk[NX], vk[NC], la[NX], lb[NX];
 #pragma unroll
       for (int k = 0; k < VSZ; k++) {
-        xb[k] = ld(i, base + k);
-        xd[k] = ld(i, O_DX + k);
+        xb[k] = sl[(base + k) * 32];
+        xd[k] = sl[(O_DX + k) * 32];
       }
 #pragma unroll
-      for (int k = 0; k < NS; k++) zk[k] = ld(i, O_XK + V_Z + k);
+      for (int k = 0; k < NS; k++) zk[k] = sl[(O_XK + V_Z + k) * 32];
 #pragma unroll
-      for (int k = 0; k < NX; k++) lk[k] = ld(i, O_XK + V_L + k);
+      for (int k = 0; k < NX; k++) lk[k] = sl[(O_XK + V_L + k) * 32];
 #pragma unroll
-      for (int k = 0; k < NC; k++) vk[k] = ld(i, O_XK + V_V + k);
+      for (int k = 0; k < NC; k++) vk[k] = sl[(O_XK + V_V + k) * 32];
       if (i < N) {
 #pragma unroll
         for (int k = 0; k < NX; k++) {
-          la[k] = ld(i + 1, base + V_L + k);
-          lb[k] = ld(i + 1, O_DX + V_L + k);
+          la[k] = sl[(E0 + lsel + k) * 32];
+          lb[k] = sl[(E0 + 2 * NX + k) * 32];
         }
       }
       double z[NS], v[NC], y[NC];
@@ -524,7 +604,9 @@ struct Lane {
   // RiccatiLinearSolver::Initialize, riccati_linear_solver.cc:77-210.
   // with_commit: the accepted step xi <- xi + t dx is applied in the same sweep
   // (saves one pass over the horizon in the common accept-then-Newton round).
-  __device__ bool factor(double sigma, double alpha, bool with_commit, double t) {
+  // any_commit: some lane of the warp commits (warp-uniform; selects the ring range)
+  __device__ bool factor(double sigma, double alpha, bool with_commit, double t,
+                         bool any_commit) {
     bool ok = true;
     double Lc[NX][NX];
     const double rs = 1.0 / sqrt(sigma);  // reciprocal diagonal of L(0) = sqrt(sigma) I
@@ -532,38 +614,54 @@ struct Lane {
     for (int a_ = 0; a_ < NX; a_++)
 #pragma unroll
       for (int b_ = 0; b_ < NX; b_++) Lc[a_][b_] = (a_ == b_) ? rs : 0.0;
+    // ring: xi.v, xi.y (with a commit in the warp: all of xi and dx), then xk.v
+    const int o0 = any_commit ? O_XI : O_XI + V_V;
+    const int o1 = any_commit ? O_RI : O_XI + VSZ;
+    const int ox = o1 - o0;
+    ring_begin();
+    for (int j = 0; j < SLOTS - 1 && j <= N; j++) ring_issue(j, j, o0, o1, j, NC, O_XK + V_V);
     for (int i = 0; i <= N; i++) {
-      prefetch(i + PREFETCH_DIST, O_XK + V_V, O_RI);
       prefetch(i + PREFETCH_DIST, O_DAT, SBF);
+      __syncwarp();
+      {
+        const int j = i + SLOTS - 1;
+        if (j <= N) ring_issue(j % SLOTS, j, o0, o1, j, NC, O_XK + V_V);
+      }
+      const double* sl = ring_wait(i % SLOTS);
       double yv[NC], vv[NC], vk[NC];
 #pragma unroll
       for (int k = 0; k < NC; k++) {
-        yv[k] = ld(i, O_XI + V_Y + k);
-        vv[k] = ld(i, O_XI + V_V + k);
-        vk[k] = ld(i, O_XK + V_V + k);
+        yv[k] = sl[(O_XI + V_Y + k - o0) * 32];
+        vv[k] = sl[(O_XI + V_V + k - o0) * 32];
+        vk[k] = sl[(ox + k) * 32];
       }
-      if (with_commit) {
+      if (any_commit) {
         double xz[V_V], dz[V_V], dv[NC], dy[NC], dd[NC];
 #pragma unroll
         for (int k = 0; k < V_V; k++) {
-          xz[k] = ld(i, O_XI + k);
-          dz[k] = ld(i, O_DX + k);
+          xz[k] = sl[(O_XI + k - O_XI) * 32];
+          dz[k] = sl[(O_DX + k - O_XI) * 32];
         }
 #pragma unroll
         for (int k = 0; k < NC; k++) {
-          dv[k] = ld(i, O_DX + V_V + k);
-          dy[k] = ld(i, O_DX + V_Y + k);
+          dv[k] = sl[(O_DX + V_V + k - O_XI) * 32];
+          dy[k] = sl[(O_DX + V_Y + k - O_XI) * 32];
           dd[k] = dat(i, D_d)[k * DS];
         }
+        const bool keep = on;
+        on = keep && with_commit;
 #pragma unroll
         for (int k = 0; k < V_V; k++) st(i, O_XI + k, fma(t, dz[k], xz[k]));
 #pragma unroll
         for (int k = 0; k < NC; k++) {
-          vv[k] = fma(t, dv[k], vv[k]);
-          yv[k] = fma(-t, -dd[k], fma(t, dy[k], yv[k]));
+          const double v2 = fma(t, dv[k], vv[k]);
+          const double y2 = fma(-t, -dd[k], fma(t, dy[k], yv[k]));
+          vv[k] = with_commit ? v2 : vv[k];
+          yv[k] = with_commit ? y2 : yv[k];
           st(i, O_XI + V_V + k, vv[k]);
           st(i, O_XI + V_Y + k, yv[k]);
         }
+        on = keep;
       }
       store_lower(i, O_FAC + oL, Lc);
       double Gam[NC];
@@ -743,24 +841,36 @@ struct Lane {
   // SG^-1(.) -> dx.z u(i) until the backward sweep writes the step there.
   __device__ void solve() {
     double th[NX];  // theta(i)
-#pragma unroll
-    for (int k = 0; k < NX; k++) th[k] = ld(0, O_RI + R_L + k);  // r2(0) = rl(0)
     double lp[NX];  // dl(i+1) in the backward sweep
+    // ring: [ ri | gamma mu | factor ] of the stage, then ri.l of the next stage
+    constexpr int F0 = O_RI, F1 = O_FAC + FS, FX = F1 - F0;
+    ring_begin();
+    for (int j = 0; j < SLOTS - 1 && j <= N; j++) ring_issue(j, j, F0, F1, j + 1, NX, O_RI + R_L);
     for (int i = 0; i <= N; i++) {
-      prefetch(i + PREFETCH_DIST, O_RI, SBF);
+      prefetch(i + PREFETCH_DIST, O_DAT, SBF);
+      __syncwarp();
+      {
+        const int j = i + SLOTS - 1;
+        if (j <= N) ring_issue(j % SLOTS, j, F0, F1, j + 1, NX, O_RI + R_L);
+      }
+      const double* sl = ring_wait(i % SLOTS);
+      if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < NX; k++) th[k] = sl[(O_RI + R_L + k - F0) * 32];  // r2(0) = rl(0)
+      }
       double rr_[RSZ], mu[NC], ga[NC], fa[FS], rln[NX];
 #pragma unroll
-      for (int k = 0; k < RSZ; k++) rr_[k] = ld(i, O_RI + k);
+      for (int k = 0; k < RSZ; k++) rr_[k] = sl[(O_RI + k - F0) * 32];
 #pragma unroll
       for (int k = 0; k < NC; k++) {
-        ga[k] = ld(i, O_GM + k);
-        mu[k] = ld(i, O_GM + NC + k);
+        ga[k] = sl[(O_GM + k - F0) * 32];
+        mu[k] = sl[(O_GM + NC + k - F0) * 32];
       }
 #pragma unroll
-      for (int k = 0; k < FS; k++) fa[k] = ld(i, O_FAC + k);
+      for (int k = 0; k < FS; k++) fa[k] = sl[(O_FAC + k - F0) * 32];
       if (i < N) {
 #pragma unroll
-        for (int k = 0; k < NX; k++) rln[k] = ld(i + 1, O_RI + R_L + k);
+        for (int k = 0; k < NX; k++) rln[k] = sl[(FX + k) * 32];
       }
       // r3 = rv ./ mus, r1 = r.z - A' r3 for this stage (:222-225)
       double tv[NC], r1[NS], rvv[NC];
@@ -868,20 +978,32 @@ struct Lane {
       }
     }
     // backward recursion :297-327
-    for (int i = N - 1; i >= 0; i--) {
-      prefetch(i - PREFETCH_DIST, O_DX, SBF);
+    // ring: [ ri.v | gamma mu | factor ] of the stage, then its dx.z, dx.l (the forward
+    // sweep's M^-1 h, SG^-1(.) and theta)
+    constexpr int B0 = O_RI + R_V, B1 = O_FAC + FS, BX = B1 - B0;
+    ring_begin();
+    for (int j = 0; j < SLOTS - 1 && j < N; j++)
+      ring_issue(j, N - 1 - j, B0, B1, N - 1 - j, NS + NX, O_DX + V_Z);
+    for (int i = N - 1, kk = 0; i >= 0; i--, kk++) {
+      prefetch(i - PREFETCH_DIST, O_DAT, SBF);
+      __syncwarp();
+      {
+        const int j = kk + SLOTS - 1;
+        if (j < N) ring_issue(j % SLOTS, N - 1 - j, B0, B1, N - 1 - j, NS + NX, O_DX + V_Z);
+      }
+      const double* sl = ring_wait(kk % SLOTS);
       double fa[FS], dxz[NS], thi[NX], rvv[NC], ga[NC], mu[NC];
 #pragma unroll
-      for (int k = 0; k < FS; k++) fa[k] = ld(i, O_FAC + k);
+      for (int k = 0; k < FS; k++) fa[k] = sl[(O_FAC + k - B0) * 32];
 #pragma unroll
-      for (int k = 0; k < NS; k++) dxz[k] = ld(i, O_DX + V_Z + k);
+      for (int k = 0; k < NS; k++) dxz[k] = sl[(BX + V_Z + k) * 32];
 #pragma unroll
-      for (int k = 0; k < NX; k++) thi[k] = ld(i, O_DX + V_L + k);
+      for (int k = 0; k < NX; k++) thi[k] = sl[(BX + V_L + k) * 32];
 #pragma unroll
       for (int k = 0; k < NC; k++) {
-        rvv[k] = ld(i, O_RI + R_V + k);
-        ga[k] = ld(i, O_GM + k);
-        mu[k] = ld(i, O_GM + NC + k);
+        rvv[k] = sl[(O_RI + R_V + k - B0) * 32];
+        ga[k] = sl[(O_GM + k - B0) * 32];
+        mu[k] = sl[(O_GM + NC + k - B0) * 32];
       }
       double Lc[NX][NX], Mm[NX][NX], SG[NU][NU];
       unpack_x(fa + oL, Lc);
@@ -1174,30 +1296,45 @@ __global__ void mpc_shared_build(MpcData d, int N, const int* mismatch, double* 
 }
 
 template <int NX, int NU, int NC, bool SHARED>
-__global__ void __launch_bounds__(32, 8) mpc_lane_kernel(const __grid_constant__ LaneArgs a) {
+__global__ void __launch_bounds__(32 * kLaneWarpsPerCta, 1) mpc_lane_kernel(const __grid_constant__ LaneArgs a) {
   using LN = Lane<NX, NU, NC, SHARED>;
   // exactly one of the two instantiations runs a launch pair
   if (a.mismatch != nullptr && ((*a.mismatch == 0) != SHARED)) return;
   const fbstab_options& o = a.opts;
   const double sigma = o.sigma0, alpha = o.alpha;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;  // warp in CTA
+  const int warp = blockIdx.x * (blockDim.x >> 5) + wic;
+  if (warp >= a.warps) return;  // (before any barrier: the whole warp leaves)
   LN p;
   p.N = a.N;
   p.nz = (a.N + 1) * LN::NS;
   p.nl = (a.N + 1) * NX;
   p.nv = (a.N + 1) * NC;
-  p.ws = a.ws + (size_t)blockIdx.x * a.ws_stride + lane;
+  p.ws = a.ws + (size_t)warp * a.ws_stride + lane;
   p.sdata = a.sdata;
-#if FBSTAB_LANE_SDATA_SMEM
-  // the common stage data ((N+1) x DSZ doubles) in the warp's shared memory
-  extern __shared__ double lane_smem[];
-  if (SHARED && a.sdata_smem) {
-    const int total = (a.N + 1) * LN::DSZ;
-    for (int e = lane; e < total; e += 32) lane_smem[e] = a.sdata[e];
-    __syncwarp();
-    p.sdata = lane_smem;
+  // shared memory: per warp [ slot mbarriers (128 bytes) | stage-block ring ], then ONE
+  // copy of the common stage data for the CTA's warps (the warps are independent:
+  // no CTA-wide barrier after this point)
+  extern __shared__ __align__(128) unsigned char lane_smem[];
+  constexpr size_t kWarpSmem = 128 + (size_t)LN::SLOTS * LN::RING_E * 256;
+  unsigned char* my = lane_smem + (size_t)wic * kWarpSmem;
+  if (lane == 0) {
+#pragma unroll
+    for (int m = 0; m < LN::SLOTS; m++) tma::mbar_init(tma::smem_addr(my) + 8 * m, 1);
+    tma::fence_mbar_init();
   }
-#endif
+  p.bar0 = tma::smem_addr(my);
+  p.ring = reinterpret_cast<double*>(my + 128) + lane;
+  p.par = 0;
+  p.on = true;
+  p.bind(a, 0);  // lanes that never own an instance still execute the ring sweeps
+  if (SHARED && a.sdata_smem) {
+    double* sd = reinterpret_cast<double*>(lane_smem + (size_t)(blockDim.x >> 5) * kWarpSmem);
+    const int total = (a.N + 1) * LN::DSZ;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) sd[e] = a.sdata[e];
+    p.sdata = sd;
+  }
+  __syncthreads();
 
   // per-lane solver state (fbstab_algorithm-impl.h:113-304 as a phase machine)
   bool active = false, exhausted = false;
@@ -1235,13 +1372,21 @@ __global__ void __launch_bounds__(32, 8) mpc_lane_kernel(const __grid_constant__
     if (!__any_sync(0xffffffffu, active)) break;
 
     // ---- evaluate -----------------------------------------------------------
+    // (the ring sweeps are executed by the whole warp -- lane 0 feeds the ring --
+    // and `on` marks the lanes they are for)
     EvalOut e;
     e.Ei = e.Eo = 0.0;
-    if (active && need_eval) {
+    const bool ev = active && need_eval;
+    if (__any_sync(0xffffffffu, ev)) {
       const bool self_bar = (phase == PH_TOP) || (phase == PH_FINAL);
       const int base = (phase == PH_FINAL && !pick_xi) ? LN::O_XK : LN::O_XI;
-      e = p.evaluate(base, phase == PH_TRIAL, tstep, self_bar, sigma, alpha);
-      evals++;
+      p.on = ev;
+      const EvalOut e2 = p.evaluate(base, phase == PH_TRIAL, tstep, self_bar, sigma, alpha);
+      p.on = true;
+      if (ev) {
+        e = e2;
+        evals++;
+      }
     }
     // ---- decide ---------------------------------------------------------------
     bool do_commit = false, do_newton = false, prox_end = false, finish = false;
@@ -1328,27 +1473,33 @@ __global__ void __launch_bounds__(32, 8) mpc_lane_kernel(const __grid_constant__
     // (lanes that go on to a Newton step commit inside the factor sweep)
     if (do_commit && !do_newton) p.commit(tstep);
     // ---- Newton step ------------------------------------------------------------
-    if (do_newton) {
-      if (!p.factor(sigma, alpha, do_commit, tstep)) {  // impl:263-267
-        status = FBSTAB_STATUS_FACTOR_FAILED;
-        finish = true;
-        which = 0;
-      } else {
-        p.solve();
-        newton++;
-        current_merit = 0.5 * Ei_c * Ei_c;
+    if (__any_sync(0xffffffffu, do_newton)) {
+      const bool wc = do_newton && do_commit;
+      p.on = do_newton;
+      const bool fok = p.factor(sigma, alpha, wc, tstep, __any_sync(0xffffffffu, wc));
+      p.solve();
+      p.on = true;
+      if (do_newton) {
+        if (!fok) {  // impl:263-267
+          status = FBSTAB_STATUS_FACTOR_FAILED;
+          finish = true;
+          which = 0;
+        } else {
+          newton++;
+          current_merit = 0.5 * Ei_c * Ei_c;
 #pragma unroll
-        for (int m = 4; m > 0; m--) merit[m] = merit[m - 1];
-        merit[0] = current_merit;
-        m0 = current_merit;
-        if (o.nonmonotone_linesearch) {
+          for (int m = 4; m > 0; m--) merit[m] = merit[m - 1];
+          merit[0] = current_merit;
+          m0 = current_merit;
+          if (o.nonmonotone_linesearch) {
 #pragma unroll
-          for (int m = 1; m < 5; m++) m0 = fmax(m0, merit[m]);
+            for (int m = 1; m < 5; m++) m0 = fmax(m0, merit[m]);
+          }
+          tstep = 1.0;
+          ls_j = 0;
+          phase = PH_TRIAL;
+          need_eval = true;
         }
-        tstep = 1.0;
-        ls_j = 0;
-        phase = PH_TRIAL;
-        need_eval = true;
       }
     }
     // ---- end of the subproblem, impl:300-216 -------------------------------------
@@ -1418,6 +1569,11 @@ const LaneVariant kLaneVariants[] = {
 
 }  // namespace
 
+static int EnvLaneInt(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 // Batch size (in units of 16 instances per SM, the CTA kernel's default
 // residency) from which the lane kernel is the faster one.  With every instance resident at once its time
 // is the latency of one solve, whatever the batch; the CTA kernel needs one
@@ -1428,6 +1584,43 @@ double MpcLaneCrossover(int nx, int nu, int nc) {
   if (nx == 4 && nu == 1 && nc == 4) return 4.2;
   if (nx == 2 && nu == 1 && nc == 6) return 1.1;
   return 4.0;
+}
+
+// dynamic shared memory of one warp: slot mbarriers (padded to 128 bytes) + the ring
+size_t MpcLaneSmemBytes(int nx, int nu, int nc) {
+  if (nx == 4 && nu == 1 && nc == 4)
+    return 128 + (size_t)Lane<4, 1, 4>::SLOTS * Lane<4, 1, 4>::RING_E * 256;
+  if (nx == 2 && nu == 1 && nc == 6)
+    return 128 + (size_t)Lane<2, 1, 6>::SLOTS * Lane<2, 1, 6>::RING_E * 256;
+  return 0;
+}
+// Warps per CTA (one CTA per SM): as many as the rings and one copy of the common
+// stage data leave room for, at most kLaneWarpsPerCta.
+static int LaneCtaWarps(int N, int nx, int nu, int nc, bool* sdata_smem) {
+  const size_t ring = MpcLaneSmemBytes(nx, nu, nc);
+  const size_t sd = MpcLaneSharedDoubles(N, nx, nu, nc) * 8;
+  const size_t cap = 227 * 1024;
+  int w = EnvLaneInt("FBSTAB_MPC_LANE_CTA_WARPS", kLaneWarpsPerCta);
+  w = std::max(1, std::min(w, kLaneWarpsPerCta));
+  bool in_smem = FBSTAB_LANE_SDATA_SMEM != 0;
+  while (w > 1 && w * ring + (in_smem ? sd : 0) > cap) w--;
+  if (w * ring + (in_smem ? sd : 0) > cap) in_smem = false;  // long horizons: read it through L1
+  if (sdata_smem) *sdata_smem = in_smem;
+  return w;
+}
+int MpcLaneWarpsPerSm(int N, int nx, int nu, int nc) {
+  return LaneCtaWarps(N, nx, nu, nc, nullptr);
+}
+// Warps launched for `batch` instances on `sms` SMs (one CTA per SM): the batch is spread
+// over every SM, and a lane's time is that of the instances it solves one after the
+// other, so rather more warps than ceil(batch / 32) than idle SMs.
+int MpcLaneWarps(int N, int nx, int nu, int nc, int batch, int sms, int* per_cta) {
+  const int cta_warps = LaneCtaWarps(N, nx, nu, nc, nullptr);
+  const int need = std::max(1, (batch + 31) / 32);
+  const int ctas = std::min(sms, need);
+  const int pc = std::min(cta_warps, (need + ctas - 1) / ctas);
+  if (per_cta) *per_cta = pc;
+  return ctas * pc;
 }
 
 bool MpcLaneSupported(int nx, int nu, int nc) {
@@ -1487,13 +1680,23 @@ int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps, const
   memset(&a.io, 0, sizeof(a.io));
   a.mismatch = nullptr;
   a.sdata = nullptr;
-  a.sdata_smem = 0;
-  size_t smem = 0;
-#if FBSTAB_LANE_SDATA_SMEM
-  smem = MpcLaneSharedDoubles(N, nx, nu, nc) * 8;
-  if (smem <= 48 * 1024) a.sdata_smem = 1; else smem = 0;
-#endif
-  const int warps = std::min(max_warps, (batch + 31) / 32);
+  bool sd_smem = false;
+  const int cta_warps = LaneCtaWarps(N, nx, nu, nc, &sd_smem);
+  const size_t smem_rings = (size_t)cta_warps * MpcLaneSmemBytes(nx, nu, nc);
+  const size_t smem_shared = smem_rings + (sd_smem ? MpcLaneSharedDoubles(N, nx, nu, nc) * 8 : 0);
+  a.sdata_smem = sd_smem ? 1 : 0;
+  if (cudaFuncSetAttribute((const void*)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem_rings) != cudaSuccess ||
+      cudaFuncSetAttribute((const void*)var->fn_shared,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem_shared) != cudaSuccess)
+    return 1;
+  int dev = 0, sms = 148, per_cta = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int warps = std::min(max_warps, MpcLaneWarps(N, nx, nu, nc, batch, sms, &per_cta));
+  const int ctas = (warps + per_cta - 1) / per_cta;
+  a.warps = warps;
   if (mismatch && sdata) {
     // common-stage-data detection: one pass over the inputs, then exactly one of
     // the two kernels below does the work (no host round trip)
@@ -1507,12 +1710,12 @@ int MpcLaneLaunch(int N, int nx, int nu, int nc, int batch, int max_warps, const
     var->build<<<32, 256, 0, stream>>>(data, N, mismatch, sdata);
     a.mismatch = mismatch;
     a.sdata = sdata;
-    var->fn_shared<<<warps, 32, smem, stream>>>(a);
+    var->fn_shared<<<ctas, 32 * per_cta, smem_shared, stream>>>(a);
     if (shared_known) return cudaGetLastError() == cudaSuccess ? 0 : 1;
   } else if (shared_known) {
     return 1;  // the caller checks lane_sdata before asking for this path
   }
-  var->fn<<<warps, 32, 0, stream>>>(a);
+  var->fn<<<ctas, 32 * per_cta, smem_rings, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

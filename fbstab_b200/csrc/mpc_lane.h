@@ -13,6 +13,12 @@ bool MpcLaneSupported(int nx, int nu, int nc);
 // Smallest batch, as a multiple of 16 instances per SM, that the lane kernel
 // solves faster than the CTA kernel (measured per shape).
 double MpcLaneCrossover(int nx, int nu, int nc);
+// Dynamic shared memory of one single-warp CTA (the stage-block ring) and the number of
+// such CTAs an SM holds.
+size_t MpcLaneSmemBytes(int nx, int nu, int nc);
+int MpcLaneWarpsPerSm(int N, int nx, int nu, int nc);
+// Warps launched for `batch` instances on a device with `sms` SMs (and warps per CTA).
+int MpcLaneWarps(int N, int nx, int nu, int nc, int batch, int sms, int* per_cta);
 // Lane-interleaved workspace of one warp (32 instances), in doubles.
 size_t MpcLaneWsDoublesPerWarp(int N, int nx, int nu, int nc);
 // Launches min(max_warps, ceil(batch/32)) single-warp CTAs; `ws` holds
