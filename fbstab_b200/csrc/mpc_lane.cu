@@ -1051,21 +1051,16 @@ struct Lane {
     }
   }
 
-  // ProjectDuals on xi
-  __device__ void project() {
-    for (int i = 0; i <= N; i++) {
-      prefetch(i + PREFETCH_DIST, O_XI + V_V, O_XI + V_Y);
-      double v[NC];
-#pragma unroll
-      for (int k = 0; k < NC; k++) v[k] = ld(i, O_XI + V_V + k);
-#pragma unroll
-      for (int k = 0; k < NC; k++) st(i, O_XI + V_V + k, fmax(v[k], 0.0));
-    }
-  }
-
-  // dx = xi - xk (y-aware), its norm, and FullFeasibility::CheckFeasibility on
-  // it (full_feasibility.cc:25-88).  Returns the status in *feas.
-  __device__ double diff_and_feasibility(double tol, bool check, int* feas) {
+  // End of a proximal subproblem in ONE sweep over the ring (impl:301, 202-216):
+  // ProjectDuals on xi; then, for the lanes with do_diff (not at the Newton cap),
+  // dx = xi - xk (y-aware), its norm, FullFeasibility::CheckFeasibility on it
+  // (full_feasibility.cc:25-88; status in *feas) and xk <- xi.  (The copy is
+  // unconditional for those lanes: after an infeasibility exit the result is dx and
+  // xk is not read again.)
+  __device__ double prox_end(bool do_diff, double tol, bool check, int* feas) {
+    // ring: [ xk | xi ] of the stage, then l of the next stage in xk and xi
+    constexpr int P0 = O_XK, P1 = O_XI + VSZ, PX = P1 - P0;
+    const bool lanes = on;
     double s[3] = {0, 0, 0};
     double mx0 = -INFINITY, mx1 = 0, mx2 = 0, mx3 = 0, mp0 = 0, mp1 = 0, mp2 = 0;
     double sm0 = 0, sm1 = 0;
@@ -1073,26 +1068,43 @@ struct Lane {
 #pragma unroll
     for (int k = 0; k < NS; k++) zp[k] = 0.0;
 #pragma unroll
-    for (int k = 0; k < NX; k++) {
-      lc[k] = ld(0, O_XI + V_L + k) + (-1.0) * ld(0, O_XK + V_L + k);
-      ln[k] = 0.0;
-    }
+    for (int k = 0; k < NX; k++) lc[k] = ln[k] = 0.0;
+    ring_begin();
+    for (int j = 0; j < SLOTS - 1 && j <= N; j++)
+      ring_issue(j, j, P0, P1, j + 1, NX, O_XK + V_L, O_XI + V_L);
     for (int i = 0; i <= N; i++) {
-      prefetch(i + PREFETCH_DIST, 0, O_DX);
       if (check) prefetch(i + PREFETCH_DIST, O_DAT, SBF);
+      __syncwarp();
+      {
+        const int j = i + SLOTS - 1;
+        if (j <= N) ring_issue(j % SLOTS, j, P0, P1, j + 1, NX, O_XK + V_L, O_XI + V_L);
+      }
+      const double* sl = ring_wait(i % SLOTS);
       double xa[VSZ], xb[VSZ], la[NX], lb[NX];
 #pragma unroll
       for (int k = 0; k < VSZ; k++) {
-        xa[k] = ld(i, O_XI + k);
-        xb[k] = ld(i, O_XK + k);
+        xa[k] = sl[(O_XI + k - P0) * 32];
+        xb[k] = sl[(O_XK + k - P0) * 32];
+      }
+      if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < NX; k++) lc[k] = xa[V_L + k] + (-1.0) * xb[V_L + k];
       }
       if (i < N) {
 #pragma unroll
         for (int k = 0; k < NX; k++) {
-          la[k] = ld(i + 1, O_XI + V_L + k);
-          lb[k] = ld(i + 1, O_XK + V_L + k);
+          la[k] = sl[(PX + NX + k) * 32];
+          lb[k] = sl[(PX + k) * 32];
         }
       }
+      // ProjectDuals (full_variable.cc:75)
+      on = lanes;
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        xa[V_V + k] = fmax(xa[V_V + k], 0.0);
+        st(i, O_XI + V_V + k, xa[V_V + k]);
+      }
+      on = lanes && do_diff;
       double z[NS], v[NC], dyv[NC];
 #pragma unroll
       for (int k = 0; k < NS; k++) {
@@ -1199,11 +1211,15 @@ struct Lane {
           mp0 = fmax(mp0, fabs(p));
         }
       }
+      // xk <- xi
+#pragma unroll
+      for (int k = 0; k < VSZ; k++) st(i, O_XK + k, xa[k]);
 #pragma unroll
       for (int k = 0; k < NS; k++) zp[k] = z[k];
 #pragma unroll
       for (int k = 0; k < NX; k++) lc[k] = ln[k];
     }
+    on = lanes;
     *feas = 0;
     if (check) {
       const double w = mx3;
@@ -1215,18 +1231,6 @@ struct Lane {
     }
     const double a = sqrt(s[0]), b = sqrt(s[1]), c2 = sqrt(s[2]);
     return sqrt(a * a + b * b + c2 * c2);
-  }
-
-  // xk <- xi
-  __device__ void copy_xi_to_xk() {
-    for (int i = 0; i <= N; i++) {
-      prefetch(i + PREFETCH_DIST, O_XI, O_DX);
-      double x[VSZ];
-#pragma unroll
-      for (int k = 0; k < VSZ; k++) x[k] = ld(i, O_XI + k);
-#pragma unroll
-      for (int k = 0; k < VSZ; k++) st(i, O_XK + k, x[k]);
-    }
   }
 
   // result block `from` (O_XK / O_XI / O_DX) -> the caller's instance-major arrays
@@ -1503,32 +1507,37 @@ __global__ void __launch_bounds__(32 * kLaneWarpsPerCta, 1) mpc_lane_kernel(cons
       }
     }
     // ---- end of the subproblem, impl:300-216 -------------------------------------
-    if (prox_end) {
-      p.project();
-      if (newton >= o.max_newton_iters) {  // impl:188-199
-        pick_xi = Eo < Ek;
-        phase = PH_FINAL;
-        need_eval = true;
-      } else {
-        int feas = 0;
-        dx_norm = p.diff_and_feasibility(o.infeas_tol, o.check_feasibility != 0, &feas);
-        if (feas != 0) {
-          eflag = (feas == 1)   ? FBSTAB_PRIMAL_INFEASIBLE
-                  : (feas == 2) ? FBSTAB_DUAL_INFEASIBLE
-                                : FBSTAB_PRIMAL_DUAL_INFEASIBLE;
-          which = 2;
-          finish = true;
+    if (__any_sync(0xffffffffu, prox_end)) {
+      const bool at_cap = newton >= o.max_newton_iters;  // impl:188-199
+      int feas = 0;
+      p.on = prox_end;
+      const double dn =
+          p.prox_end(prox_end && !at_cap, o.infeas_tol, o.check_feasibility != 0, &feas);
+      p.on = true;
+      if (prox_end) {
+        if (at_cap) {
+          pick_xi = Eo < Ek;
+          phase = PH_FINAL;
+          need_eval = true;
         } else {
-          p.copy_xi_to_xk();
-          prox++;
-          k++;
-          if (k >= o.max_prox_iters) {
-            eflag = FBSTAB_MAXITERATIONS;
-            which = 0;
+          dx_norm = dn;
+          if (feas != 0) {
+            eflag = (feas == 1)   ? FBSTAB_PRIMAL_INFEASIBLE
+                    : (feas == 2) ? FBSTAB_DUAL_INFEASIBLE
+                                  : FBSTAB_PRIMAL_DUAL_INFEASIBLE;
+            which = 2;
             finish = true;
           } else {
-            phase = PH_TOP;
-            need_eval = true;
+            prox++;
+            k++;
+            if (k >= o.max_prox_iters) {
+              eflag = FBSTAB_MAXITERATIONS;
+              which = 0;
+              finish = true;
+            } else {
+              phase = PH_TOP;
+              need_eval = true;
+            }
           }
         }
       }
