@@ -1057,9 +1057,14 @@ struct Lane {
   // (full_feasibility.cc:25-88; status in *feas) and xk <- xi.  (The copy is
   // unconditional for those lanes: after an infeasibility exit the result is dx and
   // xk is not read again.)
-  __device__ double prox_end(bool do_diff, double tol, bool check, int* feas) {
-    // ring: [ xk | xi ] of the stage, then l of the next stage in xk and xi
-    constexpr int P0 = O_XK, P1 = O_XI + VSZ, PX = P1 - P0;
+  // (with_commit: the lane's accepted step xi <- xi + t dx is applied in the same sweep,
+  // with the fused multiply-adds of commit(); any_commit: some lane of the warp does.)
+  __device__ double prox_end(bool do_diff, bool with_commit, double t, bool any_commit,
+                             double tol, bool check, int* feas) {
+    // ring: [ xk | xi ] of the stage (with a commit in the warp: | dx), then l of the
+    // next stage in xk, xi (and dx)
+    constexpr int P0 = O_XK;
+    const int P1 = any_commit ? O_RI : O_XI + VSZ, PX = P1 - P0;
     const bool lanes = on;
     double s[3] = {0, 0, 0};
     double mx0 = -INFINITY, mx1 = 0, mx2 = 0, mx3 = 0, mp0 = 0, mp1 = 0, mp2 = 0;
@@ -1069,15 +1074,16 @@ struct Lane {
     for (int k = 0; k < NS; k++) zp[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < NX; k++) lc[k] = ln[k] = 0.0;
+    const int xdl = any_commit ? O_DX + V_L : -1;
     ring_begin();
     for (int j = 0; j < SLOTS - 1 && j <= N; j++)
-      ring_issue(j, j, P0, P1, j + 1, NX, O_XK + V_L, O_XI + V_L);
+      ring_issue(j, j, P0, P1, j + 1, NX, O_XK + V_L, O_XI + V_L, xdl);
     for (int i = 0; i <= N; i++) {
       if (check) prefetch(i + PREFETCH_DIST, O_DAT, SBF);
       __syncwarp();
       {
         const int j = i + SLOTS - 1;
-        if (j <= N) ring_issue(j % SLOTS, j, P0, P1, j + 1, NX, O_XK + V_L, O_XI + V_L);
+        if (j <= N) ring_issue(j % SLOTS, j, P0, P1, j + 1, NX, O_XK + V_L, O_XI + V_L, xdl);
       }
       const double* sl = ring_wait(i % SLOTS);
       double xa[VSZ], xb[VSZ], la[NX], lb[NX];
@@ -1086,16 +1092,43 @@ struct Lane {
         xa[k] = sl[(O_XI + k - P0) * 32];
         xb[k] = sl[(O_XK + k - P0) * 32];
       }
-      if (i == 0) {
-#pragma unroll
-        for (int k = 0; k < NX; k++) lc[k] = xa[V_L + k] + (-1.0) * xb[V_L + k];
-      }
       if (i < N) {
 #pragma unroll
         for (int k = 0; k < NX; k++) {
           la[k] = sl[(PX + NX + k) * 32];
           lb[k] = sl[(PX + k) * 32];
         }
+      }
+      if (any_commit) {
+        // xi <- xi + t dx (commit(): y-aware, full_variable.cc:55-65)
+        on = lanes && with_commit;
+#pragma unroll
+        for (int k = 0; k < V_Y; k++) {
+          const double c2 = fma(t, sl[(O_DX + k - P0) * 32], xa[k]);
+          xa[k] = with_commit ? c2 : xa[k];
+        }
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+          const double y1 = fma(t, sl[(O_DX + V_Y + k - P0) * 32], xa[V_Y + k]);
+          const double y2 = fma(-t, -dat(i, D_d)[k * DS], y1);
+          xa[V_Y + k] = with_commit ? y2 : xa[V_Y + k];
+        }
+        if (i < N) {
+#pragma unroll
+          for (int k = 0; k < NX; k++) {
+            const double c2 = fma(t, sl[(PX + 2 * NX + k) * 32], la[k]);
+            la[k] = with_commit ? c2 : la[k];
+          }
+        }
+        // (v is stored below, after the projection)
+#pragma unroll
+        for (int k = 0; k < V_V; k++) st(i, O_XI + k, xa[k]);
+#pragma unroll
+        for (int k = 0; k < NC; k++) st(i, O_XI + V_Y + k, xa[V_Y + k]);
+      }
+      if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < NX; k++) lc[k] = xa[V_L + k] + (-1.0) * xb[V_L + k];
       }
       // ProjectDuals (full_variable.cc:75)
       on = lanes;
@@ -1475,7 +1508,8 @@ __global__ void __launch_bounds__(32 * kLaneWarpsPerCta, 1) mpc_lane_kernel(cons
     }
     // ---- commit the accepted (or forced) step: xi <- xi + t dx ---------------
     // (lanes that go on to a Newton step commit inside the factor sweep)
-    if (do_commit && !do_newton) p.commit(tstep);
+    // (and lanes whose subproblem ends commit inside the prox_end sweep)
+    if (do_commit && !do_newton && !prox_end) p.commit(tstep);
     // ---- Newton step ------------------------------------------------------------
     if (__any_sync(0xffffffffu, do_newton)) {
       const bool wc = do_newton && do_commit;
@@ -1510,9 +1544,10 @@ __global__ void __launch_bounds__(32 * kLaneWarpsPerCta, 1) mpc_lane_kernel(cons
     if (__any_sync(0xffffffffu, prox_end)) {
       const bool at_cap = newton >= o.max_newton_iters;  // impl:188-199
       int feas = 0;
+      const bool pc = prox_end && do_commit;
       p.on = prox_end;
-      const double dn =
-          p.prox_end(prox_end && !at_cap, o.infeas_tol, o.check_feasibility != 0, &feas);
+      const double dn = p.prox_end(prox_end && !at_cap, pc, tstep, __any_sync(0xffffffffu, pc),
+                                   o.infeas_tol, o.check_feasibility != 0, &feas);
       p.on = true;
       if (prox_end) {
         if (at_cap) {
