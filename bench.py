@@ -469,6 +469,10 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
                     lo, hi = sharding.shard_range(total, world, r)
                     rf, rc = lo, hi - lo
                 n = min(rc, 256 if wl.nz < 2000 else 32)
+                # the lane kernel serves large batches only (a small prefix would take the
+                # CTA kernel, whose factors differ by rounding): re-solve the whole range
+                if "mpc-lane" in solver.path:
+                    n = rc
                 if n == 0:
                     continue
                 dd = wl.generate(fb.problems, n, rf, threads)
