@@ -4,5 +4,5 @@ libfbstab_b200.so behind the C-ABI in include/fbstab_b200.h; this package is
 the thin host-side mirror of the reference's solver interface."""
 from . import capi, problems, sharding  # noqa: F401
 from .capi import EXIT_FLAGS, OUT_DTYPE, FbstabError, Options  # noqa: F401
-from .solver import FBstabDense, FBstabMpc  # noqa: F401
+from .solver import FBstabDense, FBstabMpc, FBstabSparse  # noqa: F401
 from .closed_loop import ClosedLoopMpc  # noqa: F401

@@ -32,6 +32,10 @@ SYMBOLS = [
     "fbstab_mpc_batch_solve", "fbstab_mpc_batch_last_launches",
     "fbstab_mpc_batch_path", "fbstab_mpc_batch_component",
     "fbstab_mpc_batch_solve_shared", "fbstab_mpc_batch_solve_lti",
+    "fbstab_sparse_batch_create", "fbstab_sparse_batch_destroy",
+    "fbstab_sparse_batch_set_options", "fbstab_sparse_batch_get_options",
+    "fbstab_sparse_batch_solve", "fbstab_sparse_batch_last_launches",
+    "fbstab_sparse_batch_path", "fbstab_sparse_batch_analysis",
     "fbstab_mpc_closed_loop_create", "fbstab_mpc_closed_loop_destroy",
     "fbstab_mpc_closed_loop_set_options", "fbstab_mpc_closed_loop_reset",
     "fbstab_mpc_closed_loop_step", "fbstab_mpc_closed_loop_run",
@@ -118,6 +122,18 @@ def lib():
         L.fbstab_mpc_batch_component.argtypes = (
             [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 12 +
             [C.POINTER(ComponentIO), C.c_void_p])
+        ip = C.POINTER(C.c_int)
+        L.fbstab_sparse_batch_path.restype = C.c_char_p
+        L.fbstab_sparse_batch_path.argtypes = [C.c_void_p]
+        L.fbstab_sparse_batch_create.argtypes = (
+            [C.c_int] * 3 + [C.c_void_p] * 7 + [C.c_int, C.c_int, C.POINTER(C.c_void_p)])
+        L.fbstab_sparse_batch_destroy.argtypes = [C.c_void_p]
+        L.fbstab_sparse_batch_last_launches.argtypes = [C.c_void_p]
+        L.fbstab_sparse_batch_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+        L.fbstab_sparse_batch_get_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+        L.fbstab_sparse_batch_solve.argtypes = (
+            [C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_void_p, C.c_void_p])
+        L.fbstab_sparse_batch_analysis.argtypes = [C.c_void_p, ip, ip, ip, C.c_void_p]
         L.fbstab_ocp_dims.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 3
         L.fbstab_ocp_generate.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 12
         L.fbstab_ocp_generate_batch.argtypes = (

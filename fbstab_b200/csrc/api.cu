@@ -25,6 +25,7 @@
 #include "fbstab_b200.h"
 #include "mpc_lane.h"
 #include "mpc_riccati.h"
+#include "sparse_lane.h"
 
 namespace {
 
@@ -616,6 +617,14 @@ struct fbstab_mpc_batch : HandleBase {
   // fbstab_mpc_batch_solve_lti: pinned host copy of the horizon (one stage replicated)
   double* lti_host = nullptr;
   size_t lti_cap = 0;
+};
+
+struct fbstab_sparse_batch : HandleBase {
+  fbs::SparsePattern pat;  // host copy of the symbolic analysis
+  fbs::SparseDev dev;      // the same tables on the device
+  int* tables = nullptr;   // one allocation behind dev's pointers
+  int warps = 0;
+  char name[200];
 };
 
 namespace {
@@ -1335,4 +1344,165 @@ int fbstab_mpc_batch_component(fbstab_mpc_batch* h, int comp, int batch,
   return st.Finish();
 }
 
+/* ---- sparse QPs with a common pattern (FBstabSparse) ------------------------------- */
+int fbstab_sparse_batch_create(int nz, int nl, int nv, const int* Hp, const int* Hi,
+                               const int* Gp, const int* Gi, const int* Ap, const int* Ai,
+                               const int* perm, int max_batch, int device,
+                               fbstab_sparse_batch** handle) {
+  if (!handle) return Fail(FBSTAB_ERR_INVALID, "null handle pointer");
+  *handle = nullptr;
+  if (max_batch < 1) return Fail(FBSTAB_ERR_INVALID, "max_batch must be >= 1");
+  auto* h = new fbstab_sparse_batch();
+  if (!fbs::SparseAnalyze(nz, nl, nv, Hp, Hi, Gp, Gi, Ap, Ai, perm, &h->pat)) {
+    const std::string msg = "sparse pattern: " + h->pat.error;
+    delete h;
+    return Fail(FBSTAB_ERR_INVALID, msg);
+  }
+  h->nz = nz;
+  h->nl = nl;
+  h->nv = nv;
+  int rc = InitDevice(h, device, max_batch);
+  auto fail = [&](int code) {
+    const std::string keep = g_last_error;
+    if (h->tables) cudaFree(h->tables);
+    h->FreeAll();
+    delete h;
+    g_last_error = keep;
+    return code;
+  };
+  if (rc) return fail(rc);
+  const fbs::SparsePattern& p = h->pat;
+  // all integer tables in one device allocation
+  const std::vector<int>* tabs[] = {&p.Hr_ptr, &p.Hr_col, &p.Hr_val, &p.Gp,  &p.Gi,    &p.Gr_ptr,
+                                    &p.Gr_col, &p.Gr_val, &p.Ap,     &p.Ai,  &p.Ar_ptr, &p.Ar_col,
+                                    &p.Ar_val, &p.iperm,  &p.Kp,     &p.Ki,  &p.Kkind,  &p.Kidx,
+                                    &p.Krow,   &p.Lp,     &p.Li,     &p.Sp,  &p.Sc,     &p.St};
+  constexpr int kTabs = sizeof(tabs) / sizeof(tabs[0]);
+  size_t off[kTabs + 1];
+  off[0] = 0;
+  for (int k = 0; k < kTabs; k++) off[k + 1] = off[k] + ((tabs[k]->size() + 3) & ~(size_t)3) + 4;
+  if (cudaMalloc(&h->tables, off[kTabs] * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    Fail(FBSTAB_ERR_ALLOC, "cudaMalloc of the sparse pattern tables failed");
+    return fail(FBSTAB_ERR_ALLOC);
+  }
+  for (int k = 0; k < kTabs; k++)
+    if (!tabs[k]->empty() &&
+        cudaMemcpy(h->tables + off[k], tabs[k]->data(), tabs[k]->size() * sizeof(int),
+                   cudaMemcpyHostToDevice) != cudaSuccess) {
+      Fail(FBSTAB_ERR_CUDA, "copy of the sparse pattern tables failed");
+      return fail(FBSTAB_ERR_CUDA);
+    }
+  fbs::SparseDev& d = h->dev;
+  d.nz = nz; d.nl = nl; d.nv = nv; d.n = p.n;
+  d.nnzH = p.nnzH; d.nnzG = p.nnzG; d.nnzA = p.nnzA; d.nnzK = p.nnzK; d.nnzL = p.nnzL;
+  const int** dst[] = {&d.Hr_ptr, &d.Hr_col, &d.Hr_val, &d.Gp,  &d.Gi,    &d.Gr_ptr,
+                       &d.Gr_col, &d.Gr_val, &d.Ap,     &d.Ai,  &d.Ar_ptr, &d.Ar_col,
+                       &d.Ar_val, &d.iperm,  &d.Kp,     &d.Ki,  &d.Kkind,  &d.Kidx,
+                       &d.Krow,   &d.Lp,     &d.Li,     &d.Sp,  &d.Sc,     &d.St};
+  for (int k = 0; k < kTabs; k++) *dst[k] = h->tables + off[k];
+  // workspace: at most ~6 GiB
+  const size_t per_warp = fbs::SparseLaneWsDoublesPerWarp(d) * sizeof(double);
+  int warps = fbs::SparseLaneWarps(max_batch, h->sm_count);
+  warps = (int)std::max<size_t>(1, std::min<size_t>(warps, ((size_t)6 << 30) / std::max<size_t>(per_warp, 1)));
+  if (cudaMalloc(&h->ws, (size_t)warps * per_warp) != cudaSuccess) {
+    cudaGetLastError();
+    Fail(FBSTAB_ERR_ALLOC, "cudaMalloc of the sparse solver workspace failed");
+    return fail(FBSTAB_ERR_ALLOC);
+  }
+  h->warps = warps;
+  snprintf(h->name, sizeof(h->name),
+           "sparse-lane (lane per instance, common pattern: n=%d nnz(K)=%d nnz(L)=%d, "
+           "%d warps, %.0f MB interleaved workspace)",
+           p.n, p.nnzK, p.nnzL, warps, warps * per_warp / 1e6);
+  h->path = h->name;
+  *handle = h;
+  return FBSTAB_OK;
+}
+
+int fbstab_sparse_batch_destroy(fbstab_sparse_batch* h) {
+  if (!h) return FBSTAB_OK;
+  cudaSetDevice(h->device);
+  if (h->tables) cudaFree(h->tables);
+  h->FreeAll();
+  delete h;
+  return FBSTAB_OK;
+}
+int fbstab_sparse_batch_set_options(fbstab_sparse_batch* h, const fbstab_options* o) {
+  return SetOptions(h, o);
+}
+int fbstab_sparse_batch_get_options(const fbstab_sparse_batch* h, fbstab_options* o) {
+  if (!h || !o) return Fail(FBSTAB_ERR_INVALID, "null argument");
+  *o = h->opts;
+  return FBSTAB_OK;
+}
+int fbstab_sparse_batch_last_launches(const fbstab_sparse_batch* h) {
+  return h ? h->last_launches : 0;
+}
+const char* fbstab_sparse_batch_path(const fbstab_sparse_batch* h) { return h ? h->path : ""; }
+int fbstab_sparse_batch_analysis(const fbstab_sparse_batch* h, int* n, int* nnzK, int* nnzL,
+                                 int* perm) {
+  if (!h) return Fail(FBSTAB_ERR_INVALID, "null handle");
+  if (n) *n = h->pat.n;
+  if (nnzK) *nnzK = h->pat.nnzK;
+  if (nnzL) *nnzL = h->pat.nnzL;
+  if (perm) std::copy(h->pat.perm.begin(), h->pat.perm.end(), perm);
+  return FBSTAB_OK;
+}
+
+int fbstab_sparse_batch_solve(fbstab_sparse_batch* h, int batch, const double* Hx,
+                              const double* f, const double* Gx, const double* hh,
+                              const double* Ax, const double* b, double* z, double* l,
+                              double* v, double* y, fbstab_out* out, void* stream) {
+  if (!h) return Fail(FBSTAB_ERR_INVALID, "null handle");
+  if (batch < 0 || batch > h->max_batch)
+    return Fail(FBSTAB_ERR_INVALID, "batch exceeds the handle's max_batch");
+  if (!out) return Fail(FBSTAB_ERR_INVALID, "null out pointer");
+  if (h->opts.refine_steps != 0 || h->opts.regularize_retries != 0)
+    return Fail(FBSTAB_ERR_INVALID, "refine_steps / regularize_retries: not on the sparse path");
+  h->last_launches = 0;
+  if (batch == 0) return FBSTAB_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const auto t0 = std::chrono::steady_clock::now();
+  Stager st;
+  st.stream = (cudaStream_t)stream;
+  st.device = h->device;
+  st.defer = true;
+  st.batch = batch;
+  const size_t nz = h->nz, nl = h->nl, nv = h->nv, B = batch, D = sizeof(double);
+  const size_t nH = h->pat.nnzH, nG = h->pat.nnzG, nA = h->pat.nnzA;
+  const double *dH, *df, *dG, *dh, *dA, *db;
+  double *dz, *dl, *dv, *dy;
+  fbstab_out* dout;
+  int rc;
+  if ((rc = st.In(&h->in[0], Hx, B * nH * D, (const void**)&dH))) return rc;
+  if ((rc = st.In(&h->in[1], f, B * nz * D, (const void**)&df))) return rc;
+  if ((rc = st.In(&h->in[2], Gx, B * nG * D, (const void**)&dG))) return rc;
+  if ((rc = st.In(&h->in[3], hh, B * nl * D, (const void**)&dh))) return rc;
+  if ((rc = st.In(&h->in[4], Ax, B * nA * D, (const void**)&dA))) return rc;
+  if ((rc = st.In(&h->in[5], b, B * nv * D, (const void**)&db))) return rc;
+  if ((rc = st.InOut(&h->io[0], z, B * nz * D, true, (void**)&dz))) return rc;
+  if ((rc = st.InOut(&h->io[1], l, B * nl * D, true, (void**)&dl))) return rc;
+  if ((rc = st.InOut(&h->io[2], v, B * nv * D, true, (void**)&dv))) return rc;
+  if ((rc = st.InOut(&h->io[3], y, B * nv * D, false, (void**)&dy))) return rc;
+  if ((rc = st.InOut(&h->out_buf, out, B * sizeof(fbstab_out), false, (void**)&dout))) return rc;
+  auto launch = [&](int lo, int n) -> int {
+    const size_t o = (size_t)lo;
+    if (fbs::SparseLaneLaunch(h->dev, n, h->warps, dH + o * nH, df + o * nz, dG + o * nG,
+                              dh + o * nl, dA + o * nA, db + o * nv, dz + o * nz, dl + o * nl,
+                              dv + o * nv, dy + o * nv, dout + lo, h->opts, h->ws, h->counter,
+                              st.stream))
+      return Fail(FBSTAB_ERR_CUDA, "sparse kernel launch failed");
+    return FBSTAB_OK;
+  };
+  if ((rc = RunPipelined(h, &st, batch, 8 * 32 * h->warps, launch))) return rc;
+  if (st.any_host && !IsDevicePtr(out)) {
+    const double sec =
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    StampSolveTime(out, batch, sec);
+  }
+  return FBSTAB_OK;
+}
+
 }  // extern "C"
+

@@ -1,0 +1,32 @@
+// sparse_lane.h -- host interface of the lane-per-instance sparse QP path (sparse_lane.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "fbstab_b200.h"
+#include "sparse_symbolic.h"
+
+namespace fbs {
+
+// The integer tables of sparse_symbolic.h in device memory (one allocation).
+struct SparseDev {
+  int nz, nl, nv, n, nnzH, nnzG, nnzA, nnzK, nnzL;
+  const int *Hr_ptr, *Hr_col, *Hr_val;
+  const int *Gp, *Gi, *Gr_ptr, *Gr_col, *Gr_val;
+  const int *Ap, *Ai, *Ar_ptr, *Ar_col, *Ar_val;
+  const int *iperm, *Kp, *Ki, *Kkind, *Kidx, *Krow;
+  const int *Lp, *Li, *Sp, *Sc, *St;
+};
+
+// Lane-interleaved workspace of one warp (32 instances), in doubles.
+size_t SparseLaneWsDoublesPerWarp(const SparseDev& d);
+// Warps launched for `batch` instances on a device with `sms` SMs.
+int SparseLaneWarps(int batch, int sms);
+// One launch solves `batch` instances (instance-major value arrays); `ws` holds
+// warps * SparseLaneWsDoublesPerWarp doubles.  Returns 0 on success.
+int SparseLaneLaunch(const SparseDev& d, int batch, int warps, const double* Hx, const double* f,
+                     const double* Gx, const double* h, const double* Ax, const double* b,
+                     double* z, double* l, double* v, double* y, fbstab_out* out,
+                     const fbstab_options& opts, double* ws, int* counter, cudaStream_t stream);
+
+}  // namespace fbs

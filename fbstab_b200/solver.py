@@ -249,3 +249,54 @@ class FBstabMpc(_Base):
                        for t in x0]
         out, y = self.solve_batch(data, z, l, v)
         return out[0], (z, l, v, y)
+
+
+class FBstabSparse(_Base):
+    """min 1/2 z'Hz + f'z  s.t. Gz = h, Az <= b with SPARSE H, G, A; every instance of a
+    batch shares one sparsity pattern (the reference plans this solver: ROADMAP.md:10,
+    over the LDL' wrapper tools/qdldl/qdldl_wrapper.h:19-84).
+
+    pattern = (Hp, Hi, Gp, Gi, Ap, Ai): H (nz x nz) by its upper triangle, G (nl x nz) and
+    A (nv x nz) in compressed-column form, row indices increasing within a column.
+    The constructor runs the symbolic analysis (elimination order, pattern of L)."""
+    _prefix = "sparse"
+    _fields = ("Hx", "f", "Gx", "h", "Ax", "b")
+
+    def __init__(self, nz, nl, nv, pattern, max_batch=1, device=0, perm=None):
+        super().__init__()
+        if nz <= 0 or nv <= 0 or nl < 0:  # as FBstabDense, fbstab_dense.cc:19-23
+            raise RuntimeError("In FBstabSparse::FBstabSparse: nz and nv must be "
+                               "positive, nl nonnegative")
+        ia = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1))
+        self.pattern = tuple(ia(a) for a in pattern)
+        Hp, Hi, Gp, Gi, Ap, Ai = self.pattern
+        if Hp.size != nz + 1 or Ap.size != nz + 1 or (nl > 0 and Gp.size != nz + 1):
+            raise RuntimeError("In FBstabSparse::FBstabSparse: column pointer arrays must "
+                               "have nz + 1 entries")
+        if Hi.size != Hp[-1] or Ai.size != Ap[-1] or (nl > 0 and Gi.size != Gp[-1]):
+            raise RuntimeError("In FBstabSparse::FBstabSparse: index arrays do not match "
+                               "the column pointers")
+        self.nz, self.nl, self.nv, self.max_batch = nz, nl, nv, max_batch
+        self.device = device
+        self.field_sizes = {"Hx": int(Hp[-1]), "f": nz, "Gx": int(Gp[-1]) if nl > 0 else 0,
+                            "h": nl, "Ax": int(Ap[-1]), "b": nv}
+        pm = ia(perm) if perm is not None else None
+        if pm is not None and pm.size != nz + nl + nv:
+            raise RuntimeError("In FBstabSparse::FBstabSparse: perm must have nz + nl + nv entries")
+        capi.check(capi.lib().fbstab_sparse_batch_create(
+            nz, nl, nv, capi.ptr(Hp), capi.ptr(Hi), capi.ptr(Gp) if nl > 0 else None,
+            capi.ptr(Gi) if nl > 0 and Gi.size else None, capi.ptr(Ap), capi.ptr(Ai),
+            capi.ptr(pm), max_batch, device, C.byref(self._h)))
+
+    def analysis(self):
+        """(n, nnz(K), nnz(L), perm) of the symbolic analysis; perm[new] = old over [z; l; w]."""
+        n, k, l = C.c_int(), C.c_int(), C.c_int()
+        capi.check(capi.lib().fbstab_sparse_batch_analysis(
+            self._h, C.byref(n), C.byref(k), C.byref(l), None))
+        perm = np.zeros(n.value, dtype=np.int32)
+        capi.check(capi.lib().fbstab_sparse_batch_analysis(
+            self._h, None, None, None, capi.ptr(perm)))
+        return n.value, k.value, l.value, perm
+
+    def component(self, *a, **k):
+        raise RuntimeError("FBstabSparse has no component-stage entry")

@@ -224,6 +224,43 @@ int fbstab_mpc_batch_solve_lti(fbstab_mpc_batch* handle, int batch, const double
                                double* l, double* v, double* y, fbstab_out* out,
                                void* stream);
 
+/* ---- sparse QPs with a common sparsity pattern (FBstabSparse) --------------
+ * The reference plans "general sparse matrix components" (ROADMAP.md:10,
+ * README.md:47) on an LDL' of the quasi-definite Newton matrix behind the
+ * interface its tools/qdldl/qdldl_wrapper.h:19-84 sketches:
+ *   fbstab_sparse_batch_create  <- QdldlWrapper::QdldlWrapper(n, Ap, Ai): the
+ *                                  symbolic analysis (ordering, elimination tree,
+ *                                  pattern of L), once per pattern, on the host;
+ *   fbstab_sparse_batch_solve   <- FBstabAlgorithm::Solve over sparse data, with
+ *                                  QdldlWrapper::Factor / ::Solve per Newton step
+ *                                  on the device (one lane per instance).
+ * Every instance of a batch has the SAME pattern: H (nz x nz) as its upper
+ * triangle in compressed-column form (the storage qdldl_wrapper.h:12-14 names),
+ * G (nl x nz) and A (nv x nz) in compressed-column form, row indices strictly
+ * increasing within a column, 0-based int32.  Values are instance-major:
+ * Hx[batch][nnz(H)], Gx[batch][nnz(G)], Ax[batch][nnz(A)]; f, h, b, z, l, v, y
+ * as for the dense entry.  perm (nz+nl+nv entries, perm[new] = old over the
+ * variables [z; l; w]) overrides the built-in minimum-degree order; NULL = built-in. */
+typedef struct fbstab_sparse_batch fbstab_sparse_batch;
+
+int fbstab_sparse_batch_create(int nz, int nl, int nv, const int* Hp, const int* Hi,
+                               const int* Gp, const int* Gi, const int* Ap, const int* Ai,
+                               const int* perm, int max_batch, int device,
+                               fbstab_sparse_batch** handle);
+int fbstab_sparse_batch_destroy(fbstab_sparse_batch* handle);
+int fbstab_sparse_batch_set_options(fbstab_sparse_batch* handle, const fbstab_options* o);
+int fbstab_sparse_batch_get_options(const fbstab_sparse_batch* handle, fbstab_options* o);
+int fbstab_sparse_batch_solve(fbstab_sparse_batch* handle, int batch, const double* Hx,
+                              const double* f, const double* Gx, const double* h,
+                              const double* Ax, const double* b, double* z, double* l,
+                              double* v, double* y, fbstab_out* out, void* stream);
+int fbstab_sparse_batch_last_launches(const fbstab_sparse_batch* handle);
+const char* fbstab_sparse_batch_path(const fbstab_sparse_batch* handle);
+/* Result of the symbolic analysis: size of K, its stored entries, entries of L, and
+ * (perm != NULL) the elimination order in use.  Any pointer may be NULL. */
+int fbstab_sparse_batch_analysis(const fbstab_sparse_batch* handle, int* n, int* nnzK,
+                                 int* nnzL, int* perm);
+
 /* ---- receding-horizon (closed-loop) MPC ----------------------------------
  * What OcpGenerator::GetSimulationInputs exists for (fbstab/test/
  * ocp_generator.h:31-38,69; ocp_generator.cc:56-71) and what the reference's

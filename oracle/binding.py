@@ -117,6 +117,13 @@ def lib():
         L.oracle_mpc_solve_batch.argtypes = (
             [C.c_int] * 5 + [_dp] * 16 + [C.POINTER(Options), C.c_void_p,
                                           C.c_int])
+        _ip = C.POINTER(C.c_int)
+        L.oracle_sparse_create.restype = C.c_void_p
+        L.oracle_sparse_create.argtypes = [C.c_int] * 3 + [_ip, _ip, _dp, _dp] * 3 + [_ip]
+        L.oracle_qdldl_solve.argtypes = [C.c_int, _ip, _ip, _dp, _dp]
+        L.oracle_sparse_solve_batch.argtypes = (
+            [C.c_int] * 4 + [_ip, _ip, _dp, _dp] * 3 + [_ip] + [_dp] * 4 +
+            [C.POINTER(Options), C.c_void_p, C.c_int])
         _lib = L
     return _lib
 
@@ -126,6 +133,13 @@ def _p(a):
         return None
     assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], (a.dtype, a.flags)
     return a.ctypes.data_as(_dp)
+
+
+def _ip(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"], (a.dtype, a.flags)
+    return a.ctypes.data_as(C.POINTER(C.c_int))
 
 
 def _f(a):
@@ -192,6 +206,22 @@ class Problem:
             raise ValueError("oracle_mpc_create rejected the sizes")
         return Problem(hd, arrs, (N + 1) * (nx + nu), (N + 1) * nx,
                        (N + 1) * nc)
+
+    @staticmethod
+    def sparse(nz, nl, nv, Hp, Hi, Hx, f, Gp, Gi, Gx, h, Ap, Ai, Ax, b, perm=None):
+        """H by its upper triangle, G and A: compressed-column int32 patterns + values."""
+        ia = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1))
+        fa = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+        ints = [ia(a) for a in (Hp, Hi, Gp, Gi, Ap, Ai)]
+        vals = [fa(a) for a in (Hx, f, Gx, h, Ax, b)]
+        pm = ia(perm) if perm is not None else None
+        hd = lib().oracle_sparse_create(
+            nz, nl, nv, _ip(ints[0]), _ip(ints[1]), _p(vals[0]), _p(vals[1]), _ip(ints[2]),
+            _ip(ints[3]), _p(vals[2]), _p(vals[3]), _ip(ints[4]), _ip(ints[5]), _p(vals[4]),
+            _p(vals[5]), _ip(pm))
+        if not hd:
+            raise ValueError("oracle_sparse_create rejected the sizes")
+        return Problem(hd, (ints, vals, pm), nz, nl, nv)
 
     # -- data ops ---------------------------------------------------------
     def forcing_norm(self):
@@ -315,4 +345,35 @@ def mpc_solve_batch(N, nx, nu, nc, seqs, opts=None, x0=None, nthreads=1, fma=Fal
     (fma_lib() if fma else lib()).oracle_mpc_solve_batch(
         N, nx, nu, nc, batch, *[_p(a) for a in seqs], _p(z), _p(l), _p(v),
         _p(y), C.byref(opts), out.ctypes.data, nthreads)
+    return out, z, l, v, y
+
+
+def qdldl_solve(n, Ap, Ai, Ax, b):
+    """QdldlWrapper: factor the upper-triangular CSC matrix, solve A x = b."""
+    Ap, Ai = [np.ascontiguousarray(np.asarray(a, dtype=np.int32)) for a in (Ap, Ai)]
+    Ax = np.ascontiguousarray(np.asarray(Ax, dtype=np.float64))
+    x = np.ascontiguousarray(np.asarray(b, dtype=np.float64)).copy()
+    rc = lib().oracle_qdldl_solve(n, _ip(Ap), _ip(Ai), _p(Ax), _p(x))
+    return rc, x
+
+
+def sparse_solve_batch(nz, nl, nv, pattern, vals, perm=None, opts=None, x0=None, nthreads=1):
+    """pattern = (Hp,Hi,Gp,Gi,Ap,Ai) int32; vals = (Hx,f,Gx,h,Ax,b) instance-major."""
+    if opts is None:
+        opts = default_options()
+    Hp, Hi, Gp, Gi, Ap, Ai = [np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1))
+                              for a in pattern]
+    Hx, f, Gx, h, Ax, b = vals
+    batch = f.size // nz
+    if x0 is None:
+        z, l, v = np.zeros(batch * nz), np.zeros(batch * nl), np.zeros(batch * nv)
+    else:
+        z, l, v = [np.ascontiguousarray(t, dtype=np.float64).reshape(-1).copy() for t in x0]
+    y = np.zeros(batch * nv)
+    out = np.zeros(batch, dtype=OUT_DTYPE)
+    pm = np.ascontiguousarray(np.asarray(perm, dtype=np.int32)) if perm is not None else None
+    lib().oracle_sparse_solve_batch(
+        nz, nl, nv, batch, _ip(Hp), _ip(Hi), _p(Hx), _p(f), _ip(Gp), _ip(Gi), _p(Gx), _p(h),
+        _ip(Ap), _ip(Ai), _p(Ax), _p(b), _ip(pm), _p(z), _p(l), _p(v), _p(y), C.byref(opts),
+        out.ctypes.data, nthreads)
     return out, z, l, v, y

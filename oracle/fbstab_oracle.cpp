@@ -31,6 +31,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -1444,17 +1445,365 @@ struct Algorithm {
 }  // namespace
 
 // ===========================================================================
+// Sparse QPs (FBstabSparse).  The reference has no sparse solver yet: it plans
+// "general sparse matrix components" (ROADMAP.md:10, README.md:47) on the LDL'
+// wrapper tools/qdldl/qdldl_wrapper.h:19-84, whose upstream source (QDLDL,
+// github.com/oxfordcontrol/qdldl, v0.1.x; tools/qdldl/BUILD.bazel:15,19 expects
+// it under tools/qdldl/qdldl/) is NOT in the reference tree.  QDLDL_etree,
+// QDLDL_factor and QDLDL_solve are therefore restated here from the published
+// algorithm and pinned by the wrapper's own test
+// (tools/qdldl/test/qdldl_test.cc:33-60: the upstream example, ||Ax - b|| <= 1e-12).
+// The data concept is abstract_components.h:24-62 over compressed-column
+// matrices; the Newton system is the quasi-definite
+//   [ H + sigma I   G'       (Gamma^1/2 A)' ]
+//   [ G            -sigma I   0             ]   (order [z; l; w], w = Gamma^1/2 A dz)
+//   [ Gamma^1/2 A   0        -I             ]
+// -- the reduction of dense_cholesky_solver.cc:32-127 with A' Gamma A unformed.
+// ===========================================================================
+static const int QDLDL_UNKNOWN = -1;
+
+// Elimination tree and column counts of L for an upper-triangular CSC matrix.
+// Returns nnz(L), -1 if an entry lies below the diagonal or a column is empty.
+int QdldlEtree(int n, const int* Ap, const int* Ai, int* work, int* Lnz, int* etree) {
+  for (int i = 0; i < n; i++) {
+    work[i] = 0;
+    Lnz[i] = 0;
+    etree[i] = QDLDL_UNKNOWN;
+    if (Ap[i] == Ap[i + 1]) return -1;
+  }
+  for (int j = 0; j < n; j++) {
+    work[j] = j;
+    for (int p = Ap[j]; p < Ap[j + 1]; p++) {
+      int i = Ai[p];
+      if (i > j) return -1;
+      while (work[i] != j) {
+        if (etree[i] == QDLDL_UNKNOWN) etree[i] = j;
+        Lnz[i]++;
+        work[i] = j;
+        i = etree[i];
+      }
+    }
+  }
+  int sum = 0;
+  for (int i = 0; i < n; i++) sum += Lnz[i];
+  return sum;
+}
+
+// Up-looking LDL' (L unit lower triangular, strictly lower part stored by columns).
+// Returns the number of positive entries of D, -1 on a zero pivot.
+int QdldlFactor(int n, const int* Ap, const int* Ai, const double* Ax, int* Lp, int* Li,
+                double* Lx, double* D, double* Dinv, const int* Lnz, const int* etree,
+                unsigned char* bwork, int* iwork, double* fwork) {
+  int positive = 0;
+  unsigned char* yMarkers = bwork;
+  int* yIdx = iwork;
+  int* elimBuffer = iwork + n;
+  int* LNextSpaceInCol = iwork + 2 * n;
+  double* yVals = fwork;
+  Lp[0] = 0;
+  for (int i = 0; i < n; i++) {
+    Lp[i + 1] = Lp[i] + Lnz[i];
+    yMarkers[i] = 0;
+    yVals[i] = 0.0;
+    D[i] = 0.0;
+    LNextSpaceInCol[i] = Lp[i];
+  }
+  D[0] = Ax[0];
+  if (D[0] == 0.0) return -1;
+  if (D[0] > 0.0) positive++;
+  Dinv[0] = 1 / D[0];
+  for (int k = 1; k < n; k++) {
+    int nnzY = 0;
+    for (int i = Ap[k]; i < Ap[k + 1]; i++) {
+      const int bidx = Ai[i];
+      if (bidx == k) {
+        D[k] = Ax[i];
+        continue;
+      }
+      yVals[bidx] = Ax[i];
+      int nextIdx = bidx;
+      if (yMarkers[nextIdx] == 0) {
+        yMarkers[nextIdx] = 1;
+        elimBuffer[0] = nextIdx;
+        int nnzE = 1;
+        nextIdx = etree[bidx];
+        while (nextIdx != QDLDL_UNKNOWN && nextIdx < k) {
+          if (yMarkers[nextIdx] == 1) break;
+          yMarkers[nextIdx] = 1;
+          elimBuffer[nnzE] = nextIdx;
+          nnzE++;
+          nextIdx = etree[nextIdx];
+        }
+        while (nnzE) yIdx[nnzY++] = elimBuffer[--nnzE];
+      }
+    }
+    for (int i = nnzY - 1; i >= 0; i--) {
+      const int cidx = yIdx[i];
+      const int tmpIdx = LNextSpaceInCol[cidx];
+      const double yVals_cidx = yVals[cidx];
+      for (int j = Lp[cidx]; j < tmpIdx; j++) yVals[Li[j]] -= Lx[j] * yVals_cidx;
+      Li[tmpIdx] = k;
+      Lx[tmpIdx] = yVals_cidx * Dinv[cidx];
+      D[k] -= yVals_cidx * Lx[tmpIdx];
+      LNextSpaceInCol[cidx]++;
+      yVals[cidx] = 0.0;
+      yMarkers[cidx] = 0;
+    }
+    if (D[k] == 0.0) return -1;
+    if (D[k] > 0.0) positive++;
+    Dinv[k] = 1 / D[k];
+  }
+  return positive;
+}
+
+// x <- (L D L')^-1 x
+void QdldlSolve(int n, const int* Lp, const int* Li, const double* Lx, const double* Dinv,
+                double* x) {
+  for (int i = 0; i < n; i++) {
+    const double val = x[i];
+    for (int j = Lp[i]; j < Lp[i + 1]; j++) x[Li[j]] -= Lx[j] * val;
+  }
+  for (int i = 0; i < n; i++) x[i] *= Dinv[i];
+  for (int i = n - 1; i >= 0; i--) {
+    double val = x[i];
+    for (int j = Lp[i]; j < Lp[i + 1]; j++) val -= Lx[j] * x[Li[j]];
+    x[i] = val;
+  }
+}
+
+// tools/qdldl/qdldl_wrapper.h:19-84
+struct QdldlWrapper {
+  int n, nnz = 0;
+  std::vector<int> etree, Lnz, Lp, Li, iwork;
+  Vec Lx, D, Dinv, fwork;
+  std::vector<unsigned char> bwork;
+  bool ok = false;
+  QdldlWrapper(int n_, const int* Ap, const int* Ai)
+      : n(n_), etree(n_), Lnz(n_), Lp(n_ + 1), iwork(3 * n_), D(n_), Dinv(n_), fwork(n_),
+        bwork(n_) {
+    nnz = QdldlEtree(n, Ap, Ai, iwork.data(), Lnz.data(), etree.data());
+    if (nnz < 0) return;
+    Li.resize(nnz);
+    Lx.resize(nnz);
+    ok = true;
+  }
+  bool Factor(const int* Ap, const int* Ai, const double* Ax) {
+    return ok && QdldlFactor(n, Ap, Ai, Ax, Lp.data(), Li.data(), Lx.data(), D.data(),
+                             Dinv.data(), Lnz.data(), etree.data(), bwork.data(), iwork.data(),
+                             fwork.data()) >= 0;
+  }
+  void Solve(double* x) const { QdldlSolve(n, Lp.data(), Li.data(), Lx.data(), Dinv.data(), x); }
+};
+
+// Data concept over compressed-column matrices: H by its upper triangle, G, A.
+// Products gather along rows (entries of a row in increasing column order), the
+// transposed ones along the stored columns.
+struct SparseData : Data {
+  const int *Hp, *Hi, *Gp, *Gi, *Ap, *Ai;
+  const double *Hx, *f, *Gx, *h, *Ax, *b;
+  struct Rows {
+    std::vector<int> ptr, col, val;
+  };
+  Rows Hr, Gr, Ar;
+  static Rows MakeRows(int rows, int cols, const int* p, const int* i, bool symmetric) {
+    std::vector<std::vector<std::pair<int, int>>> r(rows);
+    for (int c = 0; c < cols; c++)
+      for (int e = p[c]; e < p[c + 1]; e++) {
+        r[i[e]].push_back({c, e});
+        if (symmetric && i[e] != c) r[c].push_back({i[e], e});
+      }
+    Rows out;
+    out.ptr.assign(rows + 1, 0);
+    for (int k = 0; k < rows; k++) {
+      std::sort(r[k].begin(), r[k].end());
+      out.ptr[k + 1] = out.ptr[k] + (int)r[k].size();
+      for (auto& pr : r[k]) {
+        out.col.push_back(pr.first);
+        out.val.push_back(pr.second);
+      }
+    }
+    return out;
+  }
+  SparseData(int nz_, int nl_, int nv_, const int* Hp_, const int* Hi_, const double* Hx_,
+             const double* f_, const int* Gp_, const int* Gi_, const double* Gx_,
+             const double* h_, const int* Ap_, const int* Ai_, const double* Ax_,
+             const double* b_)
+      : Hp(Hp_), Hi(Hi_), Gp(Gp_), Gi(Gi_), Ap(Ap_), Ai(Ai_), Hx(Hx_), f(f_), Gx(Gx_), h(h_),
+        Ax(Ax_), b(b_) {
+    nz = nz_;
+    nl = nl_;
+    nv = nv_;
+    Hr = MakeRows(nz, nz, Hp, Hi, true);
+    if (nl > 0) Gr = MakeRows(nl, nz, Gp, Gi, false);
+    else Gr.ptr.assign(1, 0);
+    Ar = MakeRows(nv, nz, Ap, Ai, false);
+    forcing_norm = std::sqrt(dot(b, b, nv) + dot(f, f, nz) + dot(h, h, nl));
+  }
+  static void RowsGemv(const Rows& R, const double* X, int rows, const double* x, double a,
+                       double bb, double* y) {
+    scale_by_b(bb, y, rows);
+    for (int r = 0; r < rows; r++) {
+      double s = 0.0;
+      for (int q = R.ptr[r]; q < R.ptr[r + 1]; q++) s += X[R.val[q]] * x[R.col[q]];
+      y[r] += a * s;
+    }
+  }
+  static void ColsGemvT(int cols, const int* p, const int* i, const double* X, const double* x,
+                        double a, double bb, double* y) {
+    scale_by_b(bb, y, cols);
+    for (int c = 0; c < cols; c++) {
+      double s = 0.0;
+      for (int e = p[c]; e < p[c + 1]; e++) s += X[e] * x[i[e]];
+      y[c] += a * s;
+    }
+  }
+  void gemvH(const double* x, double a, double bb, double* y) const override {
+    RowsGemv(Hr, Hx, nz, x, a, bb, y);
+  }
+  void gemvA(const double* x, double a, double bb, double* y) const override {
+    RowsGemv(Ar, Ax, nv, x, a, bb, y);
+  }
+  void gemvAT(const double* x, double a, double bb, double* y) const override {
+    ColsGemvT(nz, Ap, Ai, Ax, x, a, bb, y);
+  }
+  void gemvG(const double* x, double a, double bb, double* y) const override {
+    RowsGemv(Gr, Gx, nl, x, a, bb, y);
+  }
+  void gemvGT(const double* x, double a, double bb, double* y) const override {
+    if (nl > 0) ColsGemvT(nz, Gp, Gi, Gx, x, a, bb, y);
+    else scale_by_b(bb, y, nz);
+  }
+  void axpyf(double a, double* y) const override {
+    for (int i = 0; i < nz; i++) y[i] += a * f[i];
+  }
+  void axpyh(double a, double* y) const override {
+    for (int i = 0; i < nl; i++) y[i] += a * h[i];
+  }
+  void axpyb(double a, double* y) const override {
+    for (int i = 0; i < nv; i++) y[i] += a * b[i];
+  }
+};
+
+// LinearSolver over the QDLDL factorisation of the permuted K.
+struct SparseSolver : LinearSolver {
+  const SparseData* data;
+  int nz, nl, nv, n;
+  std::vector<int> perm, iperm;  // perm[new] = old
+  std::vector<int> Kp, Ki;       // permuted upper-triangular CSC pattern
+  struct Src {
+    int kind, idx, row;  // 0 Hx[idx], 1 Hx[idx] + sigma, 2 sigma, 3 Gx[idx], 4 -sigma,
+  };                     // 5 sqrt(Gamma[row]) * Ax[idx], 6 -1
+  std::vector<Src> Ksrc;
+  Vec Kx, x, r3, adz;
+  std::unique_ptr<QdldlWrapper> ldl;
+
+  SparseSolver(const SparseData* d, const int* perm_)
+      : data(d), nz(d->nz), nl(d->nl), nv(d->nv), n(d->nz + d->nl + d->nv), perm(n), iperm(n),
+        x(n, 0.0), r3(d->nv, 0.0), adz(d->nv, 0.0) {
+    // default order: the w block first, then z, then l -- the reduction of
+    // dense_cholesky_solver.cc:32-127 (E = H + sigma I + A' Gamma A, then the Schur
+    // complement on l)
+    for (int k = 0; k < n; k++)
+      perm[k] = perm_ ? perm_[k] : (k < nv ? nz + nl + k : k - nv);
+    for (int k = 0; k < n; k++) iperm[perm[k]] = k;
+    struct T {
+      int row, col;
+      Src s;
+    };
+    std::vector<T> t;
+    auto add = [&](int r, int c, Src s) {
+      const int a = iperm[r], b = iperm[c];
+      t.push_back({std::min(a, b), std::max(a, b), s});
+    };
+    for (int c = 0; c < nz; c++) {
+      bool diag = false;
+      for (int e = d->Hp[c]; e < d->Hp[c + 1]; e++) {
+        if (d->Hi[e] == c) {
+          add(c, c, {1, e, 0});
+          diag = true;
+        } else {
+          add(d->Hi[e], c, {0, e, 0});
+        }
+      }
+      if (!diag) add(c, c, {2, 0, 0});
+    }
+    for (int c = 0; c < nz; c++)
+      for (int e = (nl > 0 ? d->Gp[c] : 0); e < (nl > 0 ? d->Gp[c + 1] : 0); e++)
+        add(c, nz + d->Gi[e], {3, e, 0});
+    for (int r = 0; r < nl; r++) add(nz + r, nz + r, {4, 0, 0});
+    for (int c = 0; c < nz; c++)
+      for (int e = d->Ap[c]; e < d->Ap[c + 1]; e++)
+        add(c, nz + nl + d->Ai[e], {5, e, d->Ai[e]});
+    for (int k = 0; k < nv; k++) add(nz + nl + k, nz + nl + k, {6, 0, 0});
+    std::sort(t.begin(), t.end(), [](const T& a, const T& b) {
+      return a.col != b.col ? a.col < b.col : a.row < b.row;
+    });
+    Kp.assign(n + 1, 0);
+    for (const T& e : t) {
+      Kp[e.col + 1]++;
+      Ki.push_back(e.row);
+      Ksrc.push_back(e.s);
+    }
+    for (int c = 0; c < n; c++) Kp[c + 1] += Kp[c];
+    Kx.assign(Ki.size(), 0.0);
+    ldl.reset(new QdldlWrapper(n, Kp.data(), Ki.data()));
+  }
+
+  bool Initialize(const Variable& xv, const Variable& xbar, double sigma) override {
+    Barrier(xv, xbar, sigma);
+    for (size_t e = 0; e < Ksrc.size(); e++) {
+      const Src& s = Ksrc[e];
+      double v;
+      switch (s.kind) {
+        case 0: v = data->Hx[s.idx]; break;
+        case 1: v = data->Hx[s.idx] + sigma; break;
+        case 2: v = sigma; break;
+        case 3: v = data->Gx[s.idx]; break;
+        case 4: v = -sigma; break;
+        case 5: v = std::sqrt(Gamma[s.row]) * data->Ax[s.idx]; break;
+        default: v = -1.0;
+      }
+      Kx[e] = v;
+    }
+    return ldl->Factor(Kp.data(), Ki.data(), Kx.data());
+  }
+
+  // r is already negated by the caller (impl:270); same reduction as
+  // dense_cholesky_solver.cc:81-127
+  bool Solve(const Residual& r, Variable* dx) override {
+    Vec r1 = r.z;
+    for (int i = 0; i < nv; i++) r3[i] = r.v[i] / mus[i];
+    data->gemvAT(r3.data(), -1.0, 1.0, r1.data());
+    for (int i = 0; i < nz; i++) x[iperm[i]] = r1[i];
+    for (int i = 0; i < nl; i++) x[iperm[nz + i]] = -r.l[i];
+    for (int i = 0; i < nv; i++) x[iperm[nz + nl + i]] = 0.0;
+    ldl->Solve(x.data());
+    for (int i = 0; i < nz; i++) dx->z[i] = x[iperm[i]];
+    for (int i = 0; i < nl; i++) dx->l[i] = x[iperm[nz + i]];
+    data->gemvA(dx->z.data(), 1.0, 0.0, adz.data());
+    for (int i = 0; i < nv; i++) {
+      dx->v[i] = (r.v[i] + gamma[i] * adz[i]) / mus[i];
+      dx->y[i] = data->b[i] - adz[i];
+    }
+    return true;
+  }
+};
+
+// ===========================================================================
 // C interface
 // ===========================================================================
 struct oracle_problem {
   Data* data = nullptr;
   DenseData* dense = nullptr;
   MpcData* mpc = nullptr;
+  SparseData* sparse = nullptr;
+  std::vector<int> perm;  // sparse: elimination order of K (empty = natural)
   ~oracle_problem() { delete data; }
 };
 
 static LinearSolver* MakeSolver(const oracle_problem* p, int variant) {
   if (p->dense) return new DenseSolver(p->dense, variant);
+  if (p->sparse) return new SparseSolver(p->sparse, p->perm.empty() ? nullptr : p->perm.data());
   return new RiccatiSolver(p->mpc);
 }
 
@@ -1681,6 +2030,55 @@ int oracle_solve(const oracle_problem* p, int variant, const oracle_options* o,
   const auto t1 = std::chrono::high_resolution_clock::now();
   out->solve_time = std::chrono::duration<double>(t1 - t0).count();
   return out->status;
+}
+
+oracle_problem* oracle_sparse_create(int nz, int nl, int nv, const int* Hp, const int* Hi,
+                                     const double* Hx, const double* f, const int* Gp,
+                                     const int* Gi, const double* Gx, const double* h,
+                                     const int* Ap, const int* Ai, const double* Ax,
+                                     const double* b, const int* perm) {
+  if (nz <= 0 || nv <= 0 || nl < 0) return nullptr;
+  auto* p = new oracle_problem;
+  p->sparse = new SparseData(nz, nl, nv, Hp, Hi, Hx, f, Gp, Gi, Gx, h, Ap, Ai, Ax, b);
+  p->data = p->sparse;
+  if (perm) p->perm.assign(perm, perm + nz + nl + nv);
+  return p;
+}
+
+int oracle_qdldl_solve(int n, const int* Ap, const int* Ai, const double* Ax, double* x) {
+  QdldlWrapper w(n, Ap, Ai);
+  if (!w.Factor(Ap, Ai, Ax)) return -1;
+  w.Solve(x);
+  return 0;
+}
+
+int oracle_sparse_solve_batch(int nz, int nl, int nv, int batch, const int* Hp, const int* Hi,
+                              const double* Hx, const double* f, const int* Gp, const int* Gi,
+                              const double* Gx, const double* h, const int* Ap, const int* Ai,
+                              const double* Ax, const double* b, const int* perm, double* z,
+                              double* l, double* v, double* y, const oracle_options* o,
+                              oracle_out* out, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  const size_t nH = Hp[nz], nG = nl > 0 ? Gp[nz] : 0, nA = Ap[nz];
+  auto work = [&](int lo, int hi) {
+    for (int i = lo; i < hi; i++) {
+      oracle_problem* p = oracle_sparse_create(
+          nz, nl, nv, Hp, Hi, Hx + (size_t)i * nH, f + (size_t)i * nz, Gp, Gi,
+          Gx + (size_t)i * nG, h + (size_t)i * nl, Ap, Ai, Ax + (size_t)i * nA,
+          b + (size_t)i * nv, perm);
+      oracle_solve(p, 0, o, z + (size_t)i * nz, l + (size_t)i * nl, v + (size_t)i * nv,
+                   y + (size_t)i * nv, out + i, nullptr, 0, nullptr);
+      oracle_destroy(p);
+    }
+  };
+  std::vector<std::thread> th;
+  const int per = (batch + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; t++) {
+    const int lo = t * per, hi = std::min(batch, lo + per);
+    if (lo < hi) th.emplace_back(work, lo, hi);
+  }
+  for (auto& t : th) t.join();
+  return 0;
 }
 
 int oracle_dense_solve_batch(int nz, int nl, int nv, int batch, const double* H,

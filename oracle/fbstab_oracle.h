@@ -122,6 +122,24 @@ int oracle_solve(const oracle_problem* p, int variant, const oracle_options* o,
                  double* z, double* l, double* v, double* y, oracle_out* out,
                  double* traj, int traj_cap, int* traj_len);
 
+/* Sparse QPs (FBstabSparse; the reference plans them, ROADMAP.md:10): H by its upper
+ * triangle, G and A, all compressed-column; perm (nz+nl+nv, perm[new] = old over
+ * [z; l; w]) is the elimination order of the Newton matrix, NULL = natural. */
+oracle_problem* oracle_sparse_create(int nz, int nl, int nv, const int* Hp, const int* Hi,
+                                     const double* Hx, const double* f, const int* Gp,
+                                     const int* Gi, const double* Gx, const double* h,
+                                     const int* Ap, const int* Ai, const double* Ax,
+                                     const double* b, const int* perm);
+/* QdldlWrapper (tools/qdldl/qdldl_wrapper.h:19-84): factor the upper-triangular CSC
+ * matrix and solve in place.  Returns 0, -1 on a zero pivot / bad pattern. */
+int oracle_qdldl_solve(int n, const int* Ap, const int* Ai, const double* Ax, double* x);
+int oracle_sparse_solve_batch(int nz, int nl, int nv, int batch, const int* Hp, const int* Hi,
+                              const double* Hx, const double* f, const int* Gp, const int* Gi,
+                              const double* Gx, const double* h, const int* Ap, const int* Ai,
+                              const double* Ax, const double* b, const int* perm, double* z,
+                              double* l, double* v, double* y, const oracle_options* o,
+                              oracle_out* out, int nthreads);
+
 /* Batched convenience for timing: instance-major arrays, nthreads host threads,
  * one solver per thread (static contiguous partition). Returns 0. */
 int oracle_dense_solve_batch(int nz, int nl, int nv, int batch, const double* H,
