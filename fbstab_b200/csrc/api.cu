@@ -623,8 +623,8 @@ struct fbstab_sparse_batch : HandleBase {
   fbs::SparsePattern pat;  // host copy of the symbolic analysis
   fbs::SparseDev dev;      // the same tables on the device
   int* tables = nullptr;   // one allocation behind dev's pointers
-  int warps = 0;
-  char name[200];
+  int warps = 0;  // resident instances (workspace columns)
+  char name[240];
 };
 
 namespace {
@@ -1401,20 +1401,21 @@ int fbstab_sparse_batch_create(int nz, int nl, int nv, const int* Hp, const int*
                        &d.Ar_val, &d.iperm,  &d.Kp,     &d.Ki,  &d.Kkind,  &d.Kidx,
                        &d.Krow,   &d.Lp,     &d.Li,     &d.Sp,  &d.Sc,     &d.St};
   for (int k = 0; k < kTabs; k++) *dst[k] = h->tables + off[k];
-  // workspace: at most ~6 GiB
-  const size_t per_warp = fbs::SparseLaneWsDoublesPerWarp(d) * sizeof(double);
-  int warps = fbs::SparseLaneWarps(max_batch, h->sm_count);
-  warps = (int)std::max<size_t>(1, std::min<size_t>(warps, ((size_t)6 << 30) / std::max<size_t>(per_warp, 1)));
-  if (cudaMalloc(&h->ws, (size_t)warps * per_warp) != cudaSuccess) {
+  // workspace: one column per resident instance, at most ~6 GiB
+  const size_t per_lane = fbs::SparseLaneWsDoublesPerLane(d) * sizeof(double);
+  size_t slots = fbs::SparseLaneSlots(max_batch, h->sm_count);
+  slots = std::max<size_t>(32, std::min<size_t>(slots, ((size_t)6 << 30) / std::max<size_t>(per_lane, 1)));
+  if (cudaMalloc(&h->ws, slots * per_lane) != cudaSuccess) {
     cudaGetLastError();
     Fail(FBSTAB_ERR_ALLOC, "cudaMalloc of the sparse solver workspace failed");
     return fail(FBSTAB_ERR_ALLOC);
   }
-  h->warps = warps;
+  h->warps = (int)slots;
   snprintf(h->name, sizeof(h->name),
            "sparse-lane (lane per instance, common pattern: n=%d nnz(K)=%d nnz(L)=%d, "
-           "%d warps, %.0f MB interleaved workspace)",
-           p.n, p.nnzK, p.nnzL, warps, warps * per_warp / 1e6);
+           "%d resident instances, %d per warp, %.0f MB interleaved workspace)",
+           p.n, p.nnzK, p.nnzL, (int)slots, fbs::SparseLaneLanes(max_batch, h->sm_count),
+           slots * per_lane / 1e6);
   h->path = h->name;
   *handle = h;
   return FBSTAB_OK;
@@ -1495,7 +1496,7 @@ int fbstab_sparse_batch_solve(fbstab_sparse_batch* h, int batch, const double* H
       return Fail(FBSTAB_ERR_CUDA, "sparse kernel launch failed");
     return FBSTAB_OK;
   };
-  if ((rc = RunPipelined(h, &st, batch, 8 * 32 * h->warps, launch))) return rc;
+  if ((rc = RunPipelined(h, &st, batch, 8 * h->warps, launch))) return rc;
   if (st.any_host && !IsDevicePtr(out)) {
     const double sec =
         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

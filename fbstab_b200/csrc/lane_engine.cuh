@@ -13,7 +13,7 @@
 //
 // The policy LN supplies (semantics as in engine.cuh, per lane):
 //   static constexpr int O_XK, O_XI, O_DX        ids of the iterate blocks
-//   int nz, nl, nv; bool on
+//   int nz, nl, nv; bool on, enabled            (enabled: the lane may own instances)
 //   void   bind(args, inst)
 //   double init(z0, l0, v0)                       -> forcing norm; xk = xi = x0, y = b - A z0
 //   EvalOut evaluate(base, trial, t, self_bar, sigma, alpha)   fused residual evaluation
@@ -37,7 +37,7 @@ __device__ __forceinline__ void lane_solve_loop(LN& p, const Args& a) {
   const fbstab_options& o = a.opts;
   const double sigma = o.sigma0, alpha = o.alpha;
   // per-lane solver state (fbstab_algorithm-impl.h:113-304 as a phase machine)
-  bool active = false, exhausted = false;
+  bool active = false, exhausted = !p.enabled;  // a disabled lane never owns an instance
   int inst = 0, phase = PH_TOP;
   int eflag = FBSTAB_MAXITERATIONS, status = FBSTAB_STATUS_OK;
   int newton = 0, prox = 0, backtracks = 0, evals = 0;

@@ -227,6 +227,7 @@ struct Lane {
   unsigned bar0;       // shared address of the SLOTS slot mbarriers
   unsigned par;        // bit s: the parity the next wait on slot s expects
   bool on;             // this lane takes part in the current sweep (stores enabled)
+  static constexpr bool enabled = true;  // every lane of a warp owns instances
 
   // sweep start: the stores of earlier sweeps become visible to the TMA engine
   __device__ __forceinline__ void ring_begin() const {

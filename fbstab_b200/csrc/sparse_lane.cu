@@ -50,6 +50,7 @@ struct SparseArgs {
   int* counter;
   fbstab_options opts;
   int warps;
+  int lanes;         // instances per warp (32, 16 or 8: see SparseLaneLanes)
 };
 
 struct SparseLane {
@@ -58,14 +59,16 @@ struct SparseLane {
   SparseDev d;
   int nz, nl, nv, n;
   bool on;
-  double* ws;  // this lane's column of the interleaved workspace
+  bool enabled;  // lanes >= `lanes per warp` never own an instance
+  int LW;        // instances per warp = interleave stride of the workspace
+  double* ws;    // this lane's column of the interleaved workspace
   // element offsets
   size_t VS, o_ri, o_gm, o_K, o_L, o_D, o_Di, o_y, o_x, o_Hx, o_f, o_Gx, o_h, o_Ax, o_b;
   const double *Hx, *f, *Gx, *h, *Ax, *b;  // this lane's instance, wire format
 
-  __device__ __forceinline__ double W(size_t e) const { return ws[e * 32]; }
+  __device__ __forceinline__ double W(size_t e) const { return ws[e * LW]; }
   __device__ __forceinline__ void S(size_t e, double v) const {
-    if (on) ws[e * 32] = v;
+    if (on) ws[e * LW] = v;
   }
   // entry i of part (0 z, 1 l, 2 v, 3 y) of iterate block `blk`
   __device__ __forceinline__ size_t vz(int blk, int i) const { return blk * VS + i; }
@@ -270,7 +273,21 @@ struct SparseLane {
       for (int q = d.Sp[k]; q < d.Sp[k + 1]; q++) {
         const int c = d.Sc[q], slot = d.St[q];
         const double yc = W(o_y + c);
-        for (int j = d.Lp[c]; j < slot; j++) {
+        // (the rows of a column are distinct: four updates in flight at a time -- the
+        // compiler cannot know that the stores do not alias the following loads)
+        int j = d.Lp[c];
+        for (; j + 4 <= slot; j += 4) {
+          const size_t y0 = o_y + d.Li[j], y1 = o_y + d.Li[j + 1], y2 = o_y + d.Li[j + 2],
+                       y3 = o_y + d.Li[j + 3];
+          const double l0 = W(o_L + j), l1 = W(o_L + j + 1), l2 = W(o_L + j + 2),
+                       l3 = W(o_L + j + 3);
+          const double v0 = W(y0), v1 = W(y1), v2 = W(y2), v3 = W(y3);
+          S(y0, fma(-l0, yc, v0));
+          S(y1, fma(-l1, yc, v1));
+          S(y2, fma(-l2, yc, v2));
+          S(y3, fma(-l3, yc, v3));
+        }
+        for (; j < slot; j++) {
           const size_t yi = o_y + d.Li[j];
           S(yi, fma(-W(o_L + j), yc, W(yi)));
         }
@@ -300,7 +317,20 @@ struct SparseLane {
     for (int k = 0; k < nv; k++) S(o_x + d.iperm[nz + nl + k], 0.0);
     for (int i = 0; i < n; i++) {
       const double xi = W(o_x + i);
-      for (int j = d.Lp[i]; j < d.Lp[i + 1]; j++) {
+      const int je = d.Lp[i + 1];
+      int j = d.Lp[i];
+      for (; j + 4 <= je; j += 4) {
+        const size_t t0 = o_x + d.Li[j], t1 = o_x + d.Li[j + 1], t2 = o_x + d.Li[j + 2],
+                     t3 = o_x + d.Li[j + 3];
+        const double l0 = W(o_L + j), l1 = W(o_L + j + 1), l2 = W(o_L + j + 2),
+                     l3 = W(o_L + j + 3);
+        const double v0 = W(t0), v1 = W(t1), v2 = W(t2), v3 = W(t3);
+        S(t0, fma(-l0, xi, v0));
+        S(t1, fma(-l1, xi, v1));
+        S(t2, fma(-l2, xi, v2));
+        S(t3, fma(-l3, xi, v3));
+      }
+      for (; j < je; j++) {
         const size_t t = o_x + d.Li[j];
         S(t, fma(-W(o_L + j), xi, W(t)));
       }
@@ -420,7 +450,10 @@ sparse_lane_kernel(const __grid_constant__ SparseArgs a) {
   if (warp >= a.warps) return;
   SparseLane p;
   p.layout(a.d);
-  p.ws = a.ws + (size_t)warp * a.ws_stride + lane;
+  p.LW = a.lanes;
+  p.enabled = lane < a.lanes;
+  // (idle lanes alias lane 0's column: they execute the warp's sweeps with their stores off)
+  p.ws = a.ws + (size_t)warp * a.ws_stride + (p.enabled ? lane : 0);
   p.on = true;
   p.bind(a, 0);
   lane_solve_loop(p, a);
@@ -428,19 +461,36 @@ sparse_lane_kernel(const __grid_constant__ SparseArgs a) {
 
 }  // namespace
 
-size_t SparseLaneWsDoublesPerWarp(const SparseDev& d) {
+// Instances per warp.  Measured on the servo OCP as a sparse QP (16,384 instances,
+// profiles/r2_sparse_lane.txt): 32 lanes 15.1 k, 16 lanes 14.6 k, 8 lanes 12.7 k solves/s --
+// the time is the dependent chain of indirectly addressed loads of ONE warp times the
+// rounds of its slowest instance, which more (narrower) warps do not shorten.  Full warps
+// are the default; FBSTAB_SPARSE_LANES = 16 / 8 re-measures.
+int SparseLaneLanes(int batch, int sms) {
+  (void)batch;
+  (void)sms;
+  if (const char* e = getenv("FBSTAB_SPARSE_LANES")) {
+    const int v = atoi(e);
+    if (v == 8 || v == 16 || v == 32) return v;
+  }
+  return 32;
+}
+
+size_t SparseLaneWsDoublesPerLane(const SparseDev& d) {
   const size_t vs = (size_t)d.nz + d.nl + 2 * (size_t)d.nv;
   const size_t per_lane = 3 * vs + ((size_t)d.nz + d.nl + d.nv) + 3 * (size_t)d.nv + d.nnzK +
                           d.nnzL + 4 * (size_t)d.n + d.nnzH + d.nz + d.nnzG + d.nl + d.nnzA + d.nv;
-  return 32 * per_lane;
+  return per_lane;
 }
 
-int SparseLaneWarps(int batch, int sms) {
-  const int need = std::max(1, (batch + 31) / 32);
-  return std::min(need, sms * 2 * kSparseWarpsPerCta);
+// Instances resident at a time (each needs a workspace column) for batches up to `batch`.
+int SparseLaneSlots(int batch, int sms) {
+  const int lanes = SparseLaneLanes(batch, sms);
+  const int need = std::max(1, (batch + lanes - 1) / lanes);
+  return lanes * std::min(need, sms * 4 * kSparseWarpsPerCta);
 }
 
-int SparseLaneLaunch(const SparseDev& d, int batch, int warps, const double* Hx, const double* f,
+int SparseLaneLaunch(const SparseDev& d, int batch, int lane_slots, const double* Hx, const double* f,
                      const double* Gx, const double* h, const double* Ax, const double* b,
                      double* z, double* l, double* v, double* y, fbstab_out* out,
                      const fbstab_options& opts, double* ws, int* counter, cudaStream_t stream) {
@@ -459,15 +509,16 @@ int SparseLaneLaunch(const SparseDev& d, int batch, int warps, const double* Hx,
   a.y = y;
   a.out = out;
   a.ws = ws;
-  a.ws_stride = SparseLaneWsDoublesPerWarp(d);
-  a.counter = counter;
-  a.opts = opts;
-  a.warps = std::min(warps, std::max(1, (batch + 31) / 32));
-  // spread the warps over the SMs: CTAs of up to kSparseWarpsPerCta warps
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int per_cta = std::max(1, std::min(kSparseWarpsPerCta, (a.warps + 2 * sms - 1) / (2 * sms)));
+  a.lanes = SparseLaneLanes(batch, sms);
+  a.ws_stride = (size_t)a.lanes * SparseLaneWsDoublesPerLane(d);
+  a.counter = counter;
+  a.opts = opts;
+  a.warps = std::max(1, std::min(lane_slots / a.lanes, (batch + a.lanes - 1) / a.lanes));
+  // spread the warps over the SMs: CTAs of up to kSparseWarpsPerCta warps
+  const int per_cta = std::max(1, std::min(kSparseWarpsPerCta, (a.warps + 4 * sms - 1) / (4 * sms)));
   const int ctas = (a.warps + per_cta - 1) / per_cta;
   // warp index = blockIdx.x * warps per CTA + warp in CTA
   sparse_lane_kernel<<<ctas, 32 * per_cta, 0, stream>>>(a);

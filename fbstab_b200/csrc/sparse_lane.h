@@ -18,13 +18,14 @@ struct SparseDev {
   const int *Lp, *Li, *Sp, *Sc, *St;
 };
 
-// Lane-interleaved workspace of one warp (32 instances), in doubles.
-size_t SparseLaneWsDoublesPerWarp(const SparseDev& d);
-// Warps launched for `batch` instances on a device with `sms` SMs.
-int SparseLaneWarps(int batch, int sms);
+// Workspace of one instance (a column of a warp's lane-interleaved block), in doubles.
+size_t SparseLaneWsDoublesPerLane(const SparseDev& d);
+// Instances per warp (32, 16 or 8) and instances resident at a time for a batch.
+int SparseLaneLanes(int batch, int sms);
+int SparseLaneSlots(int batch, int sms);
 // One launch solves `batch` instances (instance-major value arrays); `ws` holds
-// warps * SparseLaneWsDoublesPerWarp doubles.  Returns 0 on success.
-int SparseLaneLaunch(const SparseDev& d, int batch, int warps, const double* Hx, const double* f,
+// lane_slots * SparseLaneWsDoublesPerLane doubles.  Returns 0 on success.
+int SparseLaneLaunch(const SparseDev& d, int batch, int lane_slots, const double* Hx, const double* f,
                      const double* Gx, const double* h, const double* Ax, const double* b,
                      double* z, double* l, double* v, double* y, fbstab_out* out,
                      const fbstab_options& opts, double* ws, int* counter, cudaStream_t stream);
