@@ -13,6 +13,8 @@ and reports them under `per_config` (same keys: value, e2e, roofline, parity):
   5        dense nz=512 nl=128 nv=1024, 1,024 instances (sharded: strong scaling)
   1        ONE dense QP nz=50 nl=10 nv=100: CPU latency of the restated reference
            (median of 101 solves) next to the engine's single-instance latency
+  3a-sparse  the instances of 3a restated as general sparse QPs (FBstabSparse, SURVEY
+           8(f4): the reference plans this solver; common pattern, values per instance)
 
 `--config X` makes X the headline, `--per-config none` skips the rest.
 
@@ -58,9 +60,11 @@ CONFIGS = {
     "4a": ("mpc", ("spacecraft", 100), 4096, 4, 0.05, "weak", 4096),
     "4a40": ("mpc", ("spacecraft", 40), 4096, 4, 0.01, "weak", 1024),
     "4b": ("mpc", ("copolymerization", 100), 4096, 4, 0.05, "weak", 1024),
+    # config 3a's instances restated as GENERAL sparse QPs (FBstabSparse)
+    "3a-sparse": ("sparse", ("servo_motor", 50), 16384, 3, 0.02, "weak", 512),
     "5": ("dense", (512, 128, 1024), 1024, 5, None, "strong", 128),
 }
-PER_CONFIG_ORDER = ["3a", "3b", "4a", "4a40", "4b", "5"]
+PER_CONFIG_ORDER = ["3a", "3b", "4a", "4a40", "4b", "5", "3a-sparse"]
 OCP_DIMS = {"servo_motor": (4, 1, 4), "double_integrator": (2, 1, 6),
             "spacecraft": (6, 3, 12), "copolymerization": (18, 5, 10)}
 
@@ -87,6 +91,12 @@ class Workload:
                           f"{self.batch:,} instances (BASELINE config {name}; x0 = nominal + "
                           + (f"{self.rho}*U(-1,1)" if self.rho > 0 else f"{-self.rho}*U(0,1)") +
                           "), default options, cold start")
+            if self.kind == "sparse":
+                self.label = self.label.replace(
+                    "batched FBstabMpc", "batched FBstabSparse (general sparse QP form of the)")
+                self.label = self.label.replace("BASELINE config 3a-sparse",
+                                                "the instances of BASELINE config 3a")
+                self._pattern = self._perm = self._fac = None
             self.desc = {"ocp": self.ocp, "N": self.N, "nx": self.nx, "nu": self.nu,
                          "nc": self.nc, "rho": self.rho}
         self.metric = f"batched QP solves/sec ({self.label.split(' (BASELINE')[0]})"
@@ -97,12 +107,31 @@ class Workload:
             return problems.random_dense_qp(self.nz, self.nl, self.nv, count=count,
                                             config=self.cfg, first=first,
                                             nthreads=threads, alloc=alloc)
+        if self.kind == "sparse":
+            dims, d = problems.ocp_batch(self.ocp, self.N, count=count, config=self.cfg,
+                                         rho=self.rho, first=first)
+            _, pat, vals = problems.ocp_as_sparse_qp(dims, d, count, alloc=alloc)
+            if self._pattern is None:
+                self._pattern = pat
+            assert all(np.array_equal(a, b) for a, b in zip(pat, self._pattern))
+            return vals
         return problems.ocp_batch(self.ocp, self.N, count=count, config=self.cfg,
                                   rho=self.rho, first=first, alloc=alloc)[1]
+
+    def pattern(self, problems):
+        if self._pattern is None:
+            self.generate(problems, 1, 0, 1)
+        return self._pattern
 
     def solver(self, fb, max_batch, device):
         if self.kind == "dense":
             return fb.FBstabDense(self.nz, self.nl, self.nv, max_batch=max_batch, device=device)
+        if self.kind == "sparse":
+            s = fb.FBstabSparse(self.nz, self.nl, self.nv, self.pattern(fb.problems),
+                                max_batch=max_batch, device=device)
+            self._perm = s.analysis()[3]  # the CPU leg eliminates in the same order
+            self._fac = s.factor_pattern()
+            return s
         return fb.FBstabMpc(self.N, self.nx, self.nu, self.nc, max_batch=max_batch,
                             device=device)
 
@@ -111,6 +140,10 @@ class Workload:
             return ob.dense_solve_batch(self.nz, self.nl, self.nv,
                                         *[d[k] for k in problems.DENSE_FIELDS],
                                         nthreads=threads)
+        if self.kind == "sparse":
+            return ob.sparse_solve_batch(self.nz, self.nl, self.nv, self.pattern(problems),
+                                         [d[k] for k in problems.SPARSE_FIELDS],
+                                         perm=self._perm, nthreads=threads)
         return ob.mpc_solve_batch(self.N, self.nx, self.nu, self.nc,
                                   [d[k] for k in problems.MPC_FIELDS], nthreads=threads)
 
@@ -121,6 +154,22 @@ class Workload:
             f_res = 2 * nz * nz + 4 * nl * nz + 2 * nv * nz
             f_init = nv * nz * (nz + 1) + nv * nz + (nz + nl) ** 3 / 3.0
             f_solve = 4 * nv * nz + 2 * (nz + nl) ** 2
+        elif self.kind == "sparse":
+            # the formulas of SURVEY 8(a) rows a3, a9, a10 with non-zero counts for the
+            # products and the operation count of the up-looking LDL' for the factorisation
+            import fbstab_b200.problems as problems
+            Hp, Hi, Gp, Gi, Ap, Ai = self.pattern(problems)
+            nnzH = 2 * len(Hi) - int((np.repeat(np.arange(self.nz), np.diff(Hp)) == Hi).sum())
+            nnzG, nnzA = len(Gi), len(Ai)
+            n = self.nz + self.nl + self.nv
+            f_res = 2 * nnzH + 4 * nnzG + 2 * nnzA
+            if self._fac is not None:
+                cnt = np.diff(self._fac[0]).astype(np.float64)
+                f_fac, nnzL = float((cnt * cnt + 3 * cnt).sum()), float(len(self._fac[1]))
+            else:
+                f_fac, nnzL = 0.0, 0.0
+            f_init = nnzA + 4 * self.nv + f_fac
+            f_solve = 4 * nnzL + n + 4 * nnzA
         else:
             N, nx, nu, nc = self.N, self.nx, self.nu, self.nc
             ns = nx + nu
@@ -138,6 +187,10 @@ class Workload:
         if self.kind == "dense":
             nz, nl, nv = self.nz, self.nl, self.nv
             return nz * nz + nl * nz + nv * nz + nz + nl + nv
+        if self.kind == "sparse":
+            import fbstab_b200.problems as problems
+            Hp, Hi, Gp, Gi, Ap, Ai = self.pattern(problems)
+            return len(Hi) + len(Gi) + len(Ai) + self.nz + self.nl + self.nv
         N, nx, nu, nc = self.N, self.nx, self.nu, self.nc
         K = N + 1
         return (K * (nx * nx + nu * nu + nu * nx + nx + nu + nc * nx + nc * nu + nc) +

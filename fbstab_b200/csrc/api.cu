@@ -1451,6 +1451,13 @@ int fbstab_sparse_batch_analysis(const fbstab_sparse_batch* h, int* n, int* nnzK
   return FBSTAB_OK;
 }
 
+int fbstab_sparse_batch_factor_pattern(const fbstab_sparse_batch* h, int* Lp, int* Li) {
+  if (!h) return Fail(FBSTAB_ERR_INVALID, "null handle");
+  if (Lp) std::copy(h->pat.Lp.begin(), h->pat.Lp.end(), Lp);
+  if (Li) std::copy(h->pat.Li.begin(), h->pat.Li.end(), Li);
+  return FBSTAB_OK;
+}
+
 int fbstab_sparse_batch_solve(fbstab_sparse_batch* h, int batch, const double* Hx,
                               const double* f, const double* Gx, const double* hh,
                               const double* Ax, const double* b, double* z, double* l,

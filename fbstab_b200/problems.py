@@ -91,3 +91,89 @@ def random_dense_qp(nz, nl, nv, count=1, config=0, first=0, kind=0,
         config, first, count, nz, nl, nv, kind,
         *[capi.ptr(arrs[k]) for k in DENSE_FIELDS], nthreads))
     return arrs
+
+
+SPARSE_FIELDS = ("Hx", "f", "Gx", "h", "Ax", "b")
+
+
+def ocp_as_sparse_qp(dims, d, count, alloc=None):
+    """An OCP batch in the wire format as GENERAL sparse QPs on one pattern: the sign and
+    ordering conventions of the reference's MpcData (mpc_data.cc:17-289: z = [x0;u0;..;
+    xN;uN], H = blkdiag([Q S';S R]), G row-block 0 = [-I 0], row-block i = [A B] at stage
+    i-1 and -I at x_i, h = -[x0;c], A_qp = blkdiag([E L]), b = -d).
+
+    The pattern holds the entries that are non-zero in instance 0 (plus the -I blocks), so
+    it is valid for batches that share their stage matrices -- as the generator's batches
+    do: the instances differ in x0 only -- and the values of every instance are gathered
+    on it.  Returns ((nz, nl, nv), (Hp, Hi, Gp, Gi, Ap, Ai), dict of instance-major values).
+    """
+    N, nx, nu, nc = dims
+    K, ns = N + 1, nx + nu
+    sizes = mpc_field_sizes(N, nx, nu, nc)
+    nz, nl, nv = K * ns, K * nx, K * nc
+    H, G, A = [], [], []  # entries (row, col, field, offset, scale): value = scale * field[offset]
+    for i in range(K):
+        o = i * ns
+        for c in range(nx):
+            for r in range(nx):
+                if r <= c:
+                    H.append((o + r, o + c, "Q", i * nx * nx + r + c * nx, 1.0))
+        for c in range(nu):
+            for r in range(nx):  # S' above the diagonal block of R: entry (x_r, u_c) = S(c, r)
+                H.append((o + r, o + nx + c, "S", i * nu * nx + c + r * nu, 1.0))
+            for r in range(nu):
+                if r <= c:
+                    H.append((o + nx + r, o + nx + c, "R", i * nu * nu + r + c * nu, 1.0))
+        for r in range(nc):
+            for c in range(nx):
+                A.append((i * nc + r, o + c, "E", i * nc * nx + r + c * nc, 1.0))
+            for c in range(nu):
+                A.append((i * nc + r, o + nx + c, "L", i * nc * nu + r + c * nc, 1.0))
+        for r in range(nx):
+            G.append((i * nx + r, o + r, None, 0, -1.0))
+        if i > 0:
+            p = (i - 1) * ns
+            for r in range(nx):
+                for c in range(nx):
+                    G.append((i * nx + r, p + c, "A", (i - 1) * nx * nx + r + c * nx, 1.0))
+                for c in range(nu):
+                    G.append((i * nx + r, p + nx + c, "B", (i - 1) * nx * nu + r + c * nx, 1.0))
+
+    def compress(entries, cols):
+        keep = [e for e in entries if e[2] is None or d[e[2]][e[3]] != 0.0]
+        keep.sort(key=lambda e: (e[1], e[0]))
+        ptr = np.zeros(cols + 1, dtype=np.int32)
+        for e in keep:
+            ptr[e[1] + 1] += 1
+        ptr = np.cumsum(ptr).astype(np.int32)
+        idx = np.array([e[0] for e in keep], dtype=np.int32)
+        return ptr, idx, keep
+
+    def gather(keep, out):
+        out = out.reshape(count, len(keep))
+        for field in set(e[2] for e in keep):
+            cols = [k for k, e in enumerate(keep) if e[2] == field]
+            if field is None:
+                out[:, cols] = np.array([keep[k][4] for k in cols])
+            else:
+                src = d[field].reshape(count, sizes[field])
+                out[:, cols] = src[:, [keep[k][3] for k in cols]] * np.array(
+                    [keep[k][4] for k in cols])
+
+    Hp, Hi, Hk = compress(H, nz)
+    Gp, Gi, Gk = compress(G, nz)
+    Ap, Ai, Ak = compress(A, nz)
+    mk = alloc or (lambda n: np.empty(n, dtype=np.float64))
+    vals = {"Hx": mk(count * len(Hk)), "f": mk(count * nz), "Gx": mk(count * len(Gk)),
+            "h": mk(count * nl), "Ax": mk(count * len(Ak)), "b": mk(count * nv)}
+    gather(Hk, vals["Hx"])
+    gather(Gk, vals["Gx"])
+    gather(Ak, vals["Ax"])
+    f = vals["f"].reshape(count, K, ns)
+    f[:, :, :nx] = d["q"].reshape(count, K, nx)
+    f[:, :, nx:] = d["r"].reshape(count, K, nu)
+    h = vals["h"].reshape(count, K, nx)
+    h[:, 0, :] = -d["x0"].reshape(count, nx)
+    h[:, 1:, :] = -d["c"].reshape(count, N, nx)
+    vals["b"][:] = -d["d"]
+    return (nz, nl, nv), (Hp, Hi, Gp, Gi, Ap, Ai), vals

@@ -298,5 +298,13 @@ class FBstabSparse(_Base):
             self._h, None, None, None, capi.ptr(perm)))
         return n.value, k.value, l.value, perm
 
+    def factor_pattern(self):
+        """(Lp, Li): the strictly lower triangle of L, compressed columns."""
+        n, _, nnzL, _ = self.analysis()
+        Lp, Li = np.zeros(n + 1, dtype=np.int32), np.zeros(nnzL, dtype=np.int32)
+        capi.check(capi.lib().fbstab_sparse_batch_factor_pattern(
+            self._h, capi.ptr(Lp), capi.ptr(Li) if nnzL else None))
+        return Lp, Li
+
     def component(self, *a, **k):
         raise RuntimeError("FBstabSparse has no component-stage entry")

@@ -260,6 +260,10 @@ const char* fbstab_sparse_batch_path(const fbstab_sparse_batch* handle);
  * (perm != NULL) the elimination order in use.  Any pointer may be NULL. */
 int fbstab_sparse_batch_analysis(const fbstab_sparse_batch* handle, int* n, int* nnzK,
                                  int* nnzL, int* perm);
+/* The pattern of the factor L of the permuted Newton matrix (strictly lower triangle,
+ * compressed columns: Lp n+1 entries, Li nnzL entries) -- what QdldlWrapper keeps in
+ * Lp_ / Li_ (tools/qdldl/qdldl_wrapper.h:70-73).  Either pointer may be NULL. */
+int fbstab_sparse_batch_factor_pattern(const fbstab_sparse_batch* handle, int* Lp, int* Li);
 
 /* ---- receding-horizon (closed-loop) MPC ----------------------------------
  * What OcpGenerator::GetSimulationInputs exists for (fbstab/test/

@@ -21,6 +21,7 @@
 #include "fbstab/closed_loop.h"
 #include "fbstab/fbstab_dense.h"
 #include "fbstab/fbstab_mpc.h"
+#include "fbstab/fbstab_sparse.h"
 #include "fbstab/ocp_generator.h"
 
 namespace {
@@ -598,6 +599,89 @@ TEST(FBstabMpc, SizeMismatchThrows, true) {
   data.A = MatrixSequence(2, 2, 2);
   FBstabMpc::Variable x3(3, 2, 1, 6);
   EXPECT_THROW(solver3.Solve(data, &x3), "Sequence length mismatch");
+}
+
+// The dense solver tests FeasibleQPwithEQ / InfeasibleQP (fbstab_dense_unit_tests.cc:75-104,
+// 195-217) through the sparse solver: same data in compressed-column form, same assertions.
+static SparsePattern CscOf(const MatrixXd& M, bool upper, VectorXd* vals) {
+  SparsePattern s;
+  s.rows = (int)M.rows();
+  s.cols = (int)M.cols();
+  s.p.push_back(0);
+  std::vector<double> x;
+  for (int c = 0; c < s.cols; c++) {
+    for (int r = 0; r < s.rows; r++)
+      if (M(r, c) != 0.0 && (!upper || r <= c)) {
+        s.i.push_back(r);
+        x.push_back(M(r, c));
+      }
+    s.p.push_back((int)s.i.size());
+  }
+  *vals = VectorXd((int)x.size());
+  for (size_t k = 0; k < x.size(); k++) (*vals)(k) = x[k];
+  return s;
+}
+
+TEST(FBstabSparse, FeasibleQPwithEQ, true) {
+  MatrixXd H(2, 2), G(1, 2), A(2, 2);
+  H << 4, 1, 1, 2;
+  G << 1, 1;
+  A << -1, 0, 0, -1;
+  FBstabSparse::ProblemData qp;
+  const SparsePattern pH = CscOf(H, true, &qp.Hx), pG = CscOf(G, false, &qp.Gx),
+                      pA = CscOf(A, false, &qp.Ax);
+  qp.f = VectorXd(2);
+  qp.f << 1, 1;
+  qp.h = VectorXd(1);
+  qp.h << 1;
+  qp.b = VectorXd(2);
+  qp.b << 0, 0;
+  FBstabSparse solver(pH, pG, pA);
+  FBstabSparse::Options opts = FBstabSparse::DefaultOptions();
+  opts.abs_tol = 1e-8;
+  opts.display_level = Display::OFF;
+  solver.UpdateOptions(opts);
+  FBstabSparse::Variable x(2, 1, 2);
+  SolverOut out = solver.Solve(qp, &x);
+  ASSERT_EQ(out.eflag, ExitFlag::SUCCESS);
+  EXPECT_NEAR(x.z(0), 0.25, 1e-8);
+  EXPECT_NEAR(x.z(1), 0.75, 1e-8);
+  EXPECT_TRUE(solver.FactorNonzeros() > 0);
+  FBstabSparse::Variable bad(2, 0, 2);
+  EXPECT_THROW(solver.Solve(qp, &bad), "initial guess");
+}
+
+TEST(FBstabSparse, InfeasibleQP, true) {
+  MatrixXd H(2, 2), G(0, 2), A(5, 2);
+  H << 1, 0, 0, 0;
+  A << 1, 1, 1, 0, 0, 1, -1, 0, 0, -1;
+  FBstabSparse::ProblemData qp;
+  const SparsePattern pH = CscOf(H, true, &qp.Hx), pG = CscOf(G, false, &qp.Gx),
+                      pA = CscOf(A, false, &qp.Ax);
+  qp.f = VectorXd(2);
+  qp.f << 1, -1;
+  qp.h = VectorXd(0);
+  qp.b = VectorXd(5);
+  qp.b << 0, 3, 3, -1, -1;
+  FBstabSparse solver(pH, pG, pA);
+  FBstabSparse::Options opts = FBstabSparse::DefaultOptions();
+  opts.abs_tol = 1e-8;
+  opts.display_level = Display::OFF;
+  solver.UpdateOptions(opts);
+  FBstabSparse::Variable x(2, 0, 5);
+  SolverOut out = solver.Solve(qp, &x);
+  ASSERT_EQ(out.eflag, ExitFlag::PRIMAL_INFEASIBLE);
+}
+
+TEST(FBstabSparse, BadPatternThrows, false) {
+  SparsePattern H, G, A;
+  H.rows = 2;
+  H.cols = 3;  // not square
+  H.p = {0, 0, 0, 0};
+  A.rows = 1;
+  A.cols = 3;
+  A.p = {0, 0, 0, 0};
+  EXPECT_THROW(FBstabSparse(H, G, A), "H must be square");
 }
 
 }  // namespace test
