@@ -92,10 +92,10 @@ class Workload:
                           + (f"{self.rho}*U(-1,1)" if self.rho > 0 else f"{-self.rho}*U(0,1)") +
                           "), default options, cold start")
             if self.kind == "sparse":
+                self.label = self.label.replace("batched FBstabMpc", "batched FBstabSparse:")
                 self.label = self.label.replace(
-                    "batched FBstabMpc", "batched FBstabSparse (general sparse QP form of the)")
-                self.label = self.label.replace("BASELINE config 3a-sparse",
-                                                "the instances of BASELINE config 3a")
+                    "(BASELINE config 3a-sparse", "restated as general sparse QPs on one "
+                    "pattern (the instances of BASELINE config 3a")
                 self._pattern = self._perm = self._fac = None
             self.desc = {"ocp": self.ocp, "N": self.N, "nx": self.nx, "nu": self.nu,
                          "nc": self.nc, "rho": self.rho}
