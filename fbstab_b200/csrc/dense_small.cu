@@ -45,6 +45,10 @@
 #include "dense_small.h"
 #include "engine.cuh"
 
+#ifndef FBSTAB_DS_PAIR_STEPS
+#define FBSTAB_DS_PAIR_STEPS 1
+#endif
+
 namespace fbs {
 
 namespace small {
@@ -67,7 +71,8 @@ constexpr int OFF_VB = OFF_LB + NL;
 constexpr int OFF_SCR = OFF_VB + NV;  // scratch shared by the phases of a Newton step
 constexpr int SCR_SIZE = 392;  // Gamma (64) | transposition (8*LD) | pivot rows | Schur
 // pivot-row buffers of the elimination live in the scratch (free at that time):
-// 2 x (32 row entries, pivot first + 10 augmented + pad)
+// 4 x (32 row entries, pivot first + 10 augmented + pad): rows k, k + 1 being applied and
+// rows k + 2, k + 3 being published (slot = row & 3)
 constexpr int OFF_COL = OFF_SCR;
 constexpr int COL_STRIDE = 44;
 constexpr int SLAB = OFF_SCR + SCR_SIZE;
@@ -414,25 +419,120 @@ struct Warp {
     }
     if (NA & 1) sts2_if(nxt, nb + D(32 + NA - 1), g[NA - 1], 0.0);
   }
+  // Round 2, second pass: TWO pivots per trip.  A step is a chain -- pivot-row store ->
+  // __syncwarp -> broadcast load -> reciprocal -> multiplier -> update -> next store --
+  // and the warp sits in it 32 times per Newton step with one other warp to hide it.
+  // Here the rows of pivots k AND k + 1 (the second one as it is BEFORE pivot k's update)
+  // are published together, every lane redoes row k + 1's update by pivot k on the fly
+  // (r1_j = fma(-m, p_j, q_j): the very FMAs its owner executes, so the values are the
+  // owner's bit for bit) and applies both pivots to its own row: half the barriers and
+  // store -> load round trips for one redundant FMA per entry.  Same operations in the
+  // same order on every entry: results are bit-identical to the one-pivot steps
+  // (FBSTAB_DS_PAIR_STEPS=0 keeps those for A/B).
+  // Precondition: rows k0 and k0 + 1 are in slots (k0 & 3), (k0 + 1) & 3, both aligned on
+  // column k0 (store_rows2 / previous trip).
+  template <int W, int NA, int NG>
+  __device__ __forceinline__ void eliminate_step2(int k, unsigned pb, unsigned qb, unsigned n0,
+                                                  unsigned n1, int row, double (&a)[NZ],
+                                                  double (&g)[NG], double* rpiv) {
+    static_assert(W & 1, "a[0..W] travels as (W + 1) / 2 aligned pairs");
+    constexpr int NP = (W + 1) / 2, NAP = (NA + 1) / 2, CH = 2, NCH = (NP + CH - 1) / CH;
+    __syncwarp();
+    double2 cp[2][CH], cq[2][CH], xp[NAP], xq[NAP];
+#pragma unroll
+    for (int p = 0; p < CH; p++)
+      if (p < NP) {
+        cp[0][p] = lds2(pb + D(2 * p));
+        cq[0][p] = lds2(qb + D(2 * p));
+      }
+#pragma unroll
+    for (int r = 0; r < NAP; r++) {
+      xp[r] = lds2(pb + D(32 + 2 * r));
+      xq[r] = lds2(qb + D(32 + 2 * r));
+    }
+    const double d = cp[0][0].x;
+    if (!(fabs(d) > 0.0)) ok = false;
+    const double rd = 1.0 / d;
+    const double m = cq[0][0].x * rd;                    // row k + 1's multiplier for pivot k
+    const double d2 = fma(-m, cp[0][0].y, cq[0][0].y);   // pivot k + 1
+    if (!(fabs(d2) > 0.0)) ok = false;
+    const double rd2 = 1.0 / d2;
+    if (row == k) *rpiv = rd;
+    if (row == k + 1) *rpiv = rd2;
+    const double lik = (row != k) ? a[0] * rd : 0.0;
+    const double t1 = fma(-lik, cp[0][0].y, a[1]);
+    const double l2 = (row != k + 1) ? t1 * rd2 : 0.0;
+    const bool st = (row == k + 2) || (row == k + 3);
+    const unsigned nb = (row == k + 3) ? n1 : n0;
+#pragma unroll
+    for (int q = 0; q < NCH; q++) {
+#pragma unroll
+      for (int p = 0; p < CH; p++)
+        if (CH * (q + 1) + p < NP) {
+          cp[(q + 1) & 1][p] = lds2(pb + D(2 * (CH * (q + 1) + p)));
+          cq[(q + 1) & 1][p] = lds2(qb + D(2 * (CH * (q + 1) + p)));
+        }
+#pragma unroll
+      for (int p = 0; p < CH; p++) {
+        const int pg = CH * q + p;  // pair (entries 2 pg, 2 pg + 1) of the pivot rows
+        if (pg >= 1 && pg < NP) {
+          const double2 pp = cp[q & 1][p], qq = cq[q & 1][p];
+          const double tx = fma(-lik, pp.x, a[2 * pg]), ty = fma(-lik, pp.y, a[2 * pg + 1]);
+          const double rx = fma(-m, pp.x, qq.x), ry = fma(-m, pp.y, qq.y);
+          a[2 * pg - 2] = fma(-l2, rx, tx);
+          a[2 * pg - 1] = fma(-l2, ry, ty);
+          sts2_if(st, nb + D(2 * pg - 2), a[2 * pg - 2], a[2 * pg - 1]);
+        }
+      }
+    }
+    a[W - 1] = 0.0;
+    a[W] = 0.0;
+    sts2_if(st, nb + D(W - 1), 0.0, 0.0);
+#pragma unroll
+    for (int r = 0; r < NA; r++) {
+      const double mp = (r & 1) ? xp[r / 2].y : xp[r / 2].x;
+      const double mq = (r & 1) ? xq[r / 2].y : xq[r / 2].x;
+      g[r] = fma(-l2, fma(-m, mp, mq), fma(-lik, mp, g[r]));
+      if (r & 1) sts2_if(st, nb + D(32 + r - 1), g[r - 1], g[r]);
+    }
+    if (NA & 1) sts2_if(st, nb + D(32 + NA - 1), g[NA - 1], 0.0);
+  }
   // (An (even, odd) pair of steps per trip -- loop-invariant buffer addresses instead of
   // rewriting the address register of stores still in flight -- measured 2.5% SLOWER:
   // the body no longer fits the instruction cache next to its neighbours.)
   template <int W, int NA, int NG>
   __device__ __forceinline__ void eliminate(int k0, int k1, int row, double (&a)[NZ],
                                             double (&g)[NG], double* rpiv) {
+#if FBSTAB_DS_PAIR_STEPS
+#pragma unroll 1
+    for (int k = k0; k < k1; k += 2) {
+      const unsigned base = sb + D(OFF_COL);
+      eliminate_step2<W, NA>(k, base + D(COL_STRIDE * (k & 3)),
+                             base + D(COL_STRIDE * ((k + 1) & 3)),
+                             base + D(COL_STRIDE * ((k + 2) & 3)),
+                             base + D(COL_STRIDE * ((k + 3) & 3)), row, a, g, rpiv);
+    }
+#else
 #pragma unroll 1
     for (int k = k0; k < k1; k++) {
       const unsigned cb = sb + D(OFF_COL + COL_STRIDE * (k & 1));
       const unsigned nb = sb + D(OFF_COL + COL_STRIDE * ((k + 1) & 1));
       eliminate_step<W, NA>(k, cb, nb, row, a, g, rpiv);
     }
+#endif
   }
   // Row `row` == k0 into pivot buffer k0 & 1 (before the first segment).
   template <int W, int NA, int NG>
   __device__ __forceinline__ void store_row(int k0, int row, const double (&a)[NZ],
                                             const double (&g)[NG]) {
+#if FBSTAB_DS_PAIR_STEPS
+    // rows k0 and k0 + 1, each into its slot (row & 3), both aligned on column k0
+    const unsigned cb = sb + D(OFF_COL + COL_STRIDE * (row & 3));
+    const bool own = (row == k0) || (row == k0 + 1);
+#else
     const unsigned cb = sb + D(OFF_COL + COL_STRIDE * (k0 & 1));
     const bool own = (row == k0);
+#endif
 #pragma unroll
     for (int m = 0; m <= W; m += 2) sts2_if(own, cb + D(m), a[m], a[m + 1]);
 #pragma unroll
