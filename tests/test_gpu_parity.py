@@ -399,6 +399,42 @@ def test_mpc_lane_path_parity(fb, oracle, monkeypatch, kind, N, B, rho):
     assert np.abs(out2["newton_iters"] - out["newton_iters"][:nb]).max() <= 2
 
 
+@pytest.mark.parametrize("opts", [dict(max_newton_iters=4), dict(max_newton_iters=11),
+                                  dict(max_inner_iters=2), dict(max_linesearch_iters=1),
+                                  dict(max_prox_iters=2), dict(check_feasibility=0)])
+def test_mpc_lane_path_option_caps(fb, oracle, monkeypatch, opts):
+    """Every exit of the per-lane phase machine (lane_engine.cuh): the Newton cap with the
+    pick of xi or xk (impl:188-199), a subproblem that ends on max_inner_iters, a forced
+    step after a failed line search (impl:295-298), the proximal-iteration cap -- on the
+    ring sweeps, where commit / projection / difference / copy are fused."""
+    monkeypatch.setenv("FBSTAB_MPC_LANE_MIN", "256")
+    B = 300
+    dims, d = fb.problems.ocp_batch("servo_motor", 20, count=B, config=3, rho=0.1)
+    s = fb.FBstabMpc(*dims, max_batch=B)
+    assert s.path.startswith("mpc-lane"), s.path
+    s.update_options(fb.FBstabMpc.default_options(**opts))
+    z, l, v = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+    out, y = s.solve_batch(d, z, l, v)
+    oo, oz, ol, ov, oy = oracle.mpc_solve_batch(
+        *dims, [d[k] for k in fb.problems.MPC_FIELDS], opts=oracle.default_options(**opts),
+        nthreads=8)
+    assert (out["status"] == 0).all()
+    assert (out["eflag"] == oo["eflag"]).mean() >= 0.99, (out["eflag"], oo["eflag"])
+    same = _same_traj(out, oo) & (out["eflag"] == oo["eflag"])
+    # (with the feasibility check off the infeasible instances run to the proximal cap on
+    # diverging iterates -- v grows without bound -- and their iteration counts are not
+    # reproducible to rounding: the trajectory is demanded of the instances that converge)
+    conv = oo["eflag"] == 0 if not opts.get("check_feasibility", 1) else np.ones(B, bool)
+    assert conv.sum() >= B // 4 and same[conv].mean() >= 0.9, (conv.sum(), same[conv].mean())
+    Z, OZ = z.reshape(B, -1), oz.reshape(B, -1)
+    V, OV = v.reshape(B, -1), ov.reshape(B, -1)
+    for i in np.nonzero(same & conv)[0]:
+        # (capped solves stop far from the solution: the iterates are compared, and they
+        # carry the conditioning of the unconverged Newton systems)
+        assert rel_err(Z[i], OZ[i]) <= 1e-4, (i, rel_err(Z[i], OZ[i]))
+        assert rel_err(V[i], OV[i]) <= 1e-4, (i, rel_err(V[i], OV[i]))
+
+
 def _random_time_varying_ocp(N, nx, nu, nc, B, seed):
     """Strictly convex OCPs whose matrices differ from stage to stage AND from
     instance to instance (the reference's fixtures are all time-invariant, which
