@@ -623,7 +623,8 @@ struct fbstab_sparse_batch : HandleBase {
   fbs::SparsePattern pat;  // host copy of the symbolic analysis
   fbs::SparseDev dev;      // the same tables on the device
   int* tables = nullptr;   // one allocation behind dev's pointers
-  int warps = 0;  // resident instances (workspace columns)
+  int warps = 0;  // resident instances (workspace columns) of the lane path
+  int team_ctas = 0;  // > 0: the warp-per-instance path (sparse_team.cu), this many CTAs
   char name[240];
 };
 
@@ -1401,7 +1402,23 @@ int fbstab_sparse_batch_create(int nz, int nl, int nv, const int* Hp, const int*
                        &d.Ar_val, &d.iperm,  &d.Kp,     &d.Ki,  &d.Kkind,  &d.Kidx,
                        &d.Krow,   &d.Lp,     &d.Li,     &d.Sp,  &d.Sc,     &d.St};
   for (int k = 0; k < kTabs; k++) *dst[k] = h->tables + off[k];
-  // workspace: one column per resident instance, at most ~6 GiB
+  const int team_occ = fbs::SparseTeamCtasPerSm(d);
+  if (team_occ > 0) {
+    // warp per instance: the factor and the LDL' work vectors live in shared memory
+    const int ctas = std::min(max_batch, h->sm_count * team_occ);
+    const size_t per_cta = fbs::SparseTeamWsDoubles(d) * sizeof(double);
+    if (cudaMalloc(&h->ws, (size_t)ctas * per_cta) != cudaSuccess) {
+      cudaGetLastError();
+      Fail(FBSTAB_ERR_ALLOC, "cudaMalloc of the sparse solver workspace failed");
+      return fail(FBSTAB_ERR_ALLOC);
+    }
+    h->team_ctas = ctas;
+    snprintf(h->name, sizeof(h->name),
+             "sparse-team (warp per instance, common pattern: n=%d nnz(K)=%d nnz(L)=%d, L and "
+             "the LDL' work vectors in %.1f KB of shared memory, %d CTA/SM)",
+             p.n, p.nnzK, p.nnzL, fbs::SparseTeamSmemBytes(d) / 1024.0, team_occ);
+  } else {
+  // lane per instance: one workspace column per resident instance, at most ~6 GiB
   const size_t per_lane = fbs::SparseLaneWsDoublesPerLane(d) * sizeof(double);
   size_t slots = fbs::SparseLaneSlots(max_batch, h->sm_count);
   slots = std::max<size_t>(32, std::min<size_t>(slots, ((size_t)6 << 30) / std::max<size_t>(per_lane, 1)));
@@ -1416,6 +1433,7 @@ int fbstab_sparse_batch_create(int nz, int nl, int nv, const int* Hp, const int*
            "%d resident instances, %d per warp, %.0f MB interleaved workspace)",
            p.n, p.nnzK, p.nnzL, (int)slots, fbs::SparseLaneLanes(max_batch, h->sm_count),
            slots * per_lane / 1e6);
+  }
   h->path = h->name;
   *handle = h;
   return FBSTAB_OK;
@@ -1466,8 +1484,9 @@ int fbstab_sparse_batch_solve(fbstab_sparse_batch* h, int batch, const double* H
   if (batch < 0 || batch > h->max_batch)
     return Fail(FBSTAB_ERR_INVALID, "batch exceeds the handle's max_batch");
   if (!out) return Fail(FBSTAB_ERR_INVALID, "null out pointer");
-  if (h->opts.refine_steps != 0 || h->opts.regularize_retries != 0)
-    return Fail(FBSTAB_ERR_INVALID, "refine_steps / regularize_retries: not on the sparse path");
+  if (h->team_ctas == 0 && (h->opts.refine_steps != 0 || h->opts.regularize_retries != 0))
+    return Fail(FBSTAB_ERR_INVALID,
+                "refine_steps / regularize_retries: not on the lane-per-instance sparse path");
   h->last_launches = 0;
   if (batch == 0) return FBSTAB_OK;
   CUDA_TRY(cudaSetDevice(h->device));
@@ -1496,14 +1515,20 @@ int fbstab_sparse_batch_solve(fbstab_sparse_batch* h, int batch, const double* H
   if ((rc = st.InOut(&h->out_buf, out, B * sizeof(fbstab_out), false, (void**)&dout))) return rc;
   auto launch = [&](int lo, int n) -> int {
     const size_t o = (size_t)lo;
-    if (fbs::SparseLaneLaunch(h->dev, n, h->warps, dH + o * nH, df + o * nz, dG + o * nG,
-                              dh + o * nl, dA + o * nA, db + o * nv, dz + o * nz, dl + o * nl,
-                              dv + o * nv, dy + o * nv, dout + lo, h->opts, h->ws, h->counter,
-                              st.stream))
-      return Fail(FBSTAB_ERR_CUDA, "sparse kernel launch failed");
+    const int rc2 =
+        h->team_ctas > 0
+            ? fbs::SparseTeamLaunch(h->dev, n, h->team_ctas, dH + o * nH, df + o * nz,
+                                    dG + o * nG, dh + o * nl, dA + o * nA, db + o * nv,
+                                    dz + o * nz, dl + o * nl, dv + o * nv, dy + o * nv, dout + lo,
+                                    h->opts, h->ws, h->counter, st.stream)
+            : fbs::SparseLaneLaunch(h->dev, n, h->warps, dH + o * nH, df + o * nz, dG + o * nG,
+                                    dh + o * nl, dA + o * nA, db + o * nv, dz + o * nz,
+                                    dl + o * nl, dv + o * nv, dy + o * nv, dout + lo, h->opts,
+                                    h->ws, h->counter, st.stream);
+    if (rc2) return Fail(FBSTAB_ERR_CUDA, "sparse kernel launch failed");
     return FBSTAB_OK;
   };
-  if ((rc = RunPipelined(h, &st, batch, 8 * h->warps, launch))) return rc;
+  if ((rc = RunPipelined(h, &st, batch, 8 * std::max(h->warps, h->team_ctas), launch))) return rc;
   if (st.any_host && !IsDevicePtr(out)) {
     const double sec =
         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -30,4 +30,14 @@ int SparseLaneLaunch(const SparseDev& d, int batch, int lane_slots, const double
                      double* z, double* l, double* v, double* y, fbstab_out* out,
                      const fbstab_options& opts, double* ws, int* counter, cudaStream_t stream);
 
+// ---- warp-per-instance path (sparse_team.cu): L and the LDL' work vectors in shared memory
+size_t SparseTeamSmemBytes(const SparseDev& d);
+size_t SparseTeamWsDoubles(const SparseDev& d);  // global workspace of one CTA, in doubles
+// Resident single-warp CTAs per SM; 0 when the factor does not fit shared memory.
+int SparseTeamCtasPerSm(const SparseDev& d);
+int SparseTeamLaunch(const SparseDev& d, int batch, int ctas, const double* Hx, const double* f,
+                     const double* Gx, const double* h, const double* Ax, const double* b,
+                     double* z, double* l, double* v, double* y, fbstab_out* out,
+                     const fbstab_options& opts, double* ws, int* counter, cudaStream_t stream);
+
 }  // namespace fbs

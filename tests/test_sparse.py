@@ -240,16 +240,19 @@ def test_sparse_gpu_on_the_dense_solver_cases(fb, name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("team", ["1", "0"])
 @pytest.mark.parametrize("shape", [(24, 4, 40, 300), (60, 10, 90, 70), (9, 0, 14, 33)])
-def test_sparse_gpu_parity_with_the_oracle(fb, oracle, shape):
-    """Same exit flags; same trajectory (Newton, proximal and backtrack counts) and
-    solutions within 1e-8 relative (north_star's tolerance) -- the oracle eliminates in
-    the order the handle chose."""
+def test_sparse_gpu_parity_with_the_oracle(fb, oracle, monkeypatch, shape, team):
+    """Both device paths (warp per instance, sparse_team.cu; lane per instance,
+    sparse_lane.cu): same exit flags; same trajectory (Newton, proximal and backtrack
+    counts) and solutions within 1e-8 relative (north_star's tolerance) -- the oracle
+    eliminates in the order the handle chose."""
+    monkeypatch.setenv("FBSTAB_SPARSE_TEAM", team)
     nz, nl, nv, B = shape
     rng = np.random.default_rng(nz)
     pat, vals, _ = random_sparse_qp(rng, nz, nl, nv, count=B)
     s, out, z, l, v, y = _gpu_solve(fb, nz, nl, nv, pat, vals, B)
-    assert s.path.startswith("sparse-lane")
+    assert s.path.startswith("sparse-team" if team == "1" else "sparse-lane"), s.path
     n, nnzK, nnzL, perm = s.analysis()
     assert n == nz + nl + nv and sorted(perm.tolist()) == list(range(n))
     oo, oz, ol, ov, oy = oracle.sparse_solve_batch(
@@ -298,10 +301,12 @@ def test_sparse_gpu_batch_equals_single_solves_and_device_pointers(fb):
 
 
 @pytest.mark.gpu
-def test_sparse_gpu_mixed_exit_flags(fb, oracle):
+@pytest.mark.parametrize("team", ["1", "0"])
+def test_sparse_gpu_mixed_exit_flags(fb, oracle, monkeypatch, team):
     """Feasible, primal-infeasible and unbounded instances in one batch keep their own
     flags (the cases of fbstab_dense_unit_tests.cc:121-256 share a pattern once the
     zero entries are stored)."""
+    monkeypatch.setenv("FBSTAB_SPARSE_TEAM", team)
     names = ["DegenerateQP", "InfeasibleQP", "DegenerateQP", "InfeasibleQP"]
     cases = [dense_case(n) for n in names]
     keepH = np.ones((2, 2), bool)
@@ -322,10 +327,12 @@ def test_sparse_gpu_mixed_exit_flags(fb, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("team", ["1", "0"])
 @pytest.mark.parametrize("kind,N", [("double_integrator", 20), ("servo_motor", 25)])
-def test_sparse_gpu_on_ocps_matches_the_mpc_solver(fb, kind, N):
+def test_sparse_gpu_on_ocps_matches_the_mpc_solver(fb, monkeypatch, kind, N, team):
     """The reference's live MPC tests (fbstab_mpc_unit_tests.cc:62-104) as general sparse
     QPs: same flag and solution as FBstabMpc on the structured form."""
+    monkeypatch.setenv("FBSTAB_SPARSE_TEAM", team)
     B = 40
     dims, d = fb.problems.ocp_batch(kind, N, count=B, config=3, rho=0.01)
     qps = [ocp_as_qp(dims, d, i) for i in range(B)]

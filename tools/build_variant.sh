@@ -12,7 +12,7 @@ nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler
   -Iinclude -Ifbstab_b200/csrc "$@" -c "$src" -o build/variants/$name.o
 base=$(basename "$src")
 objs=""
-for o in api.cu dense_small.cu mpc_riccati.cu mpc_lane.cu microbench.cu multi_gpu.cu closed_loop.cu sparse_lane.cu problems.cpp sparse_symbolic.cpp; do
+for o in api.cu dense_small.cu mpc_riccati.cu mpc_lane.cu microbench.cu multi_gpu.cu closed_loop.cu sparse_lane.cu sparse_team.cu problems.cpp sparse_symbolic.cpp; do
   if [ "$o" == "$base" ]; then objs="$objs build/variants/$name.o"; else objs="$objs build/$o.o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$name.so $objs -ldl
