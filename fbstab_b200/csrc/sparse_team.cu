@@ -47,6 +47,7 @@ struct SparseProblem {
   const double *Hx, *f, *Gx, *h, *Ax, *bvec;  // this instance
   // shared memory
   double *L, *yw, *Dinv, *xw;
+  const int* Lis;  // the row indices of L (a copy of d.Li)
   // global workspace (per CTA)
   double *gamma, *mus, *sq, *r3, *tz;
 
@@ -131,31 +132,63 @@ struct SparseProblem {
     t.sync();
     bool ok = true;
     const int lane = t.rank();
+    // The rows are a chain (row k needs the pivots and columns before it), so what is on
+    // the chain is kept short: the entries of row k + 1's column of K are fetched one row
+    // ahead (lane p holds entry p); a row's schedule (column, slot, start of the column)
+    // is loaded by the lanes side by side and handed round by shuffles; L, its row
+    // indices, the reciprocal pivots and y are in shared memory; the warp synchronises
+    // with __syncwarp (the CTA is one warp).
+    auto fetch = [&](int k, double* diag) {
+      double v = 0.0;
+      if (k < n) {
+        const int p0 = d.Kp[k], p1 = d.Kp[k + 1];
+        *diag = kval(p1 - 1, sigma);
+        if (p0 + lane < p1 - 1) v = kval(p0 + lane, sigma);
+      }
+      return v;
+    };
+    double dnext = 0.0;
+    double knext = fetch(0, &dnext);
     for (int k = 0; k < n; k++) {
       // scatter column k of K (its diagonal entry is the last one: rows are sorted)
       const int p0 = d.Kp[k], p1 = d.Kp[k + 1];
-      for (int p = p0 + lane; p < p1 - 1; p += t.size()) yw[d.Ki[p]] = kval(p, sigma);
-      double dk = kval(p1 - 1, sigma);
-      t.sync();
-      for (int q = d.Sp[k]; q < d.Sp[k + 1]; q++) {
-        const int c = d.Sc[q], slot = d.St[q];
-        const double yc = yw[c];
-        t.sync();  // every lane holds yc before y is updated
-        for (int j = d.Lp[c] + lane; j < slot; j += t.size()) {
-          const int r = d.Li[j];
-          yw[r] = fma(-L[j], yc, yw[r]);
+      if (p0 + lane < p1 - 1) yw[d.Ki[p0 + lane]] = knext;
+      for (int p = p0 + 32 + lane; p < p1 - 1; p += 32) yw[d.Ki[p]] = kval(p, sigma);
+      double dk = dnext;
+      knext = fetch(k + 1, &dnext);
+      __syncwarp();
+      const int q0 = d.Sp[k], q1 = d.Sp[k + 1];
+      for (int qb = q0; qb < q1; qb += 32) {
+        // this lane's entry of the schedule
+        int mc = 0, mslot = 0, mj0 = 0;
+        if (qb + lane < q1) {
+          mc = d.Sc[qb + lane];
+          mslot = d.St[qb + lane];
+          mj0 = d.Lp[mc];
         }
-        const double lx = yc * Dinv[c];
-        dk = fma(-yc, lx, dk);
-        if (lane == 0) {
-          L[slot] = lx;
-          yw[c] = 0.0;
+        const int cnt = min(32, q1 - qb);
+        for (int u = 0; u < cnt; u++) {
+          const int c = __shfl_sync(0xffffffffu, mc, u);
+          const int slot = __shfl_sync(0xffffffffu, mslot, u);
+          const int j0 = __shfl_sync(0xffffffffu, mj0, u);
+          const double yc = yw[c];
+          __syncwarp();  // every lane holds yc before y is updated
+          for (int j = j0 + lane; j < slot; j += 32) {
+            const int r = Lis[j];
+            yw[r] = fma(-L[j], yc, yw[r]);
+          }
+          const double lx = yc * Dinv[c];
+          dk = fma(-yc, lx, dk);
+          if (lane == 0) {
+            L[slot] = lx;
+            yw[c] = 0.0;
+          }
+          __syncwarp();
         }
-        t.sync();
       }
       if (!(fabs(dk) > 0.0)) ok = false;
       if (lane == 0) Dinv[k] = 1.0 / dk;
-      t.sync();
+      __syncwarp();
     }
     return ok;
   }
@@ -174,21 +207,24 @@ struct SparseProblem {
       const int j0 = d.Lp[i], j1 = d.Lp[i + 1];
       if (j0 == j1) continue;
       const double xi = xw[i];
-      t.sync();
-      for (int j = j0 + lane; j < j1; j += t.size()) {
-        const int r = d.Li[j];
+      __syncwarp();
+      for (int j = j0 + lane; j < j1; j += 32) {
+        const int r = Lis[j];
         xw[r] = fma(-L[j], xi, xw[r]);
       }
-      t.sync();
+      __syncwarp();
     }
-    for (int i = lane; i < n; i += t.size()) xw[i] = xw[i] * Dinv[i];
-    t.sync();
+    for (int i = lane; i < n; i += 32) xw[i] = xw[i] * Dinv[i];
+    __syncwarp();
     // backward substitution: the sums run along one lane in the order of QDLDL_solve
     if (lane == 0) {
+      int j1 = d.Lp[n];
       for (int i = n - 1; i >= 0; i--) {
+        const int j0 = d.Lp[i];
         double xi = xw[i];
-        for (int j = d.Lp[i]; j < d.Lp[i + 1]; j++) xi = fma(-L[j], xw[d.Li[j]], xi);
+        for (int j = j0; j < j1; j++) xi = fma(-L[j], xw[Lis[j]], xi);
         xw[i] = xi;
+        j1 = j0;
       }
     }
     t.sync();
@@ -253,6 +289,11 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
   const SparseDev& d = a.d;
   const int nz = d.nz, nl = d.nl, nv = d.nv, n = d.n;
   double* ws0 = c.ws + (size_t)blockIdx.x * c.ws_stride;
+  {  // the pattern of L next to its values: one copy per CTA for all its instances
+    int* lis = reinterpret_cast<int*>(dyn_smem + d.nnzL + 3 * (size_t)n);
+    for (int j = threadIdx.x; j < d.nnzL; j += blockDim.x) lis[j] = d.Li[j];
+    __syncthreads();
+  }
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(c.counter, 1);
     __syncthreads();
@@ -293,6 +334,7 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
     p.yw = Carve(sm, n);
     p.Dinv = Carve(sm, n);
     p.xw = Carve(sm, n);
+    p.Lis = reinterpret_cast<const int*>(sm);  // filled once per CTA, below the loop head
     solve_instance(t, p, c.opts, w, c.z + (size_t)inst * nz, c.l + (size_t)inst * nl,
                    c.v + (size_t)inst * nv, c.y + (size_t)inst * nv, c.out + inst);
   }
@@ -301,7 +343,7 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
 }  // namespace
 
 size_t SparseTeamSmemBytes(const SparseDev& d) {
-  return sizeof(double) * ((size_t)d.nnzL + 3 * (size_t)d.n);
+  return sizeof(double) * ((size_t)d.nnzL + 3 * (size_t)d.n) + sizeof(int) * (((size_t)d.nnzL + 1) & ~(size_t)1);
 }
 size_t SparseTeamWsDoubles(const SparseDev& d) {
   const size_t vs = (size_t)d.nz + d.nl + 2 * (size_t)d.nv;
