@@ -11,8 +11,8 @@
 // row or entry.  Here a WARP owns an instance (the engine.cuh state machine, the
 // Problem policy below): the independent work is spread over the 32 lanes, and what is
 // sequential runs out of SHARED memory -- the factor L, the reciprocal pivots and the
-// work vectors of the LDL' (nnz(L) + 3n doubles per instance; servo OCP: 33 KB, six
-// instances per SM) -- at ~30 cycles per dependent step instead of an L2 / DRAM round
+// work vector of the LDL' and of the triangular solves (nnz(L) + 2n doubles + nnz(L)
+// 16-bit row indices per instance; servo OCP: 32.6 KB, six instances per SM) -- at ~30 cycles per dependent step instead of an L2 / DRAM round
 // trip.  Persistent single-warp CTAs pull instances from the global counter.
 //
 // The arithmetic is the lane kernel's operation for operation (same row sums in the
@@ -47,7 +47,7 @@ struct SparseProblem {
   const double *Hx, *f, *Gx, *h, *Ax, *bvec;  // this instance
   // shared memory
   double *L, *yw, *Dinv, *xw;
-  const int* Lis;  // the row indices of L (a copy of d.Li)
+  const unsigned short* Lis;  // the row indices of L (a 16-bit copy of d.Li: n < 65,536)
   // global workspace (per CTA)
   double *gamma, *mus, *sq, *r3, *tz;
 
@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
   const int nz = d.nz, nl = d.nl, nv = d.nv, n = d.n;
   double* ws0 = c.ws + (size_t)blockIdx.x * c.ws_stride;
   {  // the pattern of L next to its values: one copy per CTA for all its instances
-    int* lis = reinterpret_cast<int*>(dyn_smem + d.nnzL + 3 * (size_t)n);
-    for (int j = threadIdx.x; j < d.nnzL; j += blockDim.x) lis[j] = d.Li[j];
+    unsigned short* lis = reinterpret_cast<unsigned short*>(dyn_smem + d.nnzL + 2 * (size_t)n);
+    for (int j = threadIdx.x; j < d.nnzL; j += blockDim.x) lis[j] = (unsigned short)d.Li[j];
     __syncthreads();
   }
   for (;;) {
@@ -333,8 +333,8 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
     p.L = Carve(sm, d.nnzL);
     p.yw = Carve(sm, n);
     p.Dinv = Carve(sm, n);
-    p.xw = Carve(sm, n);
-    p.Lis = reinterpret_cast<const int*>(sm);  // filled once per CTA, below the loop head
+    p.xw = p.yw;  // the LDL' work vector is all zeros again when factor() returns
+    p.Lis = reinterpret_cast<const unsigned short*>(sm);  // filled once per CTA, above
     solve_instance(t, p, c.opts, w, c.z + (size_t)inst * nz, c.l + (size_t)inst * nl,
                    c.v + (size_t)inst * nv, c.y + (size_t)inst * nv, c.out + inst);
   }
@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
 }  // namespace
 
 size_t SparseTeamSmemBytes(const SparseDev& d) {
-  return sizeof(double) * ((size_t)d.nnzL + 3 * (size_t)d.n) + sizeof(int) * (((size_t)d.nnzL + 1) & ~(size_t)1);
+  return sizeof(double) * ((size_t)d.nnzL + 2 * (size_t)d.n) +
+         sizeof(unsigned short) * (((size_t)d.nnzL + 3) & ~(size_t)3);
 }
 size_t SparseTeamWsDoubles(const SparseDev& d) {
   const size_t vs = (size_t)d.nz + d.nl + 2 * (size_t)d.nv;
@@ -356,7 +357,7 @@ int SparseTeamCtasPerSm(const SparseDev& d) {
   if (const char* e = getenv("FBSTAB_SPARSE_TEAM"))
     if (atoi(e) == 0) return 0;
   const size_t smem = SparseTeamSmemBytes(d);
-  if (smem > 100 * 1024) return 0;
+  if (smem > 100 * 1024 || d.n > 65535) return 0;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute((const void*)sparse_team_kernel,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
