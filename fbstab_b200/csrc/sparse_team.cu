@@ -11,8 +11,8 @@
 // row or entry.  Here a WARP owns an instance (the engine.cuh state machine, the
 // Problem policy below): the independent work is spread over the 32 lanes, and what is
 // sequential runs out of SHARED memory -- the factor L, the reciprocal pivots and the
-// work vector of the LDL' and of the triangular solves (nnz(L) + 2n doubles + nnz(L)
-// 16-bit row indices per instance; servo OCP: 32.6 KB, six instances per SM) -- at ~30 cycles per dependent step instead of an L2 / DRAM round
+// work vector of the LDL' and of the triangular solves (nnz(L) + n doubles + nnz(L)
+// 16-bit row indices per instance; servo OCP: 26.7 KB, eight instances per SM) -- at ~30 cycles per dependent step instead of an L2 / DRAM round
 // trip.  Persistent single-warp CTAs pull instances from the global counter.
 //
 // The arithmetic is the lane kernel's operation for operation (same row sums in the
@@ -46,10 +46,11 @@ struct SparseProblem {
   SparseDev d;
   const double *Hx, *f, *Gx, *h, *Ax, *bvec;  // this instance
   // shared memory
-  double *L, *yw, *Dinv, *xw;
+  double *L, *yw, *xw;
   const unsigned short* Lis;  // the row indices of L (a 16-bit copy of d.Li: n < 65,536)
-  // global workspace (per CTA)
-  double *gamma, *mus, *sq, *r3, *tz;
+  // global workspace (per CTA); Dinv: the reciprocal pivots -- off the LDL' chain: a
+  // visit's reciprocal is loaded with its schedule entry
+  double *gamma, *mus, *sq, *r3, *tz, *Dinv;
 
   __device__ __forceinline__ double b(int i) const { return bvec[i]; }
   __device__ __forceinline__ double fvec(int i) const { return f[i]; }
@@ -161,23 +162,26 @@ struct SparseProblem {
       for (int qb = q0; qb < q1; qb += 32) {
         // this lane's entry of the schedule
         int mc = 0, mslot = 0, mj0 = 0;
+        double mdi = 0.0;
         if (qb + lane < q1) {
           mc = d.Sc[qb + lane];
           mslot = d.St[qb + lane];
           mj0 = d.Lp[mc];
+          mdi = Dinv[mc];  // (columns visited by row k are < k: written in earlier rows)
         }
         const int cnt = min(32, q1 - qb);
         for (int u = 0; u < cnt; u++) {
           const int c = __shfl_sync(0xffffffffu, mc, u);
           const int slot = __shfl_sync(0xffffffffu, mslot, u);
           const int j0 = __shfl_sync(0xffffffffu, mj0, u);
+          const double di = __shfl_sync(0xffffffffu, mdi, u);
           const double yc = yw[c];
           __syncwarp();  // every lane holds yc before y is updated
           for (int j = j0 + lane; j < slot; j += 32) {
             const int r = Lis[j];
             yw[r] = fma(-L[j], yc, yw[r]);
           }
-          const double lx = yc * Dinv[c];
+          const double lx = yc * di;
           dk = fma(-yc, lx, dk);
           if (lane == 0) {
             L[slot] = lx;
@@ -282,7 +286,7 @@ __device__ inline double* Carve(double*& p, size_t n) {
 
 __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constant__ SparseTeamArgs a) {
   extern __shared__ double dyn_smem[];
-  __shared__ double red[kMaxWarps * kRedSlots];
+  __shared__ double red[kRedSlots];  // one warp: team_sum / team_max use slot row 0 only
   __shared__ int s_inst;
   Team t{red};
   const CommonArgs& c = a.c;
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
   const int nz = d.nz, nl = d.nl, nv = d.nv, n = d.n;
   double* ws0 = c.ws + (size_t)blockIdx.x * c.ws_stride;
   {  // the pattern of L next to its values: one copy per CTA for all its instances
-    unsigned short* lis = reinterpret_cast<unsigned short*>(dyn_smem + d.nnzL + 2 * (size_t)n);
+    unsigned short* lis = reinterpret_cast<unsigned short*>(dyn_smem + d.nnzL + (size_t)n);
     for (int j = threadIdx.x; j < d.nnzL; j += blockDim.x) lis[j] = (unsigned short)d.Li[j];
     __syncthreads();
   }
@@ -329,10 +333,10 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
     p.sq = Carve(ws, nv);
     p.r3 = Carve(ws, nv);
     p.tz = Carve(ws, nz);
+    p.Dinv = Carve(ws, n);
     double* sm = dyn_smem;
     p.L = Carve(sm, d.nnzL);
     p.yw = Carve(sm, n);
-    p.Dinv = Carve(sm, n);
     p.xw = p.yw;  // the LDL' work vector is all zeros again when factor() returns
     p.Lis = reinterpret_cast<const unsigned short*>(sm);  // filled once per CTA, above
     solve_instance(t, p, c.opts, w, c.z + (size_t)inst * nz, c.l + (size_t)inst * nl,
@@ -343,12 +347,12 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
 }  // namespace
 
 size_t SparseTeamSmemBytes(const SparseDev& d) {
-  return sizeof(double) * ((size_t)d.nnzL + 2 * (size_t)d.n) +
+  return sizeof(double) * ((size_t)d.nnzL + (size_t)d.n) +
          sizeof(unsigned short) * (((size_t)d.nnzL + 3) & ~(size_t)3);
 }
 size_t SparseTeamWsDoubles(const SparseDev& d) {
   const size_t vs = (size_t)d.nz + d.nl + 2 * (size_t)d.nv;
-  return 4 * vs + ((size_t)d.nz + d.nl + d.nv) + 4 * (size_t)d.nv + d.nz;
+  return 4 * vs + ((size_t)d.nz + d.nl + d.nv) + 4 * (size_t)d.nv + d.nz + d.n;
 }
 
 // Resident single-warp CTAs per SM, 0 when the factor does not fit shared memory
