@@ -1403,11 +1403,11 @@ int fbstab_sparse_batch_create(int nz, int nl, int nv, const int* Hp, const int*
                        &d.Krow,   &d.Lp,     &d.Li,     &d.Sp,  &d.Sc,     &d.St};
   for (int k = 0; k < kTabs; k++) *dst[k] = h->tables + off[k];
   // Which device path: the warp-per-instance kernel's throughput is its residency over
-  // its per-instance latency whatever the batch (cfg 3a as sparse QPs: 32.5 k solves/s);
+  // its per-instance latency whatever the batch (cfg 3a as sparse QPs: 37 k solves/s);
   // the lane-per-instance kernel needs tens of thousands of instances in flight to
   // cover its latency (14 k at 16,384, 37 k at 65,536) -- it takes the large batches.
   const int team_occ = fbs::SparseTeamCtasPerSm(d);
-  if (team_occ > 0 && max_batch < EnvInt("FBSTAB_SPARSE_TEAM_MAX_BATCH", 57344)) {
+  if (team_occ > 0 && max_batch < EnvInt("FBSTAB_SPARSE_TEAM_MAX_BATCH", 98304)) {
     // warp per instance: the factor and the LDL' work vectors live in shared memory
     const int ctas = std::min(max_batch, h->sm_count * team_occ);
     const size_t per_cta = fbs::SparseTeamWsDoubles(d) * sizeof(double);

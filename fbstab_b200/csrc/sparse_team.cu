@@ -50,7 +50,7 @@ struct SparseProblem {
   const unsigned short* Lis;  // the row indices of L (a 16-bit copy of d.Li: n < 65,536)
   // global workspace (per CTA); Dinv: the reciprocal pivots -- off the LDL' chain: a
   // visit's reciprocal is loaded with its schedule entry
-  double *gamma, *mus, *sq, *r3, *tz, *Dinv;
+  double *gamma, *mus, *sq, *r3, *tz, *Dinv, *Kx;
 
   __device__ __forceinline__ double b(int i) const { return bvec[i]; }
   __device__ __forceinline__ double fvec(int i) const { return f[i]; }
@@ -117,8 +117,7 @@ struct SparseProblem {
   }
 
   // LinearSolver::Initialize: barrier terms, then the up-looking LDL' of the permuted
-  // K (the schedule of QDLDL_factor), row by row; a row's column of K is formed on the
-  // fly from its sources (no K array).  False on a zero / NaN pivot.
+  // K (the schedule of QDLDL_factor), row by row.  False on a zero / NaN pivot.
   __device__ bool factor(const Team& t, const Vars& x, const Vars& xbar, double sigma,
                          double alpha) {
     for (int k = t.rank(); k < nv; k += t.size()) {
@@ -134,29 +133,35 @@ struct SparseProblem {
     bool ok = true;
     const int lane = t.rank();
     // The rows are a chain (row k needs the pivots and columns before it), so what is on
-    // the chain is kept short: the entries of row k + 1's column of K are fetched one row
+    // the chain is kept short: the entries of a row's column of K are fetched two rows
     // ahead (lane p holds entry p); a row's schedule (column, slot, start of the column)
     // is loaded by the lanes side by side and handed round by shuffles; L, its row
     // indices, the reciprocal pivots and y are in shared memory; the warp synchronises
     // with __syncwarp (the CTA is one warp).
+    // K in one parallel pass (independent gathers, 32 in flight) ...
+    for (int e = lane; e < d.nnzK; e += 32) Kx[e] = kval(e, sigma);
+    __syncwarp();
+    // ... and the rows read it two rows ahead
     auto fetch = [&](int k, double* diag) {
       double v = 0.0;
       if (k < n) {
         const int p0 = d.Kp[k], p1 = d.Kp[k + 1];
-        *diag = kval(p1 - 1, sigma);
-        if (p0 + lane < p1 - 1) v = kval(p0 + lane, sigma);
+        *diag = Kx[p1 - 1];
+        if (p0 + lane < p1 - 1) v = Kx[p0 + lane];
       }
       return v;
     };
-    double dnext = 0.0;
-    double knext = fetch(0, &dnext);
+    double dA = 0.0, dB = 0.0;
+    double kA = fetch(0, &dA), kB = fetch(1, &dB);
     for (int k = 0; k < n; k++) {
       // scatter column k of K (its diagonal entry is the last one: rows are sorted)
       const int p0 = d.Kp[k], p1 = d.Kp[k + 1];
-      if (p0 + lane < p1 - 1) yw[d.Ki[p0 + lane]] = knext;
-      for (int p = p0 + 32 + lane; p < p1 - 1; p += 32) yw[d.Ki[p]] = kval(p, sigma);
-      double dk = dnext;
-      knext = fetch(k + 1, &dnext);
+      if (p0 + lane < p1 - 1) yw[d.Ki[p0 + lane]] = kA;
+      for (int p = p0 + 32 + lane; p < p1 - 1; p += 32) yw[d.Ki[p]] = Kx[p];
+      double dk = dA;
+      kA = kB;
+      dA = dB;
+      kB = fetch(k + 2, &dB);
       __syncwarp();
       const int q0 = d.Sp[k], q1 = d.Sp[k + 1];
       for (int qb = q0; qb < q1; qb += 32) {
@@ -334,6 +339,7 @@ __global__ void __launch_bounds__(32, 8) sparse_team_kernel(const __grid_constan
     p.r3 = Carve(ws, nv);
     p.tz = Carve(ws, nz);
     p.Dinv = Carve(ws, n);
+    p.Kx = Carve(ws, d.nnzK);
     double* sm = dyn_smem;
     p.L = Carve(sm, d.nnzL);
     p.yw = Carve(sm, n);
@@ -352,7 +358,7 @@ size_t SparseTeamSmemBytes(const SparseDev& d) {
 }
 size_t SparseTeamWsDoubles(const SparseDev& d) {
   const size_t vs = (size_t)d.nz + d.nl + 2 * (size_t)d.nv;
-  return 4 * vs + ((size_t)d.nz + d.nl + d.nv) + 4 * (size_t)d.nv + d.nz + d.n;
+  return 4 * vs + ((size_t)d.nz + d.nl + d.nv) + 4 * (size_t)d.nv + d.nz + d.n + d.nnzK;
 }
 
 // Resident single-warp CTAs per SM, 0 when the factor does not fit shared memory
