@@ -8,7 +8,7 @@ set -x
 mkdir -p gpurun_out/traffic
 for c in 2 3a 3b 4a 4a40 4b 5 3a-sparse; do
   timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
-    --clock-control none -k regex:'dense_small_kernel|mpc_lane_kernel|mpc_riccati_kernel|dense_large_kernel|sparse_lane_kernel' \
+    --clock-control none -k regex:'dense_small_kernel|mpc_lane_kernel|mpc_riccati_kernel|dense_large_kernel|sparse_lane_kernel|sparse_team_kernel' \
     --csv --log-file gpurun_out/traffic/$c.csv python tools/prof_config.py $c > gpurun_out/traffic/$c.log 2>&1
 done
 python tools/traffic_json.py gpurun_out/traffic profiles/traffic.json

@@ -18,8 +18,11 @@ done
 SCRIPT=tools/sanitize_mpc.py run "mpc lane kernel" memcheck SANITIZE_LANE=1 FBSTAB_MPC_LANE_MIN=256
 SCRIPT=tools/sanitize_mpc.py run "mpc lane kernel" racecheck SANITIZE_LANE=1 FBSTAB_MPC_LANE_MIN=256
 SCRIPT=tools/sanitize_mpc.py run "mpc lane kernel" synccheck SANITIZE_LANE=1 FBSTAB_MPC_LANE_MIN=256
-SCRIPT=tools/sanitize_sparse.py run "sparse lane kernel" memcheck X=1
-SCRIPT=tools/sanitize_sparse.py run "sparse lane kernel" racecheck X=1
+SCRIPT=tools/sanitize_sparse.py run "sparse lane kernel" memcheck FBSTAB_SPARSE_TEAM=0
+SCRIPT=tools/sanitize_sparse.py run "sparse lane kernel" racecheck FBSTAB_SPARSE_TEAM=0
+SCRIPT=tools/sanitize_sparse.py run "sparse team kernel" memcheck X=1
+SCRIPT=tools/sanitize_sparse.py run "sparse team kernel" racecheck X=1
+SCRIPT=tools/sanitize_sparse.py run "sparse team kernel" synccheck X=1
 SCRIPT=tools/sanitize_dense_large.py run "dense large kernel" memcheck X=1
 SCRIPT=tools/sanitize_dense_large.py run "dense large kernel" racecheck X=1
 cat $OUT | tail -150
