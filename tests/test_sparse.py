@@ -212,6 +212,32 @@ def test_sparse_oracle_on_an_ocp(oracle, fb):
     np.testing.assert_allclose(v, DI2_V, atol=1e-8)
 
 
+def test_sparse_pattern_validation_and_no_cpu_fallback(fb):
+    """The symbolic analysis rejects inconsistent patterns with FBSTAB_ERR_INVALID before
+    any device work; a valid pattern without a GPU fails loudly (no CPU fallback)."""
+    import torch
+    Hp, Hi = np.array([0, 1, 3], np.int32), np.array([0, 0, 1], np.int32)
+    Ap, Ai = np.array([0, 1, 2], np.int32), np.array([0, 1], np.int32)
+    nog = (np.zeros(3, np.int32), np.zeros(0, np.int32))
+    bad = [((Hp, np.array([0, 1, 0], np.int32)) + nog + (Ap, Ai), "strictly increasing"),
+           ((np.array([0, 1, 2], np.int32), np.array([1, 1], np.int32)) + nog + (Ap, Ai),
+            "upper triangle"),
+           ((Hp, Hi) + nog + (Ap, np.array([0, 5], np.int32)), "out of range")]
+    for pat, what in bad:
+        with pytest.raises(fb.FbstabError) as e:
+            fb.FBstabSparse(2, 0, 2, pat)
+        assert e.value.code == fb.capi.ERR_INVALID and what in str(e.value), str(e.value)
+    with pytest.raises(fb.FbstabError) as e:
+        fb.FBstabSparse(2, 0, 2, (Hp, Hi) + nog + (Ap, Ai), perm=[0, 1, 1, 3])
+    assert "permutation" in str(e.value)
+    with pytest.raises(RuntimeError):
+        fb.FBstabSparse(0, 0, 2, (Hp, Hi) + nog + (Ap, Ai))
+    if not torch.cuda.is_available():
+        with pytest.raises(fb.FbstabError) as e:
+            fb.FBstabSparse(2, 0, 2, (Hp, Hi) + nog + (Ap, Ai))
+        assert e.value.code == fb.capi.ERR_NOGPU
+
+
 # ---- GPU: the lane-per-instance CUDA path against the oracle ---------------------------
 def _gpu_solve(fb, nz, nl, nv, pat, vals, B, opts=None, perm=None, x0=None):
     s = fb.FBstabSparse(nz, nl, nv, pat, max_batch=B, perm=perm)
