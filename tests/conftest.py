@@ -24,6 +24,12 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def fb():
+    # (a fresh checkout has no built library: compile it once -- nvcc cross-compiles
+    # without a GPU; the product package itself never builds or falls back)
+    lib = os.path.join(ROOT, "fbstab_b200", "libfbstab_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
     import fbstab_b200
     fbstab_b200.capi.lib()
     return fbstab_b200
