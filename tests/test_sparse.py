@@ -300,6 +300,29 @@ def test_sparse_gpu_parity_with_the_oracle(fb, oracle, monkeypatch, shape, team)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("team", ["1", "0"])
+def test_sparse_gpu_wide_rows(fb, oracle, monkeypatch, team):
+    """A nearly dense pattern: columns of K, rows of the LDL' schedule and columns of L
+    with more than 32 entries (the strided loops of the warp-per-instance kernel)."""
+    monkeypatch.setenv("FBSTAB_SPARSE_TEAM", team)
+    nz, nl, nv, B = 44, 5, 60, 48
+    rng = np.random.default_rng(44)
+    pat, vals, _ = random_sparse_qp(rng, nz, nl, nv, band=nz, count=B)
+    s, out, z, l, v, y = _gpu_solve(fb, nz, nl, nv, pat, vals, B)
+    Lp, Li = s.factor_pattern()
+    assert np.diff(Lp).max() > 32 and np.diff(pat[0]).max() > 32
+    oo, oz, ol, ov, oy = oracle.sparse_solve_batch(
+        nz, nl, nv, pat, [vals[k] for k in ("Hx", "f", "Gx", "h", "Ax", "b")],
+        perm=s.analysis()[3], nthreads=4)
+    assert (out["eflag"] == oo["eflag"]).all() and (out["eflag"] == 0).all()
+    same = (out["newton_iters"] == oo["newton_iters"]) & (out["prox_iters"] == oo["prox_iters"])
+    assert same.mean() >= 0.95
+    for i in np.nonzero(same)[0]:
+        assert rel_err(z[i * nz:(i + 1) * nz], oz[i * nz:(i + 1) * nz]) <= 1e-8
+        assert rel_err(v[i * nv:(i + 1) * nv], ov[i * nv:(i + 1) * nv]) <= 1e-8
+
+
+@pytest.mark.gpu
 def test_sparse_gpu_batch_equals_single_solves_and_device_pointers(fb):
     import torch
     nz, nl, nv, B = 16, 3, 24, 37
