@@ -41,6 +41,7 @@ class ClosedLoopMpc:
         self.N, self.nx, self.nu, self.nc = dims
         self.B = data["x0"].size // self.nx
         self.max_steps = max_steps
+        self.device = device
         self._h = C.c_void_p()
         self._L = _bind(capi.lib())
         keep = [np.ascontiguousarray(data[k], dtype=np.float64) for k in problems.MPC_FIELDS]
@@ -76,8 +77,11 @@ class ClosedLoopMpc:
         ms = None
         if time_it:
             import torch
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s = torch.cuda.current_stream()
+            # (the stream and the events of the solver's OWN device, whatever the current one is)
+            with torch.cuda.device(self.device):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+            s = torch.cuda.current_stream(self.device)
             stream = s.cuda_stream
             # device time of the loop alone: steps only, logs are read afterwards
             capi.check(self._L.fbstab_mpc_closed_loop_reset(self._h, stream))
@@ -85,7 +89,7 @@ class ClosedLoopMpc:
             for _ in range(T):
                 capi.check(self._L.fbstab_mpc_closed_loop_step(self._h, 1 if warm_start else 0, stream))
             e1.record(s)
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(self.device)
             ms = e0.elapsed_time(e1)
         capi.check(self._L.fbstab_mpc_closed_loop_run(self._h, T, 1 if warm_start else 0,
                                                        capi.ptr(X), capi.ptr(U), capi.ptr(out), stream))
