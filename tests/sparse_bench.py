@@ -1,6 +1,6 @@
 """FBstabSparse on an OCP of the reference's generator restated as a GENERAL sparse QP
 (same instances as the MPC configs of bench.py: the plants differ in x0 only), next to
-FBstabMpc on the structured form.  Usage: python tools/time_sparse.py [kind] [N] [batch]"""
+FBstabMpc on the structured form.  Usage: python tests/sparse_bench.py [kind] [N] [batch]"""
 import json
 import os
 import sys
