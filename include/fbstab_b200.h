@@ -6,6 +6,8 @@
  * FBstabMpc -- same names and signatures as the reference) is a thin host
  * layer over these entry points, and INTEGRATION.md shows the binding a
  * maintainer of the reference would add.
+ * (include/fbstab/fbstab_sparse.h, FBstabSparse, is the solver the reference
+ * plans: ROADMAP.md:10.)
  *
  * What each entry point replaces in the reference (paths relative to the
  * reference tree):
@@ -20,6 +22,23 @@
  *                                  fbstab/fbstab_mpc.cc:61-89
  *   fbstab_mpc_batch_solve      <- FBstabMpc::Solve(qp,&x)
  *                                  fbstab/fbstab_mpc.h:181-195
+ *   fbstab_mpc_batch_solve_shared / _lti
+ *                               <- the same with ONE copy of the stage data /
+ *                                  one stage, as CopyOverHorizon replicates it
+ *                                  fbstab/test/ocp_generator.cc:397-418
+ *   fbstab_mpc_closed_loop_*    <- the receding-horizon loop around Solve with
+ *                                  OcpGenerator::GetSimulationInputs
+ *                                  fbstab/test/ocp_generator.h:31-38,69
+ *   fbstab_sparse_batch_create  <- QdldlWrapper::QdldlWrapper(n,Ap,Ai): the
+ *                                  symbolic analysis of the planned sparse
+ *                                  solver, tools/qdldl/qdldl_wrapper.h:24-44
+ *   fbstab_sparse_batch_solve   <- FBstabAlgorithm::Solve over sparse data
+ *                                  with QdldlWrapper::Factor / ::Solve
+ *                                  (qdldl_wrapper.h:46-60; ROADMAP.md:10)
+ *   fbstab_multi_gpu_*, fbstab_*_multi_gpu_solve
+ *                               <- (none: the reference is single-threaded) the
+ *                                  batch sharded by instance over the GPUs of a
+ *                                  box, results gathered with NCCL
  *   fbstab_*_batch_set_options  <- UpdateOptions -> UpdateParameters +
  *                                  ValidateOptions
  *                                  fbstab/fbstab_algorithm-impl.h:7-31,308-332
@@ -41,6 +60,9 @@
  *          `len x rows x cols` contiguous, column-major per matrix
  *          (tools/matrix_sequence.h:81-83); Q,R,S,q,r,E,L,d have N+1 entries,
  *          A,B,c have N; x0(nx).  A batch is instance-major and contiguous.
+ *   sparse: ONE pattern per handle (H by its upper triangle, G, A in
+ *          compressed-column form, as tools/qdldl/qdldl_wrapper.h:12-14), the
+ *          values Hx, Gx, Ax and f, h, b per instance, instance-major.
  *   iterates: z(nz) l(nl) v(nv) y(nv) per instance, instance-major.
  *
  * Every data/iterate pointer may be a HOST pointer or a DEVICE pointer on the
