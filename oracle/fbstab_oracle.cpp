@@ -59,11 +59,23 @@ double norminf(const double* a, int n) {
   return s;
 }
 
+// Grow-only per-thread scratch: the temporaries of the hot loops (Eigen evaluates the
+// same products into preallocated or stack temporaries) cost no heap traffic, so that
+// the port is not a pessimistic CPU baseline.  Slots are not shared between nested
+// callers: 0 gemv_n_acc, 1 LDLT column update, 2 variant-2 row solve, 3 LLT column
+// update, 4-6 MpcData stage temporaries.  Same arithmetic as with local vectors.
+static double* Scratch(int slot, size_t n) {
+  thread_local std::vector<double> buf[8];
+  if (buf[slot].size() < n) buf[slot].resize(n);
+  return buf[slot].data();
+}
+
 // y(rows) += a * M(rows x cols, column-major, leading dim ld) * x(cols)
 void gemv_n_acc(const double* M, int rows, int cols, int ld, const double* x,
                 double a, double* y) {
   if (rows <= 0 || cols <= 0) return;
-  Vec t(rows, 0.0);
+  double* t = Scratch(0, rows);
+  for (int i = 0; i < rows; i++) t[i] = 0.0;
   for (int j = 0; j < cols; j++) {
     const double xj = x[j];
     const double* c = M + (size_t)j * ld;
@@ -190,18 +202,18 @@ struct MpcData : Data {
   void gemvH(const double* x, double a, double bb, double* y) const override {
     scale_by_b(bb, y, nz);
     const int ns = nx + nu;
-    Vec tx(nx), tu(nu);
+    double *tx = Scratch(4, nx), *tu = Scratch(5, nu);
     for (int i = 0; i < N + 1; i++) {
       const double* vx = x + (size_t)i * ns;
       const double* vu = vx + nx;
       double* yx = y + (size_t)i * ns;
       double* yu = yx + nx;
-      std::fill(tx.begin(), tx.end(), 0.0);
-      std::fill(tu.begin(), tu.end(), 0.0);
-      gemv_n_acc(Qi(i), nx, nx, nx, vx, 1.0, tx.data());
-      gemv_t_acc(Si(i), nu, nx, nu, vu, 1.0, tx.data());
-      gemv_n_acc(Si(i), nu, nx, nu, vx, 1.0, tu.data());
-      gemv_n_acc(Ri(i), nu, nu, nu, vu, 1.0, tu.data());
+      std::fill(tx, tx + nx, 0.0);
+      std::fill(tu, tu + nu, 0.0);
+      gemv_n_acc(Qi(i), nx, nx, nx, vx, 1.0, tx);
+      gemv_t_acc(Si(i), nu, nx, nu, vu, 1.0, tx);
+      gemv_n_acc(Si(i), nu, nx, nu, vx, 1.0, tu);
+      gemv_n_acc(Ri(i), nu, nu, nu, vu, 1.0, tu);
       for (int k = 0; k < nx; k++) yx[k] += a * tx[k];
       for (int k = 0; k < nu; k++) yu[k] += a * tu[k];
     }
@@ -589,7 +601,8 @@ struct DenseSolver : LinearSolver {
         k(kk, kk) -= s;
         if (rs > 0) {
           // column-major gemv: accumulate column by column
-          Vec acc(rs, 0.0);
+          double* acc = Scratch(1, rs);
+          for (int i = 0; i < rs; i++) acc[i] = 0.0;
           for (int j = 0; j < kk; j++) {
             const double tj = temp[j];
             for (int i = 0; i < rs; i++) acc[i] += k(kk + 1 + i, j) * tj;
@@ -654,7 +667,7 @@ struct DenseSolver : LinearSolver {
     W.assign((size_t)nl * nz, 0.0);
     for (int r = 0; r < nl; r++) {
       // row r of W: solve LE w' = g_r'
-      Vec w(nz);
+      double* w = Scratch(2, nz);
       for (int j = 0; j < nz; j++) w[j] = data->G[(size_t)j * nl + r];
       for (int j = 0; j < nz; j++) {
         w[j] /= LE[(size_t)j * nz + j];
@@ -868,7 +881,8 @@ bool LltLower(double* M, int m) {
     x = std::sqrt(x);
     M[(size_t)k * m + k] = x;
     if (k > 0 && rs > 0) {
-      Vec acc(rs, 0.0);
+      double* acc = Scratch(3, rs);
+      for (int i = 0; i < rs; i++) acc[i] = 0.0;
       for (int j = 0; j < k; j++) {
         const double a = M[(size_t)j * m + k];
         for (int i = 0; i < rs; i++) acc[i] += M[(size_t)j * m + k + 1 + i] * a;
