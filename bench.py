@@ -21,7 +21,9 @@ and reports them under `per_config` (same keys: value, e2e, roofline, parity):
 A "step" is one complete batched solve of this rank's shard.  With N GPUs every
 rank solves its own shard (instances are independent: no data-path collective)
 and the result rows are gathered to rank 0 by the library's NCCL gather
-(fbstab_multi_gpu_gather) inside the timed region.  `--scaling weak` keeps the
+(fbstab_multi_gpu_gather) inside the timed region -- on a second, high-priority
+stream, so that the gather of step s overlaps the solve of step s+1 (the result
+buffers are double-buffered; the region ends after the last gather).  `--scaling weak` keeps the
 per-GPU batch fixed, `strong` shards the config's batch; default: weak for
 configs 2-4, strong for config 5, as BASELINE.json words them.
 
@@ -447,20 +449,38 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
     solver = wl.solver(fb, max(B, 1), local_rank)
     f64 = lambda n: torch.zeros(n, dtype=torch.float64, device=dev)
     u8 = lambda n: torch.zeros(n, dtype=torch.uint8, device=dev)
-    # rank 0 solves straight into its rows of the global arrays; the gather fills the rest
-    if world > 1 and rank == 0:
-        full = (f64(global_batch * nz), f64(global_batch * nl), f64(global_batch * nv),
-                f64(global_batch * nv), u8(global_batch * fb.OUT_DTYPE.itemsize))
-        sl = lambda t, w: t[first * w:(first + B) * w]
-        z, l, v, y = sl(full[0], nz), sl(full[1], nl), sl(full[2], nv), sl(full[3], nv)
-        out = sl(full[4], fb.OUT_DTYPE.itemsize)
-    else:
-        full = None
-        z, l, v, y = f64(B * nz), f64(B * nl), f64(B * nv), f64(B * nv)
-        out = u8(B * fb.OUT_DTYPE.itemsize)
+    # rank 0 solves straight into its rows of the global arrays; the gather fills the rest.
+    # With several ranks the result buffers are DOUBLE-BUFFERED: the gather of step s runs
+    # on a second, high-priority stream while step s+1 solves into the other set (the
+    # collective overlaps the next batch's compute; every gather completes inside the
+    # timed region, which ends only after the main stream has waited for the gather
+    # stream).
+    nset = 2 if world > 1 else 1
+    sets = []
+    for _ in range(nset):
+        if world > 1 and rank == 0:
+            full = (f64(global_batch * nz), f64(global_batch * nl), f64(global_batch * nv),
+                    f64(global_batch * nv), u8(global_batch * fb.OUT_DTYPE.itemsize))
+            sl = lambda t, w, full=full: t[first * w:(first + B) * w]
+            bufs = (sl(full[0], nz), sl(full[1], nl), sl(full[2], nv), sl(full[3], nv),
+                    sl(full[4], fb.OUT_DTYPE.itemsize))
+        else:
+            full = None
+            bufs = (f64(B * nz), f64(B * nl), f64(B * nv), f64(B * nv),
+                    u8(B * fb.OUT_DTYPE.itemsize))
+        sets.append((bufs, full))
     stream = torch.cuda.current_stream()
+    gstream = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    solved = [torch.cuda.Event() for _ in range(nset)]
+    gathered = [torch.cuda.Event() for _ in range(nset)]
+    state = {"step": 0, "pending": [False] * nset}
 
     def step_device(ev0=None, ev1=None):
+        k = state["step"] % nset
+        state["step"] += 1
+        (z, l, v, y, out), full = sets[k]
+        if state["pending"][k]:  # the gather that last read this set has to be done
+            stream.wait_event(gathered[k])
         z.zero_(), l.zero_(), v.zero_()  # cold start
         if ev0 is not None:
             ev0.record(stream)
@@ -469,8 +489,15 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
         if ev1 is not None:
             ev1.record(stream)
         if world > 1:  # result gather to rank 0 (the only collective on the path)
-            mg.gather(global_batch if scaling == "strong" else global_batch, (nz, nl, nv),
-                      (z, l, v, y, out), full, root=0, stream=stream.cuda_stream)
+            solved[k].record(stream)
+            gstream.wait_event(solved[k])
+            mg.gather(global_batch, (nz, nl, nv), (z, l, v, y, out), full, root=0,
+                      stream=gstream.cuda_stream)
+            gathered[k].record(gstream)
+            state["pending"][k] = True
+
+    def last_set():
+        return sets[(state["step"] - 1) % nset]
 
     def barrier():
         if world > 1:
@@ -489,6 +516,8 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
     e0.record(stream)
     for s in range(K):
         step_device(ker0[s], ker1[s])
+    if gstream is not None:
+        stream.wait_stream(gstream)  # the timed region ends after the last gather
     e1.record(stream)
     barrier()
     clocks = sampler.summary()
@@ -501,6 +530,7 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
     value = global_batch * K / (ms_total * 1e-3)
     launches = K * solver.last_launches
 
+    (z, l, v, y, out), full = last_set()
     o = np.frombuffer(out.cpu().numpy().tobytes(), dtype=fb.OUT_DTYPE)
     res = {"value": value, "ms_per_step": ms_total / K, "kernel_ms": kernel_ms, "clocks": clocks,
            "launches": int(launches), "B": B, "global_batch": global_batch, "path": solver.path,
@@ -805,6 +835,11 @@ def main():
         }
         if "gather_identical" in head:
             line["results"]["gather_identical"] = head["gather_identical"]
+        if world > 1:
+            line["results"]["gather"] = (
+                "NCCL gather of every step's results to rank 0 inside the timed region, on a "
+                "high-priority stream: it overlaps the next step's solve (double-buffered "
+                "result arrays); the region ends after the last gather")
         _emit(line)
     if mg is not None:
         mg.close()
