@@ -420,7 +420,7 @@ def trajectory_floor(wl):
     family (tests/golden/trajectory_floor.json): the floor for any implementation."""
     key = {"2": "dense_32_8_64", "3a": "servo_motor_N50", "3b": "double_integrator_N50",
            "4a40": "spacecraft_N40", "4b": "copolymerization_N100",
-           "5": "dense_512_128_1024"}.get(wl.name)
+           "5": "dense_512_128_1024", "3a-sparse": "servo_motor_N50_sparse"}.get(wl.name)
     try:
         with open(os.path.join(ROOT, "tests", "golden", "trajectory_floor.json")) as fh:
             return json.load(fh)["families"][key]["same_trajectory_frac"]

@@ -36,7 +36,7 @@ SYMBOLS = [
     "fbstab_sparse_batch_set_options", "fbstab_sparse_batch_get_options",
     "fbstab_sparse_batch_solve", "fbstab_sparse_batch_last_launches",
     "fbstab_sparse_batch_path", "fbstab_sparse_batch_analysis",
-    "fbstab_sparse_batch_factor_pattern",
+    "fbstab_sparse_batch_factor_pattern", "fbstab_sparse_analyze",
     "fbstab_mpc_closed_loop_create", "fbstab_mpc_closed_loop_destroy",
     "fbstab_mpc_closed_loop_set_options", "fbstab_mpc_closed_loop_reset",
     "fbstab_mpc_closed_loop_step", "fbstab_mpc_closed_loop_run",
@@ -136,6 +136,7 @@ def lib():
             [C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_void_p, C.c_void_p])
         L.fbstab_sparse_batch_analysis.argtypes = [C.c_void_p, ip, ip, ip, C.c_void_p]
         L.fbstab_sparse_batch_factor_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fbstab_sparse_analyze.argtypes = ([C.c_int] * 3 + [C.c_void_p] * 7 + [ip, ip, ip, C.c_void_p])
         L.fbstab_ocp_dims.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 3
         L.fbstab_ocp_generate.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 12
         L.fbstab_ocp_generate_batch.argtypes = (

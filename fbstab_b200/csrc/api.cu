@@ -1473,6 +1473,23 @@ int fbstab_sparse_batch_analysis(const fbstab_sparse_batch* h, int* n, int* nnzK
   return FBSTAB_OK;
 }
 
+// Host only (no device is touched): the symbolic analysis fbstab_sparse_batch_create
+// would run for this pattern.
+int fbstab_sparse_analyze(int nz, int nl, int nv, const int* Hp, const int* Hi, const int* Gp,
+                          const int* Gi, const int* Ap, const int* Ai, const int* user_perm,
+                          int* n, int* nnzK, int* nnzL, int* perm) {
+  if (nz <= 0 || nl < 0 || nv <= 0 || !Hp || !Hi || !Ap || !Ai || (nl > 0 && !Gp))
+    return Fail(FBSTAB_ERR_INVALID, "In FBstabSparse::FBstabSparse: invalid sizes or null pattern");
+  fbs::SparsePattern pat;
+  if (!fbs::SparseAnalyze(nz, nl, nv, Hp, Hi, Gp, Gi, Ap, Ai, user_perm, &pat))
+    return Fail(FBSTAB_ERR_INVALID, pat.error.c_str());
+  if (n) *n = pat.n;
+  if (nnzK) *nnzK = pat.nnzK;
+  if (nnzL) *nnzL = pat.nnzL;
+  if (perm) std::copy(pat.perm.begin(), pat.perm.end(), perm);
+  return FBSTAB_OK;
+}
+
 int fbstab_sparse_batch_factor_pattern(const fbstab_sparse_batch* h, int* Lp, int* Li) {
   if (!h) return Fail(FBSTAB_ERR_INVALID, "null handle");
   if (Lp) std::copy(h->pat.Lp.begin(), h->pat.Lp.end(), Lp);

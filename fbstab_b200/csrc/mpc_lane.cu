@@ -87,8 +87,46 @@ constexpr int kLaneWarpsPerCta = 4;
 // RECIPROCAL of their diagonal in the diagonal slot, so that the ~40 dependent
 // divisions per stage of the triangular solves become multiplications (an FP64
 // division is a ~100-cycle dependent chain; a straggler instance runs its
-// stages strictly one after the other).  Results differ from the dividing
-// kernels by rounding only.
+// stages strictly one after the other).
+//
+// Which reciprocal matters for parity (profiles/r2_lane_diag_ab.txt, cfg 3a, 2,048 servo
+// instances against the oracle; the oracle's own FMA on/off floor is 97.6 %):
+//   FBSTAB_LANE_DIAG=0  rsqrt(x), multiply           255 k solves/s   95.7 % same trajectory
+//                       (and one-sided: 69 of the 89 other instances end one Newton step EARLY)
+//   FBSTAB_LANE_DIAG=1  sqrt(x), divide (the CPU reference's operation sequence, Eigen's
+//                       unblocked llt_inplace)        122 k            97.9 %
+//   FBSTAB_LANE_DIAG=2  1 / sqrt(x), both correctly rounded, multiply   (default)
+//                                                     252 k            97.9 %
+//   FBSTAB_LANE_DIAG=3  rsqrt(x) + one Newton step, multiply
+//                                                     257 k            94.7 %
+// The reciprocal of the ROUNDED square root -- the number the reference divides by -- keeps
+// the factor consistent with the reference's; the better approximation of x^-1/2 does not.
+#ifndef FBSTAB_LANE_DIAG
+#define FBSTAB_LANE_DIAG 2
+#endif
+// x scaled by the inverse of a factor's diagonal entry d (the diagonal slot holds 1/d,
+// or d itself under FBSTAB_LANE_DIAG=1)
+__device__ __forceinline__ double by_diag(double x, double slot) {
+#if FBSTAB_LANE_DIAG == 1
+  return x / slot;
+#else
+  return x * slot;
+#endif
+}
+// the diagonal slot of sqrt(x)
+__device__ __forceinline__ double diag_slot(double x) {
+#if FBSTAB_LANE_DIAG == 1
+  return sqrt(x);
+#elif FBSTAB_LANE_DIAG == 2
+  return 1.0 / sqrt(x);
+#elif FBSTAB_LANE_DIAG == 3
+  const double r = rsqrt(x);  // r (1 + (1 - x r^2) / 2)
+  const double e = fma(-(x * r), r, 1.0);
+  return fma(0.5 * r, e, r);
+#else
+  return rsqrt(x);  // MUFU.RSQ64H + Newton: a third of the sqrt + division chain
+#endif
+}
 template <int M>
 __device__ __forceinline__ bool chol(double (&A)[M][M]) {
   bool ok = true;
@@ -99,24 +137,24 @@ __device__ __forceinline__ bool chol(double (&A)[M][M]) {
     for (int j = 0; j < k; j++) s = fma(A[k][j], A[k][j], s);
     double x = A[k][k] - s;
     if (!(x > 0.0)) ok = false;
-    const double rx = rsqrt(x);  // MUFU.RSQ64H + Newton: a third of the sqrt + division chain
+    const double rx = diag_slot(x);
 #pragma unroll
     for (int i = k + 1; i < M; i++) {
       double a = 0.0;
 #pragma unroll
       for (int j = 0; j < k; j++) a = fma(A[i][j], A[k][j], a);
-      A[i][k] = (A[i][k] - a) * rx;
+      A[i][k] = by_diag(A[i][k] - a, rx);
     }
-    A[k][k] = rx;  // reciprocal diagonal
+    A[k][k] = rx;  // diagonal slot
   }
   return ok;
 }
-// y = L^-1 x (x destroyed); L carries reciprocal diagonals
+// y = L^-1 x (x destroyed); L carries diagonal slots
 template <int M>
 __device__ __forceinline__ void trsv_l(const double (&L)[M][M], double (&x)[M], double (&y)[M]) {
 #pragma unroll
   for (int j = 0; j < M; j++) {
-    const double xj = x[j] * L[j][j];
+    const double xj = by_diag(x[j], L[j][j]);
     y[j] = xj;
 #pragma unroll
     for (int i = j + 1; i < M; i++) x[i] = fma(-L[i][j], xj, x[i]);
@@ -127,7 +165,7 @@ template <int M>
 __device__ __forceinline__ void trsv_lt(const double (&L)[M][M], double (&x)[M], double (&y)[M]) {
 #pragma unroll
   for (int i = M - 1; i >= 0; i--) {
-    const double xi = x[i] * L[i][i];
+    const double xi = by_diag(x[i], L[i][i]);
     y[i] = xi;
 #pragma unroll
     for (int r = 0; r < i; r++) x[r] = fma(-L[i][r], xi, x[r]);
@@ -142,7 +180,7 @@ __device__ __forceinline__ void row_trsm_lt(const double (&L)[M][M], const doubl
     double s = src[j];
 #pragma unroll
     for (int k = 0; k < j; k++) s = fma(-X[k], L[j][k], s);
-    X[j] = s * L[j][j];
+    X[j] = by_diag(s, L[j][j]);
   }
 }
 
@@ -610,7 +648,11 @@ struct Lane {
                          bool any_commit) {
     bool ok = true;
     double Lc[NX][NX];
+#if FBSTAB_LANE_DIAG == 1
+    const double rs = sqrt(sigma);  // diagonal slot of L(0) = sqrt(sigma) I
+#else
     const double rs = 1.0 / sqrt(sigma);  // reciprocal diagonal of L(0) = sqrt(sigma) I
+#endif
 #pragma unroll
     for (int a_ = 0; a_ < NX; a_++)
 #pragma unroll
@@ -697,7 +739,7 @@ struct Lane {
         for (int k = 0; k < NX; k++) w[k] = (k == cc) ? 1.0 : 0.0;
 #pragma unroll
         for (int j = 0; j < NX; j++) {
-          w[j] *= Lc[j][j];
+          w[j] = by_diag(w[j], Lc[j][j]);
           const double wj = w[j];
 #pragma unroll
           for (int k = j + 1; k < NX; k++) w[k] = fma(-Lc[k][j], wj, w[k]);
@@ -707,7 +749,7 @@ struct Lane {
           double sv = w[k];
 #pragma unroll
           for (int j = k + 1; j < NX; j++) sv = fma(-Lc[j][k], w[j], sv);
-          w[k] = sv * Lc[k][k];
+          w[k] = by_diag(sv, Lc[k][k]);
         }
 #pragma unroll
         for (int rr = cc; rr < NX; rr++) Mm[rr][cc] = w[rr];

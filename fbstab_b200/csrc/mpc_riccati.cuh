@@ -19,6 +19,15 @@
 #include "mpc_riccati.h"
 #include "tma.cuh"
 
+// Diagonal slot of the warp-wide Cholesky: 0 = rsqrt(x) (rounds 1-2), 1 = 1 / sqrt(x) with
+// both operations correctly rounded -- the reciprocal of the number the reference divides
+// by; see FBSTAB_LANE_DIAG in mpc_lane.cu and profiles/r2_lane_diag_ab.txt: on the servo
+// problem 94.9 % -> 97.9 % of the instances on the oracle's trajectory (its own FMA on/off
+// floor: 97.6 %) for 4 % of throughput (cfg 4a40 18.8 k -> 18.0 k, cfg 4b 15.0 k -> 14.5 k).
+#ifndef FBSTAB_CTA_DIAG
+#define FBSTAB_CTA_DIAG 1
+#endif
+
 namespace fbs {
 
 // ---- small dense helpers (column-major, ld = rows), team-cooperative -------
@@ -53,7 +62,11 @@ __device__ __forceinline__ bool team_chol(const Team& t, int T, double* M, int m
           for (int j = 0; j < k; j++) a = fma(M[lane + j * m], M[k + j * m], a);
         const double x = __shfl_sync(0xffffffffu, diag, k);
         if (!(x > 0.0)) ok = false;
+#if FBSTAB_CTA_DIAG == 0
         const double rx = rsqrt(x);
+#else
+        const double rx = 1.0 / sqrt(x);  // as the lane kernel (FBSTAB_LANE_DIAG, mpc_lane.cu)
+#endif
         if (lane > k && lane < m) {
           const double l = (M[lane + k * m] - a) * rx;
           M[lane + k * m] = l;

@@ -288,6 +288,21 @@ class FBstabSparse(_Base):
             capi.ptr(Gi) if nl > 0 and Gi.size else None, capi.ptr(Ap), capi.ptr(Ai),
             capi.ptr(pm), max_batch, device, C.byref(self._h)))
 
+    @staticmethod
+    def analyze(nz, nl, nv, pattern, perm=None):
+        """(n, nnz(K), nnz(L), perm) of the symbolic analysis the constructor would run for
+        this pattern -- host only, no device needed (fbstab_sparse_analyze)."""
+        ia = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1))
+        Hp, Hi, Gp, Gi, Ap, Ai = (ia(a) for a in pattern)
+        pm = ia(perm) if perm is not None else None
+        n, k, l = C.c_int(), C.c_int(), C.c_int()
+        out = np.zeros(nz + nl + nv, dtype=np.int32)
+        capi.check(capi.lib().fbstab_sparse_analyze(
+            nz, nl, nv, capi.ptr(Hp), capi.ptr(Hi), capi.ptr(Gp) if nl > 0 else None,
+            capi.ptr(Gi) if nl > 0 and Gi.size else None, capi.ptr(Ap), capi.ptr(Ai),
+            capi.ptr(pm), C.byref(n), C.byref(k), C.byref(l), capi.ptr(out)))
+        return n.value, k.value, l.value, out
+
     def analysis(self):
         """(n, nnz(K), nnz(L), perm) of the symbolic analysis; perm[new] = old over [z; l; w]."""
         n, k, l = C.c_int(), C.c_int(), C.c_int()

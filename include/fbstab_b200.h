@@ -282,6 +282,13 @@ const char* fbstab_sparse_batch_path(const fbstab_sparse_batch* handle);
  * (perm != NULL) the elimination order in use.  Any pointer may be NULL. */
 int fbstab_sparse_batch_analysis(const fbstab_sparse_batch* handle, int* n, int* nnzK,
                                  int* nnzL, int* perm);
+/* The same analysis without a handle and without a device (host only): what
+ * QdldlWrapper's constructor computes from (n, Ap, Ai) before any numeric work
+ * (tools/qdldl/qdldl_wrapper.h:33-40).  user_perm as in fbstab_sparse_batch_create
+ * (NULL: the built-in minimum-degree order); any output pointer may be NULL. */
+int fbstab_sparse_analyze(int nz, int nl, int nv, const int* Hp, const int* Hi,
+                          const int* Gp, const int* Gi, const int* Ap, const int* Ai,
+                          const int* user_perm, int* n, int* nnzK, int* nnzL, int* perm);
 /* The pattern of the factor L of the permuted Newton matrix (strictly lower triangle,
  * compressed columns: Lp n+1 entries, Li nnzL entries) -- what QdldlWrapper keeps in
  * Lp_ / Li_ (tools/qdldl/qdldl_wrapper.h:70-73).  Either pointer may be NULL. */

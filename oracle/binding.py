@@ -80,6 +80,10 @@ def fma_lib():
         L.oracle_mpc_solve_batch.argtypes = (
             [C.c_int] * 5 + [_dp] * 16 + [C.POINTER(Options), C.c_void_p,
                                           C.c_int])
+        _ip = C.POINTER(C.c_int)
+        L.oracle_sparse_solve_batch.argtypes = (
+            [C.c_int] * 4 + [_ip, _ip, _dp, _dp] * 3 + [_ip] + [_dp] * 4 +
+            [C.POINTER(Options), C.c_void_p, C.c_int])
         _fma_lib = L
     return _fma_lib
 
@@ -357,7 +361,8 @@ def qdldl_solve(n, Ap, Ai, Ax, b):
     return rc, x
 
 
-def sparse_solve_batch(nz, nl, nv, pattern, vals, perm=None, opts=None, x0=None, nthreads=1):
+def sparse_solve_batch(nz, nl, nv, pattern, vals, perm=None, opts=None, x0=None, nthreads=1,
+                       fma=False):
     """pattern = (Hp,Hi,Gp,Gi,Ap,Ai) int32; vals = (Hx,f,Gx,h,Ax,b) instance-major."""
     if opts is None:
         opts = default_options()
@@ -372,7 +377,7 @@ def sparse_solve_batch(nz, nl, nv, pattern, vals, perm=None, opts=None, x0=None,
     y = np.zeros(batch * nv)
     out = np.zeros(batch, dtype=OUT_DTYPE)
     pm = np.ascontiguousarray(np.asarray(perm, dtype=np.int32)) if perm is not None else None
-    lib().oracle_sparse_solve_batch(
+    (fma_lib() if fma else lib()).oracle_sparse_solve_batch(
         nz, nl, nv, batch, _ip(Hp), _ip(Hi), _p(Hx), _p(f), _ip(Gp), _ip(Gi), _p(Gx), _p(h),
         _ip(Ap), _ip(Ai), _p(Ax), _p(b), _ip(pm), _p(z), _p(l), _p(v), _p(y), C.byref(opts),
         out.ctypes.data, nthreads)

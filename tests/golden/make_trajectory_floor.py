@@ -30,6 +30,9 @@ FAMILIES = {
     "double_integrator_N50": ("mpc", ("double_integrator", 50), 2048, 3, -0.1),
     "spacecraft_N40": ("mpc", ("spacecraft", 40), 256, 4, 0.01),
     "copolymerization_N100": ("mpc", ("copolymerization", 100), 256, 4, 0.05),
+    # the servo instances restated as general sparse QPs (bench.py config 3a-sparse); both
+    # builds eliminate in the order the engine's symbolic analysis chooses (host only)
+    "servo_motor_N50_sparse": ("sparse", ("servo_motor", 50), 512, 3, 0.02),
 }
 
 
@@ -44,6 +47,15 @@ def measure(name, threads=8, count=None):
         args = [d[k] for k in fb.problems.DENSE_FIELDS]
         a = ob.dense_solve_batch(nz, nl, nv, *args, nthreads=threads)
         b = ob.dense_solve_batch(nz, nl, nv, *args, nthreads=threads, fma=True)
+        width = nz
+    elif kind == "sparse":
+        ocp, N = spec
+        dims, d = fb.problems.ocp_batch(ocp, N, count=n, config=cfg, rho=rho)
+        (nz, nl, nv), pat, vals = fb.problems.ocp_as_sparse_qp(dims, d, n)
+        perm = fb.FBstabSparse.analyze(nz, nl, nv, pat)[3]
+        V = [vals[k] for k in fb.problems.SPARSE_FIELDS]
+        a = ob.sparse_solve_batch(nz, nl, nv, pat, V, perm=perm, nthreads=threads)
+        b = ob.sparse_solve_batch(nz, nl, nv, pat, V, perm=perm, nthreads=threads, fma=True)
         width = nz
     else:
         ocp, N = spec

@@ -11,8 +11,8 @@ threshold, the tests take their threshold from a MEASURED floor: two builds of
 the oracle itself, without and with FMA contraction, on the same instances
 (tests/golden/trajectory_floor.json, tests/test_oracle_fma_floor.py: 100% of the
 dense 32/8/64 and double-integrator families, 97.6% of servo-motor instances).
-`required_same_frac` allows twice the floor rate (two perturbation sources: FMA and
-summation order) plus the sampling margin; off-trajectory
+`required_same_frac` demands the floor's own rate, less the sampling margin of the
+batch; off-trajectory
 instances must still agree to 1e-5 (the two oracle builds differ by up to
 3.6e-6 there) and by at most 2 Newton iterations.
 """
