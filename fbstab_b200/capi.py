@@ -47,6 +47,8 @@ SYMBOLS = [
     "fbstab_dense_multi_gpu_set_options", "fbstab_dense_multi_gpu_solve",
     "fbstab_mpc_multi_gpu_create", "fbstab_mpc_multi_gpu_destroy",
     "fbstab_mpc_multi_gpu_set_options", "fbstab_mpc_multi_gpu_solve",
+    "fbstab_sparse_multi_gpu_create", "fbstab_sparse_multi_gpu_destroy",
+    "fbstab_sparse_multi_gpu_set_options", "fbstab_sparse_multi_gpu_solve",
     "fbstab_ocp_dims", "fbstab_ocp_generate", "fbstab_ocp_generate_batch",
     "fbstab_ocp_simulation",
     "fbstab_random_dense_qp", "fbstab_fp64_peak",

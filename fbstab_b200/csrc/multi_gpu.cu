@@ -263,6 +263,14 @@ struct fbstab_mpc_multi_gpu {
   long max_batch = 0;
 };
 
+struct fbstab_sparse_multi_gpu {
+  int nz = 0, nl = 0, nv = 0;
+  size_t nnzH = 0, nnzG = 0, nnzA = 0;
+  std::vector<int> devices;
+  std::vector<fbstab_sparse_batch*> shards;
+  long max_batch = 0;
+};
+
 static int CheckDevices(int ndev, const int* devices) {
   if (ndev < 1 || !devices) return Fail(FBSTAB_ERR_INVALID, "empty device list");
   const int have = fbstab_device_count();
@@ -426,6 +434,92 @@ int fbstab_mpc_multi_gpu_solve(fbstab_mpc_multi_gpu* h, long batch, const double
           B + o * N * nx * nu, c + o * N * nx, E + o * K * nc * nx, L + o * K * nc * nu,
           d + o * K * nc, x0 + o * nx, z + o * nz, l + o * nl, v + o * nv, y + o * nv, out + o,
           nullptr);
+      if (rcs[i]) errs[i] = fbstab_last_error();
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < nd; i++)
+    if (rcs[i]) return Fail(rcs[i], "device " + std::to_string(h->devices[i]) + ": " + errs[i]);
+  return FBSTAB_OK;
+}
+
+int fbstab_sparse_multi_gpu_create(int ndev, const int* devices, int nz, int nl, int nv,
+                                   const int* Hp, const int* Hi, const int* Gp, const int* Gi,
+                                   const int* Ap, const int* Ai, const int* perm,
+                                   long max_batch, fbstab_sparse_multi_gpu** handle) {
+  if (!handle) return Fail(FBSTAB_ERR_INVALID, "null handle pointer");
+  *handle = nullptr;
+  int rc = CheckDevices(ndev, devices);
+  if (rc) return rc;
+  if (max_batch < 1) return Fail(FBSTAB_ERR_INVALID, "max_batch must be >= 1");
+  if (nz <= 0 || !Hp || !Ap || (nl > 0 && !Gp))
+    return Fail(FBSTAB_ERR_INVALID, "In FBstabSparse::FBstabSparse: invalid sizes or null pattern");
+  auto* h = new fbstab_sparse_multi_gpu;
+  h->nz = nz;
+  h->nl = nl;
+  h->nv = nv;
+  h->nnzH = (size_t)Hp[nz];
+  h->nnzG = nl > 0 ? (size_t)Gp[nz] : 0;
+  h->nnzA = (size_t)Ap[nz];
+  h->max_batch = max_batch;
+  h->devices.assign(devices, devices + ndev);
+  for (int i = 0; i < ndev; i++) {
+    long first, count;
+    ShardRange(ndev, i, max_batch, &first, &count);
+    fbstab_sparse_batch* s = nullptr;
+    // every shard runs the same symbolic analysis: same elimination order on every device
+    rc = fbstab_sparse_batch_create(nz, nl, nv, Hp, Hi, Gp, Gi, Ap, Ai, perm,
+                                    (int)std::max<long>(count, 1), devices[i], &s);
+    if (rc) {
+      for (auto* p : h->shards) fbstab_sparse_batch_destroy(p);
+      delete h;
+      return rc;
+    }
+    h->shards.push_back(s);
+  }
+  *handle = h;
+  return FBSTAB_OK;
+}
+
+int fbstab_sparse_multi_gpu_destroy(fbstab_sparse_multi_gpu* h) {
+  if (!h) return FBSTAB_OK;
+  for (auto* p : h->shards) fbstab_sparse_batch_destroy(p);
+  delete h;
+  return FBSTAB_OK;
+}
+
+int fbstab_sparse_multi_gpu_set_options(fbstab_sparse_multi_gpu* h, const fbstab_options* o) {
+  if (!h || !o) return Fail(FBSTAB_ERR_INVALID, "null argument");
+  for (auto* p : h->shards) {
+    int rc = fbstab_sparse_batch_set_options(p, o);
+    if (rc) return rc;
+  }
+  return FBSTAB_OK;
+}
+
+int fbstab_sparse_multi_gpu_solve(fbstab_sparse_multi_gpu* h, long batch, const double* Hx,
+                                  const double* f, const double* Gx, const double* hh,
+                                  const double* Ax, const double* b, double* z, double* l,
+                                  double* v, double* y, fbstab_out* out) {
+  if (!h) return Fail(FBSTAB_ERR_INVALID, "null handle");
+  if (batch < 0 || batch > h->max_batch)
+    return Fail(FBSTAB_ERR_INVALID, "batch exceeds the handle's max_batch");
+  const int nd = (int)h->shards.size();
+  const size_t nz = h->nz, nl = h->nl, nv = h->nv;
+  const size_t nH = h->nnzH, nG = h->nnzG, nA = h->nnzA;
+  std::vector<int> rcs(nd, FBSTAB_OK);
+  std::vector<std::string> errs(nd);
+  std::vector<std::thread> th;
+  for (int i = 0; i < nd; i++) {
+    long first, count;
+    ShardRange(nd, i, batch, &first, &count);
+    if (count == 0) continue;
+    th.emplace_back([=, &rcs, &errs] {
+      const size_t o = (size_t)first;
+      rcs[i] = fbstab_sparse_batch_solve(
+          h->shards[i], (int)count, Hx + o * nH, f + o * nz, Gx ? Gx + o * nG : Gx,
+          hh ? hh + o * nl : hh, Ax + o * nA, b + o * nv, z + o * nz, l ? l + o * nl : l,
+          v + o * nv, y + o * nv, out + o, nullptr);
       if (rcs[i]) errs[i] = fbstab_last_error();
     });
   }

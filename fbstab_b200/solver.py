@@ -288,6 +288,44 @@ class FBstabSparse(_Base):
             capi.ptr(Gi) if nl > 0 and Gi.size else None, capi.ptr(Ap), capi.ptr(Ai),
             capi.ptr(pm), max_batch, device, C.byref(self._h)))
 
+    def solve_batch_devices(self, data, z, l, v, devices, perm=None):
+        """The batch cut into contiguous ranges over several GPUs of this box, one host
+        thread and one engine handle per device (fbstab_sparse_multi_gpu_solve): HOST
+        arrays only; returns (out, y) like solve_batch, identical byte for byte."""
+        L = capi.lib()
+        L.fbstab_sparse_multi_gpu_create.argtypes = (
+            [C.c_int, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p] * 7 +
+            [C.c_long, C.POINTER(C.c_void_p)])
+        L.fbstab_sparse_multi_gpu_solve.argtypes = [C.c_void_p, C.c_long] + [C.c_void_p] * 11
+        L.fbstab_sparse_multi_gpu_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+        L.fbstab_sparse_multi_gpu_destroy.argtypes = [C.c_void_p]
+        if not all(_is_host(a) for a in (z, l, v)):
+            raise RuntimeError("solve_batch_devices takes host arrays")
+        batch = z.size // self.nz
+        Hp, Hi, Gp, Gi, Ap, Ai = self.pattern
+        pm = np.ascontiguousarray(np.asarray(perm, dtype=np.int32)) if perm is not None else None
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        capi.check(L.fbstab_sparse_multi_gpu_create(
+            len(devices), devs, self.nz, self.nl, self.nv, capi.ptr(Hp), capi.ptr(Hi),
+            capi.ptr(Gp) if self.nl > 0 else None,
+            capi.ptr(Gi) if self.nl > 0 and Gi.size else None, capi.ptr(Ap), capi.ptr(Ai),
+            capi.ptr(pm), max(batch, 1), C.byref(h)))
+        try:
+            if getattr(self, "opts", None) is not None:
+                capi.check(L.fbstab_sparse_multi_gpu_set_options(h, C.byref(self.opts)))
+            y = np.zeros(batch * self.nv)
+            out = np.zeros(batch, dtype=OUT_DTYPE)
+            capi.check(L.fbstab_sparse_multi_gpu_solve(
+                h, batch, *[capi.ptr(_flat(data[k], batch * self.field_sizes[k], k, None))
+                            for k in self._fields],
+                capi.ptr(_flat(z, batch * self.nz, "z", None)),
+                capi.ptr(_flat(l, batch * self.nl, "l", None)),
+                capi.ptr(_flat(v, batch * self.nv, "v", None)), capi.ptr(y), capi.ptr(out)))
+        finally:
+            L.fbstab_sparse_multi_gpu_destroy(h)
+        return out, y
+
     @staticmethod
     def analyze(nz, nl, nv, pattern, perm=None):
         """(n, nnz(K), nnz(L), perm) of the symbolic analysis the constructor would run for

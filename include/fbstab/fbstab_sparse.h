@@ -73,7 +73,8 @@ class FBstabSparse {
    */
   FBstabSparse(const SparsePattern& H, const SparsePattern& G, const SparsePattern& A,
                int max_batch = 1, int device = 0)
-      : nz_(H.cols), nl_(G.rows), nv_(A.rows), nnzH_(H.nnz()), nnzG_(G.nnz()), nnzA_(A.nnz()) {
+      : nz_(H.cols), nl_(G.rows), nv_(A.rows), nnzH_(H.nnz()), nnzG_(G.nnz()), nnzA_(A.nnz()),
+        H_(H), G_(G), A_(A) {
     if (nz_ <= 0 || nl_ < 0 || nv_ <= 0)
       throw std::runtime_error("In FBstabSparse::FBstabSparse: Inputs must be positive.");
     if (H.rows != nz_ || (int)H.p.size() != nz_ + 1 || (int)H.i.size() != nnzH_)
@@ -133,6 +134,36 @@ class FBstabSparse {
     return res;
   }
 
+  /**
+   * The same batch on several GPUs of this box (cf. FBstabDense::SolveBatch(..., devices)):
+   * contiguous instance ranges, one host thread and one engine handle per device, every
+   * device with the same elimination order (fbstab_sparse_multi_gpu_solve).  HOST pointers
+   * only; `devices`: CUDA ordinals, no duplicates.
+   */
+  std::vector<SolverOut> SolveBatch(int batch, const double* Hx, const double* f,
+                                    const double* Gx, const double* h, const double* Ax,
+                                    const double* b, double* z, double* l, double* v,
+                                    double* y, const std::vector<int>& devices) {
+    fbstab_sparse_multi_gpu* m = nullptr;
+    detail::Check(fbstab_sparse_multi_gpu_create(
+                      (int)devices.size(), devices.data(), nz_, nl_, nv_, H_.p.data(),
+                      H_.i.data(), nl_ > 0 ? G_.p.data() : nullptr,
+                      nl_ > 0 ? G_.i.data() : nullptr, A_.p.data(), A_.i.data(), nullptr,
+                      batch > 0 ? batch : 1, &m),
+                  "FBstabSparse::SolveBatch");
+    std::unique_ptr<fbstab_sparse_multi_gpu, DestroyMulti> guard(m);
+    fbstab_options o = opts_.ToC();
+    detail::Check(fbstab_sparse_multi_gpu_set_options(m, &o), "FBstabSparse::SolveBatch");
+    std::vector<fbstab_out> out((size_t)(batch > 0 ? batch : 0));
+    detail::Check(fbstab_sparse_multi_gpu_solve(m, batch, Hx, f, Gx, h, Ax, b, z, l, v, y,
+                                                out.data()),
+                  "FBstabSparse::SolveBatch");
+    std::vector<SolverOut> res;
+    res.reserve(out.size());
+    for (const fbstab_out& r : out) res.push_back(detail::FromC(r));
+    return res;
+  }
+
   void UpdateOptions(const Options& options) {
     fbstab_options o = options.ToC();
     detail::Check(fbstab_sparse_batch_set_options(handle_.get(), &o),
@@ -164,6 +195,9 @@ class FBstabSparse {
   struct Destroy {
     void operator()(fbstab_sparse_batch* h) const { fbstab_sparse_batch_destroy(h); }
   };
+  struct DestroyMulti {
+    void operator()(fbstab_sparse_multi_gpu* h) const { fbstab_sparse_multi_gpu_destroy(h); }
+  };
   void Validate(const ProblemData& qp, const Variable& x) const {
     if (qp.Hx.size() != nnzH_ || qp.Gx.size() != nnzG_ || qp.Ax.size() != nnzA_ ||
         qp.f.size() != nz_ || qp.h.size() != nl_ || qp.b.size() != nv_)
@@ -174,6 +208,7 @@ class FBstabSparse {
           "In FBstabSparse::Solve: mismatch between *this and initial guess dimensions.");
   }
   int nz_ = 0, nl_ = 0, nv_ = 0, nnzH_ = 0, nnzG_ = 0, nnzA_ = 0;
+  SparsePattern H_, G_, A_;  // kept for the per-device handles of SolveBatch(..., devices)
   Options opts_;
   std::unique_ptr<fbstab_sparse_batch, Destroy> handle_;
 };

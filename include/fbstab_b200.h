@@ -35,6 +35,8 @@
  *   fbstab_sparse_batch_solve   <- FBstabAlgorithm::Solve over sparse data
  *                                  with QdldlWrapper::Factor / ::Solve
  *                                  (qdldl_wrapper.h:46-60; ROADMAP.md:10)
+ *   fbstab_sparse_analyze       <- the same symbolic analysis on the host only
+ *                                  (no handle, no device)
  *   fbstab_multi_gpu_*, fbstab_*_multi_gpu_solve
  *                               <- (none: the reference is single-threaded) the
  *                                  batch sharded by instance over the GPUs of a
@@ -446,6 +448,24 @@ int fbstab_mpc_multi_gpu_solve(fbstab_mpc_multi_gpu* handle, long batch,
                                const double* L, const double* d, const double* x0,
                                double* z, double* l, double* v, double* y,
                                fbstab_out* out);
+
+/* The same for sparse QPs with a common pattern (fbstab_sparse_batch_*): every device runs
+ * the same symbolic analysis (same elimination order), values and results are
+ * instance-major HOST arrays sharded by contiguous index range. */
+typedef struct fbstab_sparse_multi_gpu fbstab_sparse_multi_gpu;
+int fbstab_sparse_multi_gpu_create(int ndev, const int* devices, int nz, int nl, int nv,
+                                   const int* Hp, const int* Hi, const int* Gp,
+                                   const int* Gi, const int* Ap, const int* Ai,
+                                   const int* perm, long max_batch,
+                                   fbstab_sparse_multi_gpu** handle);
+int fbstab_sparse_multi_gpu_destroy(fbstab_sparse_multi_gpu* handle);
+int fbstab_sparse_multi_gpu_set_options(fbstab_sparse_multi_gpu* handle,
+                                        const fbstab_options* o);
+int fbstab_sparse_multi_gpu_solve(fbstab_sparse_multi_gpu* handle, long batch,
+                                  const double* Hx, const double* f, const double* Gx,
+                                  const double* h, const double* Ax, const double* b,
+                                  double* z, double* l, double* v, double* y,
+                                  fbstab_out* out);
 
 /* ---- synthetic problems (host code; mirrors fbstab/test/ocp_generator.h) - */
 #define FBSTAB_OCP_DOUBLE_INTEGRATOR 0 /* ocp_generator.cc:319-363 nx2 nu1 nc6  */

@@ -651,6 +651,45 @@ TEST(FBstabSparse, FeasibleQPwithEQ, true) {
   EXPECT_THROW(solver.Solve(qp, &bad), "initial guess");
 }
 
+// SolveBatch(..., devices) of the sparse facade: every visible GPU, host buffers, the same
+// bytes as the single-handle batch solve.
+TEST(FBstabSparse, SolveBatchOnAllDevices, true) {
+  MatrixXd H(2, 2), G(1, 2), A(2, 2);
+  H << 4, 1, 1, 2;
+  G << 1, 1;
+  A << -1, 0, 0, -1;
+  VectorXd Hx0, Gx0, Ax0;
+  const SparsePattern pH = CscOf(H, true, &Hx0), pG = CscOf(G, false, &Gx0),
+                      pA = CscOf(A, false, &Ax0);
+  const int B = 7, nH = (int)Hx0.size(), nG = (int)Gx0.size(), nA = (int)Ax0.size();
+  std::vector<double> Hx(B * nH), Gx(B * nG), Ax(B * nA), f(B * 2), h(B), b(B * 2, 0.0);
+  for (int i = 0; i < B; i++) {
+    for (int k = 0; k < nH; k++) Hx[i * nH + k] = Hx0(k) * (1.0 + 0.1 * i);
+    for (int k = 0; k < nG; k++) Gx[i * nG + k] = Gx0(k);
+    for (int k = 0; k < nA; k++) Ax[i * nA + k] = Ax0(k);
+    f[2 * i] = 1.0 - 0.2 * i;
+    f[2 * i + 1] = 1.0 + 0.3 * i;
+    h[i] = 1.0 + 0.05 * i;
+  }
+  FBstabSparse solver(pH, pG, pA, B);
+  std::vector<double> z(B * 2, 0.0), l(B, 0.0), v(B * 2, 0.0), y(B * 2, 0.0);
+  std::vector<SolverOut> one = solver.SolveBatch(B, Hx.data(), f.data(), Gx.data(), h.data(),
+                                                 Ax.data(), b.data(), z.data(), l.data(),
+                                                 v.data(), y.data());
+  std::vector<int> devices;
+  for (int d = 0; d < fbstab_device_count(); d++) devices.push_back(d);
+  std::vector<double> z2(B * 2, 0.0), l2(B, 0.0), v2(B * 2, 0.0), y2(B * 2, 0.0);
+  std::vector<SolverOut> all = solver.SolveBatch(B, Hx.data(), f.data(), Gx.data(), h.data(),
+                                                 Ax.data(), b.data(), z2.data(), l2.data(),
+                                                 v2.data(), y2.data(), devices);
+  for (int i = 0; i < B; i++) {
+    ASSERT_EQ(one[i].eflag, ExitFlag::SUCCESS);
+    ASSERT_EQ(all[i].eflag, one[i].eflag);
+    ASSERT_EQ(all[i].newton_iters, one[i].newton_iters);
+  }
+  EXPECT_TRUE(z == z2 && l == l2 && v == v2 && y == y2);
+}
+
 TEST(FBstabSparse, InfeasibleQP, true) {
   MatrixXd H(2, 2), G(0, 2), A(5, 2);
   H << 1, 0, 0, 0;

@@ -89,6 +89,21 @@ def main():
             out["newton_iters"] == o1["newton_iters"]).all()
         print(f"single-process solve on {nd} device(s): identical bytes = {same}", flush=True)
         ok = ok and same
+        # the sparse entry (fbstab_sparse_multi_gpu_solve): the servo OCP as general sparse QPs
+        Bs = 1003
+        dims, dm = fb.problems.ocp_batch("servo_motor", 20, count=Bs, config=3, rho=0.02)
+        (snz, snl, snv), pat, vals = fb.problems.ocp_as_sparse_qp(dims, dm, Bs)
+        ss = fb.FBstabSparse(snz, snl, snv, pat, max_batch=Bs, device=local)
+        z, l, v = np.zeros(Bs * snz), np.zeros(Bs * snl), np.zeros(Bs * snv)
+        out, y = ss.solve_batch_devices(vals, z, l, v, list(range(nd)))
+        z1, l1, v1 = np.zeros(Bs * snz), np.zeros(Bs * snl), np.zeros(Bs * snv)
+        o1, y1 = ss.solve_batch(vals, z1, l1, v1)
+        same = all(a.tobytes() == b.tobytes() for a, b in ((z, z1), (l, l1), (v, v1), (y, y1)))
+        same = same and (out["eflag"] == o1["eflag"]).all() and (
+            out["newton_iters"] == o1["newton_iters"]).all()
+        print(f"single-process sparse solve on {nd} device(s): identical bytes = {same}",
+              flush=True)
+        ok = ok and same
     mg.close()
     if world > 1:
         dist.destroy_process_group()

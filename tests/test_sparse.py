@@ -404,8 +404,35 @@ def test_sparse_gpu_on_ocps_matches_the_mpc_solver(fb, monkeypatch, kind, N, tea
     om, ym = m.solve_batch(d, zm, lm, vm)
     # (the perturbed initial states make some instances infeasible: both solvers say so)
     assert (out["eflag"] == om["eflag"]).all() and (out["eflag"] == 0).sum() >= B // 3
+    # two different linear solvers, each stopping at the absolute tolerance 1e-6 on its own
+    # trajectory: they agree like off-trajectory instances do (tests/golden/
+    # trajectory_floor.json: two builds of ONE solver differ by up to 3.6e-6 on the servo
+    # family, 3.5e-5 in the sparse form), not to 1e-8
+    tol = 1e-5
     for i in np.nonzero(out["eflag"] == 0)[0]:
-        assert rel_err(z[i * nz:(i + 1) * nz], zm[i * nz:(i + 1) * nz]) <= 1e-6
-        assert rel_err(l[i * nl:(i + 1) * nl], lm[i * nl:(i + 1) * nl]) <= 1e-6
-        assert rel_err(v[i * nv:(i + 1) * nv], vm[i * nv:(i + 1) * nv]) <= 1e-6
+        assert rel_err(z[i * nz:(i + 1) * nz], zm[i * nz:(i + 1) * nz]) <= tol
+        assert rel_err(l[i * nl:(i + 1) * nl], lm[i * nl:(i + 1) * nl]) <= tol
+        assert rel_err(v[i * nv:(i + 1) * nv], vm[i * nv:(i + 1) * nv]) <= tol
         assert out["residual"][i] <= 1e-6
+
+
+@pytest.mark.gpu
+def test_sparse_multi_device_solve_matches_one_handle(fb):
+    """fbstab_sparse_multi_gpu_solve over every visible device (host arrays, contiguous
+    instance ranges, the same elimination order on every device): the same bytes as one
+    handle on one device.  (On the one-GPU test box this is a single shard; the N-GPU run
+    is tests/multi_gpu_check.py.)"""
+    nz, nl, nv, B = 24, 4, 40, 203
+    rng = np.random.default_rng(7)
+    pat, vals, _ = random_sparse_qp(rng, nz, nl, nv, count=B)
+    s, out, z, l, v, y = _gpu_solve(fb, nz, nl, nv, pat, vals, B)
+    z2, l2, v2 = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+    devices = list(range(fb.capi.device_count()))
+    out2, y2 = s.solve_batch_devices(vals, z2, l2, v2, devices)
+    for a, b in ((z, z2), (l, l2), (v, v2), (y, y2)):
+        assert a.tobytes() == b.tobytes()
+    for f in ("eflag", "newton_iters", "prox_iters", "ls_backtracks", "status"):
+        assert (out[f] == out2[f]).all(), f
+    with pytest.raises(fb.FbstabError):
+        s.solve_batch_devices(vals, z2, l2, v2, [0, 0])  # duplicate device
+
