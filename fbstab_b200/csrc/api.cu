@@ -255,9 +255,57 @@ __device__ inline void SetupDenseT(const Args& a, int inst, double*& ws,
   p->tmp = Carve(ws, p->n);
   p->tz = Carve(ws, a.nz);
 }
+__host__ __device__ inline size_t DenseDataDoubles(int nz, int nl, int nv) {
+  return (size_t)nz * nz + (size_t)nl * nz + (size_t)nv * nz + (size_t)(nz + nl + nv);
+}
+// Generic dense kernel.  vec_in_smem >= 2: the linear solver's workspace (K and its
+// vectors) lives in the CTA's shared memory behind the iterates instead of the per-CTA
+// global workspace; == 3: the instance's H, G, A, f, h, b are staged there too, once per
+// instance.  Same code, same operation order -- only the address space changes, so the
+// results are bit-identical; what changes is that the dependent loads of the left-looking
+// LDL' and of the mat-vecs cost a shared-memory round trip instead of an L2 one (the
+// reference's own single-QP case, BASELINE config 1, is latency-bound on exactly those).
 __device__ inline void SetupDense(const DenseArgs& a, int inst, double*& ws,
                                   fbs::DenseProblem* p) {
-  SetupDenseT(a, inst, ws, p);
+  const int mode = a.c.vec_in_smem;
+  if (mode < 2) {
+    SetupDenseT(a, inst, ws, p);
+    return;
+  }
+  extern __shared__ double dyn_smem[];
+  double* sm = dyn_smem + VecDoubles(a.nz, a.nl, a.nv);
+  const int nz = a.nz, nl = a.nl, nv = a.nv;
+  p->nz = nz;
+  p->nl = nl;
+  p->nv = nv;
+  p->n = nz + nl;
+  p->K = Carve(sm, (size_t)p->n * p->n);
+  p->r1 = Carve(sm, p->n);
+  p->r2 = Carve(sm, nv);
+  p->gamma = Carve(sm, nv);
+  p->mus = Carve(sm, nv);
+  p->tmp = Carve(sm, p->n);
+  p->tz = Carve(sm, nz);
+  const double* src[6] = {a.H + (size_t)inst * nz * nz, a.f + (size_t)inst * nz,
+                          a.G + (size_t)inst * nl * nz, a.h + (size_t)inst * nl,
+                          a.A + (size_t)inst * nv * nz, a.b + (size_t)inst * nv};
+  if (mode >= 3) {
+    const size_t cnt[6] = {(size_t)nz * nz, (size_t)nz, (size_t)nl * nz, (size_t)nl,
+                           (size_t)nv * nz, (size_t)nv};
+    // (the loop-top barrier of PersistentLoop separates this from the previous instance)
+    for (int k = 0; k < 6; k++) {
+      double* dst = Carve(sm, cnt[k]);
+      for (size_t i = threadIdx.x; i < cnt[k]; i += blockDim.x) dst[i] = __ldg(src[k] + i);
+      src[k] = dst;
+    }
+    __syncthreads();
+  }
+  p->H = src[0];
+  p->f = src[1];
+  p->G = src[2];
+  p->h = src[3];
+  p->A = src[4];
+  p->bvec = src[5];
 }
 size_t DenseWsDoubles(int nz, int nl, int nv) {
   const size_t n = nz + nl;
@@ -780,6 +828,55 @@ int fbstab_validate_options(fbstab_options* o) {
 }
 
 // ---- dense -------------------------------------------------------------------
+// Shared-memory residency of the generic dense kernel (SetupDense).  Measured on the B200
+// (profiles/r2_dense_generic_resident.txt; every mode returns the same bytes): with the
+// data and the workspace resident a LONE instance is 10 % faster (BASELINE config 1,
+// 50/10/100: 2.43 -> 2.19 ms), but the larger footprint costs occupancy and a full batch
+// is 7-12 % slower; the workspace alone (mode 2) is +9 % on 40/0/80 and -30 % on
+// 96/16/180.  So: FBSTAB_DENSE_RESIDENT=-1 (default) takes mode 3 when the handle's
+// max_batch fits ONE wave of resident CTAs (the latency regime) and it fits shared memory,
+// the global workspace otherwise; 0 / 2 / 3 force a mode where it fits (A/B, tests).
+static int ConfigureDenseResident(HandleBase* h) {
+  int want = EnvInt("FBSTAB_DENSE_RESIDENT", -1);
+  const bool automatic = want < 0;
+  if (automatic) want = 3;
+  if (want < 2) return FBSTAB_OK;
+  int smem_optin = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin,
+                                  h->device));
+  cudaFuncAttributes fa;
+  CUDA_TRY(cudaFuncGetAttributes(&fa, (const void*)dense_generic_kernel));
+  const size_t room = (size_t)smem_optin - fa.sharedSizeBytes;
+  const size_t vec = VecDoubles(h->nz, h->nl, h->nv), ws = DenseWsDoubles(h->nz, h->nl, h->nv),
+               data = DenseDataDoubles(h->nz, h->nl, h->nv);
+  int mode = 0;
+  size_t bytes = 0;
+  if (want >= 3 && (vec + ws + data) * sizeof(double) <= room) {
+    mode = 3;
+    bytes = (vec + ws + data) * sizeof(double);
+  } else if ((vec + ws) * sizeof(double) <= room) {
+    mode = 2;
+    bytes = (vec + ws) * sizeof(double);
+  }
+  if (!mode) return FBSTAB_OK;
+  CUDA_TRY(cudaFuncSetAttribute((const void*)dense_generic_kernel,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)room));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &occ, (const void*)dense_generic_kernel, h->block, bytes));
+  if (occ < 1) return FBSTAB_OK;  // keep the global workspace
+  if (automatic && (mode != 3 || h->max_batch > h->sm_count * occ)) return FBSTAB_OK;
+  h->vec_in_smem = mode;
+  h->dyn_smem = bytes;
+  h->grid_max = std::max(1, std::min(h->grid_max, h->sm_count * occ));
+  h->path = mode == 3 ? "dense-generic-cta (CTA per instance, data and LDL' workspace "
+                        "resident in shared memory)"
+                      : "dense-generic-cta (CTA per instance, LDL' workspace in shared "
+                        "memory, data from L2)";
+  return FBSTAB_OK;
+}
+
 int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
                               fbstab_dense_batch** handle) {
   if (!handle) return Fail(FBSTAB_ERR_INVALID, "null handle pointer");
@@ -801,6 +898,7 @@ int fbstab_dense_batch_create(int nz, int nl, int nv, int max_batch, int device,
                             DenseWsDoubles(nz, nl, nv), fbs::dl::kThreads, kDenseLargeSmem)
                : InitCommon(h, device, max_batch, (const void*)dense_generic_kernel,
                             DenseWsDoubles(nz, nl, nv), block);
+  if (rc == FBSTAB_OK && !h->large) rc = ConfigureDenseResident(h);
   if (rc == FBSTAB_OK && !EnvInt("FBSTAB_FORCE_GENERIC", 0))
     rc = fbs::DenseSmallInit(&h->small, nz, nl, nv, h->sm_count, h->counter);
   if (rc) {

@@ -927,6 +927,31 @@ def test_dense_large_tma_equals_cp_async(fb, monkeypatch):
         assert np.array_equal(a, b_)
 
 
+@pytest.mark.parametrize("sizes,B,modes", [((50, 10, 100), 40, ("0", "2", "3")),
+                                           ((96, 16, 180), 6, ("0", "2")),
+                                           ((9, 3, 4), 7, ("0", "3"))])
+def test_dense_generic_resident_modes_are_bit_identical(fb, monkeypatch, sizes, B, modes):
+    """The generic CTA kernel with its LDL' workspace (and the instance's data) in shared
+    memory runs the same operations in the same order as with the global workspace: same
+    bytes out (FBSTAB_DENSE_RESIDENT, api.cu::SetupDense)."""
+    nz, nl, nv = sizes
+    monkeypatch.setenv("FBSTAB_FORCE_GENERIC", "1")  # (9, 3, 4) would take the warp kernel
+    d = fb.problems.random_dense_qp(nz, nl, nv, count=B, config=1)
+    res = []
+    for mode in modes:
+        monkeypatch.setenv("FBSTAB_DENSE_RESIDENT", mode)
+        s = fb.FBstabDense(nz, nl, nv, max_batch=B)
+        want = {"0": "generic", "2": "LDL' workspace in shared", "3": "data and LDL' workspace"}
+        assert want[mode] in s.path, (mode, s.path)
+        z, l, v = np.zeros(B * nz), np.zeros(B * nl), np.zeros(B * nv)
+        out, y = s.solve_batch(d, z, l, v)
+        assert (out["eflag"] == 0).all()
+        res.append((z, l, v, y, out["newton_iters"].copy(), out["ls_backtracks"].copy()))
+    for r in res[1:]:
+        for a, b_ in zip(res[0], r):
+            assert np.array_equal(a, b_)
+
+
 def test_device_pointers_and_stream(fb):
     """Device-resident buffers (torch CUDA tensors) are used in place and the
     call is asynchronous on the given stream; results equal the host path."""
