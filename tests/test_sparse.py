@@ -239,6 +239,32 @@ def test_sparse_pattern_validation_and_no_cpu_fallback(fb):
 
 
 # ---- GPU: the lane-per-instance CUDA path against the oracle ---------------------------
+def test_sparse_analyze_runs_on_the_host(fb, oracle):
+    """fbstab_sparse_analyze: the handle's symbolic analysis without a handle or a device --
+    a valid elimination order of [z; l; w], the fill it implies, the caller's order kept,
+    bad patterns rejected; the oracle solves in that order."""
+    nz, nl, nv, B = 24, 4, 40, 3
+    rng = np.random.default_rng(3)
+    pat, vals, _ = random_sparse_qp(rng, nz, nl, nv, count=B)
+    n, nnzK, nnzL, perm = fb.FBstabSparse.analyze(nz, nl, nv, pat)
+    assert n == nz + nl + nv and sorted(perm.tolist()) == list(range(n))
+    assert nnzK >= n and nnzL > 0
+    # the natural order [w; z; l] fills at least as much as the minimum-degree order
+    natural = np.concatenate([nz + nl + np.arange(nv), np.arange(nz), nz + np.arange(nl)])
+    n2, k2, l2, p2 = fb.FBstabSparse.analyze(nz, nl, nv, pat, perm=natural)
+    assert (p2 == natural).all() and k2 == nnzK and l2 >= nnzL
+    V = [vals[k] for k in ("Hx", "f", "Gx", "h", "Ax", "b")]
+    oa = oracle.sparse_solve_batch(nz, nl, nv, pat, V, perm=perm)
+    ob_ = oracle.sparse_solve_batch(nz, nl, nv, pat, V, perm=natural)
+    assert (oa[0]["eflag"] == 0).all() and (ob_[0]["eflag"] == 0).all()
+    assert rel_err(oa[1], ob_[1]) <= 1e-7
+    Hp, Hi, Gp, Gi, Ap, Ai = pat
+    with pytest.raises(fb.FbstabError):
+        fb.FBstabSparse.analyze(nz, nl, nv, (Hp, Hi[::-1].copy(), Gp, Gi, Ap, Ai))
+    with pytest.raises(fb.FbstabError):
+        fb.FBstabSparse.analyze(nz, nl, nv, pat, perm=np.zeros(n, np.int32))
+
+
 def _gpu_solve(fb, nz, nl, nv, pat, vals, B, opts=None, perm=None, x0=None):
     s = fb.FBstabSparse(nz, nl, nv, pat, max_batch=B, perm=perm)
     if opts is not None:
