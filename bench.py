@@ -259,6 +259,48 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def gpu_local_cpus(torch, dev_index):
+    """The CPUs NVML names as local to this GPU, within the set this process may run on
+    (None when unknown or when that is every allowed CPU).  Pinned host buffers are
+    allocated from a thread confined to them, so that first touch puts the pages on the
+    GPU's NUMA node: on a two-socket box the H2D copies of the e2e leg otherwise cross the
+    socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(dev_index)
+        bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        local = cpus & allowed
+        return local if local and local != allowed else None
+    except Exception:
+        return None
+
+
+class on_cpus:
+    """Runs the calling thread on `cpus` for the duration of the block (no-op for None)."""
+
+    def __init__(self, cpus):
+        self.cpus, self.prev = cpus, None
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.prev = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+            except Exception:
+                self.prev = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            os.sched_setaffinity(0, self.prev)
+        return False
+
+
 def csrc_hash():
     """SHA-256 over the kernel sources: profiles/traffic.json is tied to a build."""
     h = hashlib.sha256()
@@ -442,7 +484,12 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
     threads = max(1, host_threads() // max(world, 1))
     nz, nl, nv = wl.nz, wl.nl, wl.nv
     t_gen = time.perf_counter()
-    pin = lambda n: torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True).numpy()[:n]
+    local_cpus = env.get("local_cpus")
+
+    def pin(n):  # pinned, first touched from a CPU next to this rank's GPU
+        with on_cpus(local_cpus):
+            return torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True).numpy()[:n]
+
     d_host = wl.generate(fb.problems, B, first, threads, alloc=pin)
     d_dev = {k: torch.from_numpy(a).to(dev) for k, a in d_host.items()}
     t_gen = time.perf_counter() - t_gen
@@ -580,8 +627,9 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
     if with_e2e and B:
         Ke = max(1, min(K, 3))
         yh = pin(B * nv)
-        oh = np.frombuffer(torch.empty(B * fb.OUT_DTYPE.itemsize, dtype=torch.uint8,
-                                       pin_memory=True).numpy(), dtype=fb.OUT_DTYPE)
+        with on_cpus(local_cpus):
+            oh = np.frombuffer(torch.empty(B * fb.OUT_DTYPE.itemsize, dtype=torch.uint8,
+                                           pin_memory=True).numpy(), dtype=fb.OUT_DTYPE)
         warm = []
         for _ in range(Ke + 1):
             bufs = (pin(B * nz), pin(B * nl), pin(B * nv))
@@ -624,6 +672,9 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
             dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         agg = world * 2 * d_host[big].nbytes / float(tb.item()) / 1e9
         res["e2e"]["host_h2d_aggregate_gbs"] = agg
+        res["e2e"]["pinned_buffers"] = (
+            f"first touched on the {len(local_cpus)} CPUs NVML names as local to the GPU"
+            if local_cpus else "default placement (GPU-local CPUs unknown or all of them)")
         res["e2e"]["host_ceiling"] = global_batch / (h2d / (agg / world * 1e9))
         if wl.kind == "mpc":
             # the same solve with ONE copy of the stage data (fbstab_mpc_batch_solve_shared):
@@ -768,6 +819,7 @@ def main():
         pass
     env = {"torch": torch, "dist": dist, "fb": fb, "mg": mg, "rank": rank, "world": world,
            "local_rank": local_rank, "dev": dev, "peaks": fb.capi.fp64_peak(local_rank),
+           "local_cpus": gpu_local_cpus(torch, local_rank),
            "hbm_peak": hbm_peak, "hbm_src": hbm_src}
     W = max(args.warmup, 3)
     K = args.steps
