@@ -40,3 +40,20 @@ def test_product_arm_has_no_cpu_fallback():
     assert r.returncode != 0
     assert r.stdout.strip() == ""
     assert "no CUDA device" in r.stderr
+
+
+def test_pinned_allocation_affinity_helper_restores_the_thread():
+    """bench.py's on_cpus: a no-op for None, confines the calling thread for the block and
+    puts the previous affinity back; gpu_local_cpus never raises without NVML / a GPU."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import torch
+    before = os.sched_getaffinity(0)
+    with bench.on_cpus(None):
+        assert os.sched_getaffinity(0) == before
+    one = {sorted(before)[0]}
+    with bench.on_cpus(one):
+        assert os.sched_getaffinity(0) == one
+    assert os.sched_getaffinity(0) == before
+    if not torch.cuda.is_available():
+        assert bench.gpu_local_cpus(torch, 0) is None
