@@ -341,6 +341,38 @@ def cpu_reference_run(wl, count, threads, first=0):
     return count / dt, dt, out, z
 
 
+def reference_sources_check(wl, count, threads, first, co):
+    """The checker checked: on a prefix of the oracle's sample, the reference's OWN sources
+    (oracle/_ref/libfbstab_ref.so: the reference's algorithm code compiled against a stand-in
+    for Eigen, `make -C oracle _ref`; a prebuilt file on the GPU box) must end every instance
+    with the oracle's exit flag and iteration counts.  None when the library is not there;
+    never raises (the bench line does not depend on it)."""
+    try:
+        import fbstab_b200.problems as problems
+        from oracle import binding as ob
+        if wl.kind == "sparse" or ob.ref_lib() is None:
+            return None
+        n = min(count, 4 if wl.name == "5" else 256 if wl.kind == "dense" else 128)
+        d = wl.generate(problems, n, first, threads)
+        if wl.kind == "dense":
+            ro = ob.ref_dense_solve_batch(wl.nz, wl.nl, wl.nv,
+                                          *[d[k] for k in problems.DENSE_FIELDS],
+                                          nthreads=threads)[0]
+        else:
+            ro = ob.ref_mpc_solve_batch(wl.N, wl.nx, wl.nu, wl.nc,
+                                        [d[k] for k in problems.MPC_FIELDS],
+                                        nthreads=threads)[0]
+        o = co[:n]
+        same = ((ro["eflag"] == o["eflag"]) & (ro["newton_iters"] == o["newton_iters"]) &
+                (ro["prox_iters"] == o["prox_iters"]))
+        return {"instances": int(n), "same_flags": bool((ro["eflag"] == o["eflag"]).all()),
+                "same_trajectory_frac": float(same.mean()),
+                "what": "oracle (the CPU baseline and parity checker) against the reference's "
+                        "own algorithm sources compiled on a stand-in for Eigen (oracle/_ref)"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
 def cpu_latency_config1(repeats=101):
     """BASELINE config 1: ONE dense QP nz=50 nl=10 nv=100 on the CPU (the reference's own
     runnable case): median wall time of `repeats` cold-start solves of the restated
@@ -734,6 +766,7 @@ def measure(env, wl, K, W, scaling, with_cpu, with_e2e=True):
                          f"{cdt:.1f} s on {cores} host threads (one solver per thread)",
                "note": "restated reference (oracle/): Eigen is not in this image"}
         cpu.update(par)
+        cpu["oracle_vs_reference_sources"] = reference_sources_check(wl, count, cores, first, co)
         # the oracle's counters where it was run: wasted GPU work earns no credit
         for k, f in enumerate(("newton_iters", "prox_iters", "ls_backtracks")):
             W_counters[k][:count] = co[f]

@@ -352,6 +352,75 @@ def mpc_solve_batch(N, nx, nu, nc, seqs, opts=None, x0=None, nthreads=1, fma=Fal
     return out, z, l, v, y
 
 
+# ---- the reference's own sources (oracle/_ref, `make -C oracle _ref`) ---------------------
+# libfbstab_ref.so = the reference's unmodified algorithm sources compiled against
+# oracle/eigen_shim (Eigen itself is not in this image); built only where /root/reference
+# exists, shipped to the GPU box as a prebuilt file.  Used by tests to pin the oracle's
+# TRAJECTORY to the reference's own code, never by the product.
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libfbstab_ref.so")
+_ref_lib = None
+
+
+def build_ref(reference="/root/reference"):
+    """Builds oracle/_ref/libfbstab_ref.so when the reference tree is present; returns the
+    path, or None when there is neither a tree nor a prebuilt library."""
+    if os.path.isdir(os.path.join(reference, "fbstab", "components")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "_ref", "REF=" + reference])
+    return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
+
+
+def ref_lib():
+    """The reference-sources library, or None when it is not available."""
+    global _ref_lib
+    if _ref_lib is None:
+        if not os.path.exists(_REF_LIB_PATH) and build_ref() is None:
+            return None
+        L = C.CDLL(_REF_LIB_PATH)
+        L.ref_dense_solve_batch.argtypes = (
+            [C.c_int] * 4 + [_dp] * 10 + [C.POINTER(Options), C.c_void_p, C.c_int])
+        L.ref_mpc_solve_batch.argtypes = (
+            [C.c_int] * 5 + [_dp] * 16 + [C.POINTER(Options), C.c_void_p, C.c_int])
+        _ref_lib = L
+    return _ref_lib
+
+
+def ref_dense_solve_batch(nz, nl, nv, H, f, G, h, A, b, opts=None, x0=None, nthreads=1):
+    """FBstabDense::Solve of the reference's own sources on every instance of the batch;
+    same arguments and results as dense_solve_batch (ls_backtracks / residual_evals = -1:
+    the reference does not count them)."""
+    if opts is None:
+        opts = default_options()
+    batch = f.size // nz
+    if x0 is None:
+        z, l, v = np.zeros(batch * nz), np.zeros(batch * nl), np.zeros(batch * nv)
+    else:
+        z, l, v = [np.ascontiguousarray(t, dtype=np.float64).reshape(-1).copy() for t in x0]
+    y = np.zeros(batch * nv)
+    out = np.zeros(batch, dtype=OUT_DTYPE)
+    ref_lib().ref_dense_solve_batch(
+        nz, nl, nv, batch, _p(H), _p(f), _p(G), _p(h), _p(A), _p(b), _p(z), _p(l), _p(v),
+        _p(y), C.byref(opts), out.ctypes.data, nthreads)
+    return out, z, l, v, y
+
+
+def ref_mpc_solve_batch(N, nx, nu, nc, seqs, opts=None, x0=None, nthreads=1):
+    """FBstabMpc::Solve of the reference's own sources; arguments as mpc_solve_batch."""
+    if opts is None:
+        opts = default_options()
+    nz, nl, nv = (N + 1) * (nx + nu), (N + 1) * nx, (N + 1) * nc
+    batch = seqs[-1].size // nx
+    if x0 is None:
+        z, l, v = np.zeros(batch * nz), np.zeros(batch * nl), np.zeros(batch * nv)
+    else:
+        z, l, v = [np.ascontiguousarray(t, dtype=np.float64).reshape(-1).copy() for t in x0]
+    y = np.zeros(batch * nv)
+    out = np.zeros(batch, dtype=OUT_DTYPE)
+    ref_lib().ref_mpc_solve_batch(
+        N, nx, nu, nc, batch, *[_p(a) for a in seqs], _p(z), _p(l), _p(v), _p(y),
+        C.byref(opts), out.ctypes.data, nthreads)
+    return out, z, l, v, y
+
+
 def qdldl_solve(n, Ap, Ai, Ax, b):
     """QdldlWrapper: factor the upper-triangular CSC matrix, solve A x = b."""
     Ap, Ai = [np.ascontiguousarray(np.asarray(a, dtype=np.int32)) for a in (Ap, Ai)]

@@ -10,8 +10,16 @@
 // therefore pinned against every golden vector the reference's own tests hold
 // for this path (tests/test_oracle_goldens.py lists them with file:line).
 // Those tests pin exit flags, solutions and component values; they do NOT pin
-// iteration counts, so the *trajectory* (newton/prox counts, step sizes) is
-// pinned only by this restatement: "trajectory parity unpinned vs real Eigen".
+// iteration counts.  The *trajectory* (newton / prox counts) is pinned by the
+// reference's OWN algorithm sources, compiled where they lie under
+// /root/reference against a stand-in for the Eigen API they use
+// (oracle/_ref/libfbstab_ref.so: `make -C oracle _ref`, ref_wrapper.cpp,
+// eigen_shim/Eigen/Dense): tests/test_reference_sources.py holds this restatement
+// to the same exit flag and iteration counts on every instance of every benchmark
+// family, and to the same BYTES on the MPC path.  What remains unpinned is only
+// Eigen's own rounding (its blocked, packetised sums): two correctly rounded
+// evaluations of the same formulas, like this file built with and without FMA
+// contraction (tests/golden/trajectory_floor.json).
 //
 // Eigen arithmetic that is not in /root/reference is restated from its
 // published algorithm (Eigen 3.4.0): LDLT = in-place unblocked LDL' of the

@@ -7,6 +7,13 @@
  * reference legs may load it.  Nothing under fbstab_b200/ links, imports or
  * calls it.
  *
+ * Pinned (a) by every golden vector of the reference's own tests
+ * (tests/test_oracle_goldens.py) and (b) by the reference's OWN algorithm sources
+ * compiled here against a stand-in for Eigen (oracle/_ref, `make -C oracle _ref`,
+ * ref_wrapper.cpp, eigen_shim/): same exit flags and iteration counts on every
+ * instance of every benchmark family, the same bytes on the MPC path
+ * (tests/test_reference_sources.py).
+ *
  * Layout conventions are the reference's: dense matrices column-major
  * (Eigen default), MPC sequences `len x rows x cols` contiguous with each
  * matrix column-major (reference tools/matrix_sequence.h:81-83).
