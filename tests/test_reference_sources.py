@@ -86,6 +86,9 @@ def test_reference_sources_pass_the_mpc_solver_tests(ref, fb, kind, N):
 @pytest.mark.parametrize("kind,N,B,rho,cfg", [("servo_motor", 50, 512, 0.02, 3),
                                               ("double_integrator", 50, 512, -0.1, 3),
                                               ("spacecraft", 40, 48, 0.01, 4),
+                                              # (N = 100: the reference's code, too, stops at
+                                              # MAXITERATIONS after 200 Newton steps)
+                                              ("spacecraft", 100, 8, 0.01, 4),
                                               ("copolymerization", 100, 32, 0.05, 4)])
 def test_oracle_is_the_reference_code_on_the_mpc_families(ref, fb, kind, N, B, rho, cfg):
     """Same instances as bench.py's configs 3a, 3b, 4a40, 4b (prefixes): identical exit
@@ -104,9 +107,9 @@ def test_oracle_is_the_reference_code_on_the_mpc_families(ref, fb, kind, N, B, r
 
 
 @pytest.mark.parametrize("sizes,B,cfg", [((32, 8, 64), 512, 2), ((50, 10, 100), 96, 1),
-                                         ((9, 3, 4), 64, 2)])
+                                         ((9, 3, 4), 64, 2), ((512, 128, 1024), 2, 5)])
 def test_oracle_follows_the_reference_code_on_dense_qps(ref, fb, sizes, B, cfg):
-    """bench.py's configs 2 and 1 (prefixes): same flags and iteration counts on every
+    """bench.py's configs 2, 1 and 5 (prefixes): same flags and iteration counts on every
     instance, solutions within 1e-8 (the pivoted LDL' of the stand-in and the oracle's
     restatement of Eigen's differ in the order of a few sums)."""
     nz, nl, nv = sizes
