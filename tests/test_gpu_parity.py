@@ -952,6 +952,43 @@ def test_dense_generic_resident_modes_are_bit_identical(fb, monkeypatch, sizes, 
             assert np.array_equal(a, b_)
 
 
+@pytest.mark.parametrize("name", ["dense_32_8_64", "dense_50_10_100", "servo_motor_N50",
+                                  "double_integrator_N50", "spacecraft_N40",
+                                  "copolymerization_N100", "servo_motor_N25_mixed"])
+def test_gpu_walks_the_trajectories_of_the_reference_code(fb, name):
+    """The CUDA engine against tests/golden/reference_trajectories.json: the exit flag and
+    the Newton / proximal iteration counts that the REFERENCE'S OWN CODE (oracle/_ref: its
+    unmodified algorithm sources on a stand-in for Eigen; the fixture is committed, so this
+    runs on a box without the reference) produced for the first instances of every bench
+    family.  Exit flags must be identical on every instance; iteration counts identical on
+    the fraction the family's measured rounding floor allows (100 % everywhere but the servo
+    problem)."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location(
+        "make_reference_trajectories",
+        os.path.join(here, "golden", "make_reference_trajectories.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(here, "golden", "reference_trajectories.json")) as fh:
+        rec = json.load(fh)["families"][name]
+    kind, dims, d = mod.family_data(fb, name)
+    B = rec["instances"]
+    s = fb.FBstabDense(*dims, max_batch=B) if kind == "dense" else fb.FBstabMpc(*dims, max_batch=B)
+    z, l, v = np.zeros(B * s.nz), np.zeros(B * s.nl), np.zeros(B * s.nv)
+    out, y = s.solve_batch(d, z, l, v)
+    assert (out["status"] == 0).all()
+    assert out["eflag"].tolist() == rec["eflag"], "exit flags differ from the reference's code"
+    same = (out["newton_iters"] == np.array(rec["newton_iters"])) & \
+        (out["prox_iters"] == np.array(rec["prox_iters"]))
+    family = "servo_motor_N50" if name.startswith("servo_motor") else name
+    assert same.mean() >= required_same_frac(family, B), \
+        f"{(~same).sum()} of {B} instances leave the reference code's trajectory"
+    assert np.abs(out["newton_iters"] - np.array(rec["newton_iters"])).max() <= 2
+
+
 def test_device_pointers_and_stream(fb):
     """Device-resident buffers (torch CUDA tensors) are used in place and the
     call is asynchronous on the given stream; results equal the host path."""

@@ -136,3 +136,35 @@ def test_mixed_exit_flags_and_options_follow_the_reference_code(ref, fb):
         assert (ro["eflag"] == oo["eflag"]).all()
         assert _same(ro, oo).all()
     assert len(np.unique(ro["eflag"])) >= 2, "the batch should mix exit flags"
+
+
+# ---- the committed fixture: what the reference's code did, instance by instance ----------
+def _fixture():
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location(
+        "make_reference_trajectories", os.path.join(here, "golden", "make_reference_trajectories.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(here, "golden", "reference_trajectories.json")) as fh:
+        return mod, json.load(fh)["families"]
+
+
+@pytest.mark.parametrize("which", ["oracle", "ref"])
+def test_committed_reference_trajectories(oracle, fb, which):
+    """tests/golden/reference_trajectories.json (exit flag, Newton and proximal counts of the
+    reference's own code on the first instances of every family) is reproduced by the
+    reference's code where it is available, and by the oracle everywhere: the GPU parity
+    tests may use the fixture as the reference's word."""
+    mod, fam = _fixture()
+    if which == "ref" and oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref/libfbstab_ref.so is not available")
+    assert set(fam) == set(mod.FAMILIES)
+    for name, rec in fam.items():
+        out = mod.solve(oracle, fb, name, which)[0]
+        assert out.size == rec["instances"]
+        for f in ("eflag", "newton_iters", "prox_iters"):
+            assert out[f].tolist() == rec[f], (name, f)
+    assert len(set(fam["servo_motor_N25_mixed"]["eflag"])) >= 2
