@@ -369,6 +369,19 @@ def build_ref(reference="/root/reference"):
     return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
 
 
+_REF_TESTS_PATH = os.path.join(_HERE, "_ref", "ref_unit_tests")
+
+
+def build_ref_tests(reference="/root/reference"):
+    """Builds oracle/_ref/ref_unit_tests -- the reference's own live unit tests
+    (fbstab/test/*_unit_tests.cc), unmodified, on its own code, against eigen_shim/ and
+    gtest_shim/ -- where the reference tree is present; returns the path of the binary, or
+    None when there is neither a tree nor a prebuilt binary."""
+    if os.path.isdir(os.path.join(reference, "fbstab", "test")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "_ref_tests", "REF=" + reference])
+    return _REF_TESTS_PATH if os.path.exists(_REF_TESTS_PATH) else None
+
+
 def ref_lib():
     """The reference-sources library, or None when it is not available."""
     global _ref_lib
@@ -382,6 +395,28 @@ def ref_lib():
             [C.c_int] * 5 + [_dp] * 16 + [C.POINTER(Options), C.c_void_p, C.c_int])
         _ref_lib = L
     return _ref_lib
+
+
+def ref_ocp_generate(kind, N):
+    """The reference's own OcpGenerator (fbstab/test/ocp_generator.cc) at horizon N:
+    kind 0 DoubleIntegrator, 1 ServoMotor, 2 SpacecraftRelativeMotion,
+    3 CopolymerizationReactor.  Returns ((N, nx, nu, nc), {field: flat array}) in the wire
+    format of fbstab_b200.problems.ocp_batch."""
+    L = ref_lib()
+    ip = C.POINTER(C.c_int)
+    L.ref_ocp_generate.argtypes = [C.c_int, C.c_int, ip] + [_dp] * 12
+    sizes = (C.c_int * 3)()
+    if L.ref_ocp_generate(kind, N, sizes, *([None] * 12)) != 0:
+        raise RuntimeError("ref_ocp_generate failed")
+    nx, nu, nc = sizes[0], sizes[1], sizes[2]
+    shp = {"Q": (N + 1) * nx * nx, "R": (N + 1) * nu * nu, "S": (N + 1) * nu * nx,
+           "q": (N + 1) * nx, "r": (N + 1) * nu, "A": N * nx * nx, "B": N * nx * nu,
+           "c": N * nx, "E": (N + 1) * nc * nx, "L": (N + 1) * nc * nu, "d": (N + 1) * nc,
+           "x0": nx}
+    d = {k: np.zeros(n) for k, n in shp.items()}
+    if L.ref_ocp_generate(kind, N, None, *[_p(d[k]) for k in shp]) != 0:
+        raise RuntimeError("ref_ocp_generate failed")
+    return (N, nx, nu, nc), d
 
 
 def ref_dense_solve_batch(nz, nl, nv, H, f, G, h, A, b, opts=None, x0=None, nthreads=1):

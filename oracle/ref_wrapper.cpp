@@ -19,6 +19,7 @@
 
 #include "fbstab/fbstab_dense.h"
 #include "fbstab/fbstab_mpc.h"
+#include "fbstab/test/ocp_generator.h"
 #include "fbstab_oracle.h"
 #include "tools/matrix_sequence.h"
 
@@ -171,6 +172,39 @@ int ref_mpc_solve_batch(int N, int nx, int nu, int nc, int batch, const double* 
     }
   });
   return 0;
+}
+
+// The reference's own OCP generator (fbstab/test/ocp_generator.cc:73-421): the eleven
+// sequences and x0 of kind 0 DoubleIntegrator, 1 ServoMotor, 2 SpacecraftRelativeMotion,
+// 3 CopolymerizationReactor at horizon N, in the wire format -- the cross-check of the
+// engine's restated generator (fbstab_b200/csrc/problems.cpp, fbstab_ocp_generate).
+// sizes (may be NULL): nx, nu, nc.  Any output pointer may be NULL.
+int ref_ocp_generate(int kind, int N, int* sizes, double* Q, double* R, double* S, double* q,
+                     double* r, double* A, double* B, double* c, double* E, double* L, double* d,
+                     double* x0) {
+  try {
+    fbstab::test::OcpGenerator g;
+    if (kind == 0) g.DoubleIntegrator(N);
+    else if (kind == 1) g.ServoMotor(N);
+    else if (kind == 2) g.SpacecraftRelativeMotion(N);
+    else if (kind == 3) g.CopolymerizationReactor(N);
+    else return 1;
+    const fbstab::FBstabMpc::ProblemDataRef p = g.GetFBstabInputRef();
+    if (sizes) {
+      sizes[0] = p.Q.rows();
+      sizes[1] = p.R.rows();
+      sizes[2] = p.E.rows();
+    }
+    const fbstab::MapMatrixSequence* seq[11] = {&p.Q, &p.R, &p.S, &p.q, &p.r, &p.A,
+                                                &p.B, &p.c, &p.E, &p.L, &p.d};
+    double* dst[11] = {Q, R, S, q, r, A, B, c, E, L, d};
+    for (int k = 0; k < 11; k++)
+      if (dst[k]) std::copy(seq[k]->data(), seq[k]->data() + seq[k]->size(), dst[k]);
+    if (x0) std::copy(p.x0.data(), p.x0.data() + p.x0.size(), x0);
+    return 0;
+  } catch (const std::exception&) {
+    return 2;
+  }
 }
 
 }  // extern "C"

@@ -168,3 +168,43 @@ def test_committed_reference_trajectories(oracle, fb, which):
         for f in ("eflag", "newton_iters", "prox_iters"):
             assert out[f].tolist() == rec[f], (name, f)
     assert len(set(fam["servo_motor_N25_mixed"]["eflag"])) >= 2
+
+
+# ---- the reference's own unit tests and its own problem generator ------------------------
+def test_the_reference_unit_tests_pass_on_the_reference_code(oracle):
+    """fbstab/test/fbstab_dense_unit_tests.cc and fbstab_mpc_unit_tests.cc -- the ten live
+    tests of the reference, compiled UNMODIFIED together with its ocp_generator.cc and its
+    algorithm sources against oracle/eigen_shim and oracle/gtest_shim (`make -C oracle
+    _ref_tests`): all pass.  This is what qualifies the stand-in linear algebra."""
+    import subprocess
+    binary = oracle.build_ref_tests()
+    if binary is None:
+        pytest.skip("oracle/_ref/ref_unit_tests: no reference tree and no prebuilt binary")
+    p = subprocess.run([binary], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert "10 tests, 0 failed" in p.stdout, p.stdout[-3000:]
+    for name in ("FBstabDense.FeasibleQP", "FBstabDense.InfeasibleQP", "FBstabDense.UnboundedQP",
+                 "FBstabMpc.DoubleIntegrator", "FBstabMpc.CopolymerizationReactor"):
+        assert "[  OK  ] " + name in p.stdout
+
+
+@pytest.mark.parametrize("kind,name,N", [(0, "double_integrator", 10), (0, "double_integrator", 2),
+                                         (1, "servo_motor", 20), (1, "servo_motor", 50),
+                                         (2, "spacecraft", 40), (3, "copolymerization", 70),
+                                         (3, "copolymerization", 100)])
+def test_the_engines_ocp_generator_is_the_reference_generator(ref, fb, kind, name, N):
+    """fbstab_ocp_generate (fbstab_b200/csrc/problems.cpp, the restated constant tables of
+    fbstab/test/ocp_generator.cc:73-421) returns the BYTES the reference's own OcpGenerator
+    produces: all eleven sequences and x0, every problem, any horizon.  (Exact equality of
+    every value; the only byte that may differ is the sign bit of a zero, -Q xtrg = -0.0 in
+    the reference's q where the restated table holds +0.0.)"""
+    dims, d = ref.ref_ocp_generate(kind, N)
+    dims2, d2 = fb.problems.ocp_batch(name, N)
+    assert tuple(dims) == tuple(dims2)
+    for k in fb.problems.MPC_FIELDS:
+        a, b = d[k], np.ascontiguousarray(d2[k]).reshape(-1)
+        assert a.shape == b.shape and np.array_equal(a, b), k
+        diff = a.tobytes() != b.tobytes()
+        if diff:
+            assert ((a == 0) | (a.view(np.int64) == b.view(np.int64))).all(), k
+
