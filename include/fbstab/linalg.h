@@ -31,6 +31,9 @@
 
 namespace Eigen {
 
+class MatrixXd;
+class VectorXd;
+
 namespace shim {
 
 // Row-by-row comma initialiser: `M << 1, 2, 3, 4;`
@@ -71,6 +74,11 @@ class Base {
     for (long i = 0; i < size(); i++) s += data()[i] * data()[i];
     return std::sqrt(s);
   }
+  // What the reference's tests compute from a solution (the KKT check of
+  // fbstab_dense_unit_tests.cc:173-174: H z + f + A' v and min(y, v)); defined below.
+  MatrixXd transpose() const;
+  template <class D2, class S2>
+  VectorXd cwiseMin(const Base<D2, S2>& o) const;
   template <class S = Scalar,
             class = typename std::enable_if<!std::is_const<S>::value>::type>
   void fill(double a) const {
@@ -209,6 +217,39 @@ class Map<const VectorXd> : public shim::Base<Map<const VectorXd>, const double>
   const double* p_;
   long n_;
 };
+
+namespace shim {
+template <class D, class S>
+MatrixXd Base<D, S>::transpose() const {
+  MatrixXd t(cols(), rows());
+  for (long j = 0; j < cols(); j++)
+    for (long i = 0; i < rows(); i++) t(j, i) = coeffRef(i, j);
+  return t;
+}
+template <class D, class S>
+template <class D2, class S2>
+VectorXd Base<D, S>::cwiseMin(const Base<D2, S2>& o) const {
+  VectorXd m(size());
+  for (long i = 0; i < size(); i++) m(i) = data()[i] < o.data()[i] ? data()[i] : o.data()[i];
+  return m;
+}
+// matrix * vector and vector + vector (column vectors: the right operand has one column)
+template <class D1, class S1, class D2, class S2>
+VectorXd operator*(const Base<D1, S1>& a, const Base<D2, S2>& x) {
+  if (a.cols() != x.rows() || x.cols() != 1) throw std::invalid_argument("size mismatch in product");
+  VectorXd y(a.rows());
+  for (long j = 0; j < a.cols(); j++)
+    for (long i = 0; i < a.rows(); i++) y(i) += a.coeffRef(i, j) * x.data()[j];
+  return y;
+}
+template <class D1, class S1, class D2, class S2>
+VectorXd operator+(const Base<D1, S1>& a, const Base<D2, S2>& b) {
+  if (a.size() != b.size()) throw std::invalid_argument("size mismatch in sum");
+  VectorXd y(a.size());
+  for (long i = 0; i < a.size(); i++) y(i) = a.data()[i] + b.data()[i];
+  return y;
+}
+}  // namespace shim
 
 }  // namespace Eigen
 
