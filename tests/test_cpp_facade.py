@@ -99,3 +99,21 @@ def test_the_references_own_unit_tests_pass_on_the_engine():
     p = subprocess.run([binary], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:]
     assert "10 tests, 0 failed" in p.stdout
+
+
+def test_facade_compiles_in_its_eigen_branch():
+    """With an <Eigen/Dense> on the include path the facade takes its FBSTAB_HAVE_EIGEN branch
+    (Eigen's own types instead of the stand-ins of linalg.h).  Eigen is not installed here;
+    oracle/eigen_shim provides the header, which is enough to compile that branch -- the
+    facade's own tests and, where the reference tree exists, the reference's unit tests."""
+    srcs = [os.path.join(ROOT, "tests", "cpp", "facade_tests.cc")]
+    ref = [os.path.join(REFERENCE, "fbstab", "test", f)
+           for f in ("fbstab_dense_unit_tests.cc", "fbstab_mpc_unit_tests.cc")]
+    if all(os.path.exists(t) for t in ref):
+        srcs += ref
+    for src in srcs:
+        subprocess.check_call(
+            ["g++", "-std=c++14", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"),
+             "-I" + os.path.join(ROOT, "oracle", "eigen_shim"),
+             "-I" + os.path.join(ROOT, "tests", "cpp", "ref_compat"),
+             "-I" + os.path.join(ROOT, "oracle", "gtest_shim"), src])
